@@ -1,0 +1,183 @@
+/*
+ * ugeval.h — C ABI of libugeval.so, the B200-native (sm_100a) replacement for UnrealGo's batched
+ * network-evaluation path.  Plain pointers and sizes only; no TensorFlow, torch or C++ types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the reference tree).
+ * Conventions: functions returning int give 0 on success, >0 for the reference's "returns false",
+ * <0 where the reference would throw (std::runtime_error); ug_last_error() holds the message.
+ * Exactly one thread may drive an evaluator handle at a time (same contract as the reference: only
+ * UctSearch::NetworkEvalThread touches the evaluator, search/UctSearch.cpp:164-205); the leaf queue
+ * (ug_queue_*) is the multi-producer entry.
+ */
+#ifndef UGEVAL_H
+#define UGEVAL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UG_BOARD_SIZE 19          /* GO_MAX_SIZE,      config/BoardStaticConfig.h:11-15 */
+#define UG_NUM_POINTS 361         /* GO_MAX_ONBOARD,   config/BoardStaticConfig.h:27    */
+#define UG_NUM_MOVES 362          /* GO_MAX_MOVES,     config/BoardStaticConfig.h:28    */
+#define UG_NUM_PLANES 17          /* NUM_MAPS,         funcapproximator/DlTFNetworkEvaluator.h:13 */
+#define UG_HISTORY 8              /* (17-1)/2,         gouct/GoUctGlobalSearch.h:166    */
+#define UG_MASK_WORDS 12          /* ceil(361/32) */
+
+/* value_transform, funcapproximator/DlConfig.h:8-13 */
+enum { UG_TR_IDENTITY = 0, UG_TR_FLIP_SIGN = 1, UG_TR_FLIP_PROB = 2 };
+/* DataFormat, funcapproximator/DataFormat.h:22-25 */
+enum { UG_DF_HWC = 0, UG_DF_CHW = 1 };
+/* arithmetic of the tower: bf16 tcgen05 path (product) or fp32 SIMT validation build */
+enum { UG_PREC_BF16 = 0, UG_PREC_FP32 = 1 };
+
+/*
+ * Packed search leaf: what a search thread hands to the GPU encoder instead of running
+ * GoUctGlobalSearchState::CollectFeatures (gouct/GoUctGlobalSearch.h:160-206) on the CPU.
+ * black[k]/white[k] = stones on the board after undoing k moves (k = 0 is the leaf); when the history is
+ * shorter than 8 the oldest position repeats (GoBoard::GetLastMove null rule, go/GoBoard.h:659-667).
+ * Bit i of word i>>5 is point index i = (row-1)*19 + (col-1)  (GoPointUtil::Point2Index, board/GoPoint.h:139-146).
+ * to_play: 0 = black (SG_BLACK), 1 = white (SG_WHITE)  (board/GoBlackWhite.h:8-9).
+ */
+typedef struct ug_packed_pos {
+  uint32_t black[UG_HISTORY][UG_MASK_WORDS];
+  uint32_t white[UG_HISTORY][UG_MASK_WORDS];
+  uint32_t to_play;
+  uint32_t reserved[3];
+} ug_packed_pos; /* 784 bytes */
+
+typedef struct ug_net_info {
+  int blocks;           /* residual blocks */
+  int filters;          /* tower width C */
+  int policy_channels;  /* 1x1 policy conv outputs */
+  int value_channels;   /* 1x1 value conv outputs */
+  int value_hidden;     /* value FC width */
+  int input_planes;     /* 17 */
+  double flops_per_position; /* algorithmic FLOPs (SURVEY 8(d) formula evaluated on this net) */
+  int conv_ctas;        /* 1 or 2: cta_group of the tower kernel in use */
+  int sm_count;
+} ug_net_info;
+
+typedef struct ug_eval ug_eval;
+typedef struct ug_queue ug_queue;
+typedef struct ug_dlcfg ug_dlcfg;
+
+/* ------------------------------------------------------------------ evaluator (DlTFNetworkEvaluator<T>) */
+
+/* DlTFNetworkEvaluator(graphPath, df) ctor, funcapproximator/DlTFNetworkEvaluator.cc:27-53: never loads;
+ * defaults: checkpoint "bootstrap-ckpt", input "feature_input", outputs the two resnet/tower_0 names.
+ * device = CUDA ordinal; precision = UG_PREC_*; max_batch = largest n a run call may pass (buffers are sized once). */
+ug_eval* ug_eval_create(int device, int precision, int max_batch);
+/* ~DlTFNetworkEvaluator, .cc:67-69 (safe when nothing was loaded). */
+void ug_eval_destroy(ug_eval* h);
+/* message of the last failing call on h (h may be NULL for ug_eval_create failures) */
+const char* ug_last_error(const ug_eval* h);
+
+/* SetNetworkInput / SetNetworkOutput, .cc:56-64: node names without ":0"; outputs[0]=policy, [1]=value. */
+int ug_eval_set_io(ug_eval* h, const char* input, const char* const* outputs, int n_outputs);
+/* LoadGraph, .cc:77-83 (+LoadMetaGraph .cc:115-167): ".meta" -> MetaGraphDef, ".pb" -> GraphDef, else 1
+ * ("false").  Unreadable / unparsable file or an op pattern the loader does not recognise -> <0 (throws). */
+int ug_eval_load_graph(ug_eval* h, const char* path);
+/* UpdateCheckPoint, .cc:230-236,170-200: TF V2 bundle prefix (<p>.index + <p>.data-00000-of-00001); "" reuses
+ * the last prefix; >0 on failure (never throws); may be called repeatedly (hot swap). */
+int ug_eval_load_checkpoint(ug_eval* h, const char* prefix);
+/* MetaGraphLoaded, .cc:239-241 */
+int ug_eval_ready(const ug_eval* h);
+/* 1 when graph and weights are both resident */
+int ug_eval_has_weights(const ug_eval* h);
+/* value_transform applied by run calls (the reference reads it from the DlConfig singleton, .cc:300) */
+int ug_eval_set_value_transform(ug_eval* h, int vt);
+int ug_eval_info(const ug_eval* h, ug_net_info* out);
+/* use cta_group::1 or ::2 tower kernels (default 2); testing/benchmark knob */
+int ug_eval_set_conv_ctas(ug_eval* h, int ctas);
+
+/* Evaluate(char feature[][17][19][19], double policies[][362], double value[], n), .cc:287-318.
+ * HOST buffers, synchronous.  On failure outputs are left untouched (as .cc:315-317) and <0 is returned. */
+int ug_eval_run_planes(ug_eval* h, const int8_t* chw, int n, double* policy, double* value);
+/* Evaluate(char feature[][19][19][17], ...) overload, .cc:321-352. */
+int ug_eval_run_planes_hwc(ug_eval* h, const int8_t* hwc, int n, double* policy, double* value);
+
+/* Native fast path: packed leaves in, fp32 out, HOST buffers, synchronous (H2D + kernels + D2H).
+ * legal (optional, n x 12 words, bit i = move index i legal, 361 = pass): priors are renormalised over the
+ * legal set as UctSearch::UpdatePrior does (search/UctSearch.cpp:1257-1270), illegal entries are 0. */
+int ug_eval_run_packed(ug_eval* h, const ug_packed_pos* pos, int n, const uint32_t* legal, float* policy,
+                       float* value);
+/* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = the evaluator's own stream). */
+int ug_eval_run_packed_device(ug_eval* h, const ug_packed_pos* d_pos, int n, const uint32_t* d_legal,
+                              float* d_policy, float* d_value, void* stream);
+/* block until everything queued on the evaluator's own stream has finished */
+int ug_eval_sync(ug_eval* h);
+
+/* ------------------------------------------------------------------ encoder hooks (CollectFeatures seam) */
+/* UctThreadState::CollectFeatures(char[][19][19], 17), search/UctSearch.h:95: packed leaves -> the reference's
+ * int8 planes [n][17][19][19], computed on the GPU (HOST buffers). */
+int ug_encode_planes(ug_eval* h, const ug_packed_pos* pos, int n, int8_t* chw_out);
+/* The tower's actual input: [n][19][19][17] bytes read back from the NHWC bf16 tensor the encoder wrote
+ * (what TransformFeature, .cc:366-389, hands to TensorFlow as bool[n,19,19,17]). */
+int ug_encode_nhwc(ug_eval* h, const ug_packed_pos* pos, int n, int8_t* hwc_out);
+/* same, from reference planes (the K2 re-layout kernel used by ug_eval_run_planes) */
+int ug_transform_planes(ug_eval* h, const int8_t* chw, int n, int8_t* hwc_out);
+
+/* ------------------------------------------------------------------ debugging / parity */
+/* After a run call: copy the fp32 image of intermediate tensor `layer` to host as [n][361][channels].
+ * layer 0 = stem output, 1..2*blocks = tower convs in order; returns channels or <0. */
+int ug_eval_debug_layer(ug_eval* h, int layer, int n, float* out);
+/* Device-buffer kernel timings of the last ug_eval_bench call. */
+typedef struct ug_bench_result {
+  float ms_total;    /* CUDA-event time of `iters` full passes (encoder+tower+heads), device-resident inputs */
+  float ms_encoder;  /* per-pass averages of the three kernel groups, measured in separate event brackets */
+  float ms_tower;
+  float ms_heads;
+  int launches_per_pass;
+} ug_bench_result;
+int ug_eval_bench(ug_eval* h, const ug_packed_pos* host_pos, int n, int iters, ug_bench_result* out);
+
+/* Raw kernel entry for unit tests: one 3x3 conv layer on device buffers (bf16 NHWC in/out, packed bf16
+ * weights [cout][9*cin], fp32 bias, optional bf16 residual).  ck in {32,64}, ctas in {1,2}. */
+int ug_k_conv3x3_bf16(int device, const void* d_in, const void* d_w, const float* d_bias, const void* d_res,
+                      void* d_out, int n, int cin, int cout, int relu, int ck, int ctas);
+
+/* ------------------------------------------------------------------ leaf-batching queue (Q1) */
+/* Replaces EvalBuffer/EvalMsg + NetworkEvalThread's spin loop (search/UctSearch.h:59-72,126-130;
+ * search/UctSearch.cpp:164-205): lock-free multi-producer ring, the consumer thread gathers up to max_batch
+ * leaves (or flushes after timeout_us), double-buffered pinned staging on two CUDA streams. */
+ug_queue* ug_queue_create(ug_eval* h, int max_batch, int timeout_us, int capacity);
+void ug_queue_destroy(ug_queue* q);
+/* called by search threads; copies *pos (and legal, optional 12 words); returns ticket >= 0, or <0 */
+int64_t ug_queue_submit(ug_queue* q, const ug_packed_pos* pos, const uint32_t* legal);
+/* blocks until the ticket's own result is ready; policy[362], *value */
+int ug_queue_wait(ug_queue* q, int64_t ticket, float* policy, float* value);
+/* counters: batches run, leaves evaluated, sum of batch sizes, timeouts */
+int ug_queue_stats(ug_queue* q, uint64_t* batches, uint64_t* leaves, uint64_t* flush_timeouts);
+/* pause the consumer, swap the checkpoint, resume (hot swap between searches, search/UctSearch.cpp:178-182) */
+int ug_queue_swap_checkpoint(ug_queue* q, const char* prefix);
+
+/* ------------------------------------------------------------------ dlcfg (DlConfig) */
+/* DlConfig(filename) + parse(), funcapproximator/DlConfig.cc:20-41. A missing file yields an empty map. */
+ug_dlcfg* ug_dlcfg_open(const char* path);
+void ug_dlcfg_close(ug_dlcfg* c);
+/* get(key, default), DlConfig.cc:164-176; returns bytes written (excluding NUL), truncated to cap-1 */
+int ug_dlcfg_get(const ug_dlcfg* c, const char* key, const char* dflt, char* out, int cap);
+int ug_dlcfg_value_transform(const ug_dlcfg* c);   /* DlConfig.cc:228-246 */
+int ug_dlcfg_reuse_search_tree(const ug_dlcfg* c); /* DlConfig.cc:221-226 */
+/* nn_outputs split at ':' (DlConfig.cc:214-219); returns count, writes up to max names of cap bytes each */
+int ug_dlcfg_network_outputs(const ug_dlcfg* c, char* out, int cap, int max);
+
+/* Host-only (no CUDA call): parse graph_path (.meta/.pb), build the network plan from input/policy/value node
+ * names (NULL = the reference defaults) and, if ckpt_prefix is non-empty, verify every variable the plan needs.
+ * Writes a JSON description (or the error message) to out.  0 ok, 1 bad suffix, 2 checkpoint problem, <0 graph
+ * unreadable/unsupported.  Same loader as LoadGraph/UpdateCheckPoint. */
+int ug_inspect_model(const char* graph_path, const char* ckpt_prefix, const char* input, const char* policy_out,
+                     const char* value_out, char* out, int cap);
+
+/* library build info */
+const char* ug_version(void);
+/* CRC-32C (Castagnoli), the checksum of TF bundle entries; exported for the checkpoint tooling */
+uint32_t ug_crc32c(const void* p, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UGEVAL_H */

@@ -1,0 +1,52 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def ckpt_dir(tmp_path_factory):
+    return str(tmp_path_factory.mktemp("ckpt"))
+
+
+def _make(ckpt_dir, name, blocks, filters, seed, **kw):
+    from unrealgo_b200 import tfformat
+    d = os.path.join(ckpt_dir, name)
+    return tfformat.write_synthetic_checkpoint(d, blocks, filters, seed=seed, **kw)
+
+
+@pytest.fixture(scope="session")
+def small_ckpt(ckpt_dir):
+    """2 blocks x 64 filters"""
+    return _make(ckpt_dir, "small", 2, 64, 11)
+
+
+@pytest.fixture(scope="session")
+def small_ckpt_b(ckpt_dir):
+    """same architecture, different weights (hot-swap tests)"""
+    return _make(ckpt_dir, "small_b", 2, 64, 12)
+
+
+@pytest.fixture(scope="session")
+def wide_ckpt(ckpt_dir):
+    """3 blocks x 256 filters: the production tile shape (N=256, K=2304)"""
+    return _make(ckpt_dir, "wide", 3, 256, 13)
+
+
+@pytest.fixture(scope="session")
+def positions():
+    import oracle
+    return oracle.synthetic_positions(96, seed=20260119)
+
+
+def rng(seed=0):
+    return np.random.default_rng(seed)

@@ -1,0 +1,42 @@
+"""K1/K2 parity (bit-exact, integer work): GPU encoder vs the oracle's CollectFeatures / TransformFeature."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ev():
+    from unrealgo_b200 import DlTFNetworkEvaluator
+    e = DlTFNetworkEvaluator("", max_batch=4096)
+    yield e
+    e.close()
+
+
+def test_encoder_planes_bit_exact(ev, positions):
+    packed, planes = positions
+    got = ev.encode_planes(packed)
+    assert got.dtype == np.int8 and got.shape == planes.shape
+    assert np.array_equal(got, planes)
+
+
+def test_encoder_nhwc_is_transform_feature(ev, positions):
+    import oracle
+    packed, planes = positions
+    want = oracle.transform_feature(planes, data_format=0, as_bool=True)  # bool[n,19,19,17] handed to TF
+    assert np.array_equal(ev.encode_nhwc(packed), want)
+    assert np.array_equal(ev.TransformFeature(planes), want)
+
+
+def test_transform_feature_bool_semantics(ev):
+    import oracle
+    rng = np.random.default_rng(5)
+    planes = rng.integers(-3, 4, size=(9, 17, 19, 19)).astype(np.int8)  # (bool)char: any non-zero is 1
+    assert np.array_equal(ev.TransformFeature(planes), oracle.transform_feature(planes, 0, True))
+
+
+def test_encoder_many_positions(ev):
+    import oracle
+    packed, planes = oracle.synthetic_positions(3000, seed=77)
+    assert np.array_equal(ev.encode_planes(packed), planes)
+    assert np.array_equal(ev.encode_nhwc(packed), oracle.transform_feature(planes, 0, True))

@@ -1,0 +1,147 @@
+"""End-to-end parity of the evaluator against the oracle (interpreted graph, fp32 CPU) on synthetic
+checkpoints, through the C ABI (reference-facing Evaluate() and the packed fast path).
+
+Tolerances (BASELINE.json north_star): bf16 build — max-abs policy-probability error <= 1e-3, value error
+<= 5e-3; fp32 validation build — <= 1e-5."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BF16_POL, BF16_VAL = 1e-3, 5e-3
+FP32_POL, FP32_VAL = 1e-5, 1e-5
+
+
+def _oracle(ckpt):
+    from oracle.net_oracle import GraphOracle
+    return GraphOracle(*ckpt)
+
+
+def _evaluator(ckpt, precision, max_batch=128, ctas=2):
+    from unrealgo_b200 import DlTFNetworkEvaluator
+    ev = DlTFNetworkEvaluator(ckpt[0], precision=precision, max_batch=max_batch)
+    assert ev.MetaGraphLoaded()
+    assert ev.UpdateCheckPoint(ckpt[1])
+    ev.set_conv_ctas(ctas)
+    return ev
+
+
+def _run_reference_api(ev, planes):
+    n = planes.shape[0]
+    pol = np.full((n, 362), -7.0)
+    val = np.full(n, -7.0)
+    assert ev.Evaluate(planes, pol, val, n)
+    return pol, val
+
+
+@pytest.mark.parametrize("n", [1, 7, 16, 64])
+def test_fp32_validation_build_small(small_ckpt, positions, n):
+    from unrealgo_b200 import PREC_FP32
+    packed, planes = positions
+    ev = _evaluator(small_ckpt, PREC_FP32)
+    want_p, want_v = _oracle(small_ckpt).evaluate_reference(planes[:n])
+    got_p, got_v = _run_reference_api(ev, planes[:n])
+    assert np.abs(got_p - want_p).max() <= FP32_POL
+    assert np.abs(got_v - want_v).max() <= FP32_VAL
+    pp, pv = ev.evaluate_packed(packed[:n])
+    assert np.abs(pp - want_p).max() <= FP32_POL and np.abs(pv - want_v).max() <= FP32_VAL
+    ev.close()
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("n", [1, 7, 16, 64])
+def test_bf16_small(small_ckpt, positions, n, ctas):
+    from unrealgo_b200 import PREC_BF16
+    packed, planes = positions
+    ev = _evaluator(small_ckpt, PREC_BF16, ctas=ctas)
+    want_p, want_v = _oracle(small_ckpt).evaluate_reference(planes[:n])
+    got_p, got_v = _run_reference_api(ev, planes[:n])
+    assert abs(got_p.sum(1) - 1).max() < 1e-5
+    assert np.abs(got_p - want_p).max() <= BF16_POL, np.abs(got_p - want_p).max()
+    assert np.abs(got_v - want_v).max() <= BF16_VAL, np.abs(got_v - want_v).max()
+    pp, pv = ev.evaluate_packed(packed[:n])
+    assert np.array_equal(pp.astype(np.float64), got_p) and np.array_equal(pv.astype(np.float64), got_v)
+    ev.close()
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+def test_bf16_wide_layers_and_outputs(wide_ckpt, positions, ctas):
+    """256 filters (the production tile) — per-layer comparison against the fp32 validation build and
+    end-to-end against the oracle."""
+    from unrealgo_b200 import PREC_BF16, PREC_FP32
+    packed, planes = positions
+    n = 40  # 40*361 = 14440 rows: tail tile for both 128- and 256-row tiles
+    ev16 = _evaluator(wide_ckpt, PREC_BF16, ctas=ctas)
+    ev32 = _evaluator(wide_ckpt, PREC_FP32)
+    p16, v16 = ev16.evaluate_packed(packed[:n])
+    p32, v32 = ev32.evaluate_packed(packed[:n])
+    for layer in range(0, 7):
+        a16 = ev16.debug_layer(layer, n)
+        a32 = ev32.debug_layer(layer, n)
+        scale = np.abs(a32).max()
+        assert np.abs(a16 - a32).max() <= 0.02 * scale + 1e-3, (layer, np.abs(a16 - a32).max(), scale)
+    want_p, want_v = _oracle(wide_ckpt).evaluate_reference(planes[:n])
+    assert np.abs(p32 - want_p).max() <= FP32_POL and np.abs(v32 - want_v).max() <= FP32_VAL
+    assert np.abs(p16 - want_p).max() <= BF16_POL and np.abs(v16 - want_v).max() <= BF16_VAL
+    ev16.close()
+    ev32.close()
+
+
+def test_value_transform_and_failure_semantics(small_ckpt, positions):
+    import oracle
+    from unrealgo_b200 import DlTFNetworkEvaluator, PREC_BF16
+    _, planes = positions
+    ev = _evaluator(small_ckpt, PREC_BF16)
+    base_p, base_v = _run_reference_api(ev, planes[:8])
+    for vt in (1, 2, 0, 9):
+        ev.set_value_transform(vt)
+        p, v = _run_reference_api(ev, planes[:8])
+        eff = vt if vt in (1, 2) else 0
+        assert np.array_equal(v, oracle.value_transform(base_v, eff)) and np.array_equal(p, base_p)
+    ev.close()
+    # evaluate without a network: logs, leaves outputs untouched (DlTFNetworkEvaluator.cc:315-317)
+    bare = DlTFNetworkEvaluator("")
+    pol = np.full((2, 362), 3.0)
+    val = np.full(2, 4.0)
+    assert not bare.Evaluate(planes[:2], pol, val, 2)
+    assert (pol == 3.0).all() and (val == 4.0).all()
+    bare.close()
+
+
+def test_checkpoint_hot_swap(small_ckpt, small_ckpt_b, positions):
+    from unrealgo_b200 import PREC_BF16
+    _, planes = positions
+    ev = _evaluator(small_ckpt, PREC_BF16)
+    pa, va = _run_reference_api(ev, planes[:8])
+    assert ev.UpdateCheckPoint(small_ckpt_b[1])
+    pb, vb = _run_reference_api(ev, planes[:8])
+    want_p, want_v = _oracle(small_ckpt_b).evaluate_reference(planes[:8])
+    assert np.abs(pb - want_p).max() <= BF16_POL and np.abs(vb - want_v).max() <= BF16_VAL
+    assert np.abs(pa - pb).max() > 1e-4
+    assert not ev.UpdateCheckPoint("/nonexistent/prefix")  # returns false, keeps the old weights
+    pc, vc = _run_reference_api(ev, planes[:8])
+    assert np.array_equal(pb, pc) and np.array_equal(vb, vc)
+    ev.close()
+
+
+def test_legal_mask_renormalisation(small_ckpt, positions):
+    """masked-softmax variant == UctSearch::UpdatePrior over the legal children"""
+    import oracle
+    from unrealgo_b200 import PREC_BF16
+    packed, _ = positions
+    n = 12
+    ev = _evaluator(small_ckpt, PREC_BF16)
+    p, _ = ev.evaluate_packed(packed[:n])
+    rng = np.random.default_rng(3)
+    legal_idx = [np.sort(rng.choice(362, size=int(rng.integers(1, 300)), replace=False)) for _ in range(n)]
+    masks = np.zeros((n, 12), np.uint32)
+    for i, idx in enumerate(legal_idx):
+        for j in idx:
+            masks[i, j >> 5] |= np.uint32(1 << (j & 31))
+    pm, _ = ev.evaluate_packed(packed[:n], legal=masks)
+    for i, idx in enumerate(legal_idx):
+        want = oracle.update_prior(p[i].astype(np.float64), idx)
+        assert np.abs(pm[i, idx] - want).max() < 1e-5
+        rest = np.setdiff1d(np.arange(362), idx)
+        assert (pm[i, rest] == 0).all()
+    ev.close()

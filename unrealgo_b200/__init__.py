@@ -1,0 +1,7 @@
+"""unrealgo_b200 — B200-native (sm_100a) drop-in for UnrealGo's batched network-evaluation path.
+
+The product is the C-ABI CUDA library unrealgo_b200/lib/libugeval.so (include/ugeval.h); this package holds its
+sources (csrc/), the C++ host shim mirroring the reference classes (host/), and thin Python bindings used by
+the tests and bench.py.  No CPU fallback exists anywhere in this package.
+"""
+from .evaluator import DlConfig, DlTFNetworkEvaluator, LeafQueue, UctBoardEvaluator, inspect_model  # noqa: F401

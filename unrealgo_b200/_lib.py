@@ -1,0 +1,106 @@
+"""ctypes binding of libugeval.so (C ABI declared in include/ugeval.h).
+
+The library is the product; there is no Python or CPU fallback.  Importing this module without the built
+library raises, and creating an evaluator without a B200 raises (ug_eval_create returns NULL).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libugeval.so")
+
+NUM_POINTS = 361
+NUM_MOVES = 362
+NUM_PLANES = 17
+HISTORY = 8
+MASK_WORDS = 12
+PACKED_POS_BYTES = 784
+
+TR_IDENTITY, TR_FLIP_SIGN, TR_FLIP_PROB = 0, 1, 2
+PREC_BF16, PREC_FP32 = 0, 1
+
+
+class PackedPos(C.Structure):
+    _fields_ = [
+        ("black", (C.c_uint32 * MASK_WORDS) * HISTORY),
+        ("white", (C.c_uint32 * MASK_WORDS) * HISTORY),
+        ("to_play", C.c_uint32),
+        ("reserved", C.c_uint32 * 3),
+    ]
+
+
+class NetInfo(C.Structure):
+    _fields_ = [
+        ("blocks", C.c_int), ("filters", C.c_int), ("policy_channels", C.c_int), ("value_channels", C.c_int),
+        ("value_hidden", C.c_int), ("input_planes", C.c_int), ("flops_per_position", C.c_double),
+        ("conv_ctas", C.c_int), ("sm_count", C.c_int),
+    ]
+
+
+class BenchResult(C.Structure):
+    _fields_ = [("ms_total", C.c_float), ("ms_encoder", C.c_float), ("ms_tower", C.c_float),
+                ("ms_heads", C.c_float), ("launches_per_pass", C.c_int)]
+
+
+# name -> (restype, argtypes); every symbol include/ugeval.h declares
+SIGNATURES = {
+    "ug_eval_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int]),
+    "ug_eval_destroy": (None, [C.c_void_p]),
+    "ug_last_error": (C.c_char_p, [C.c_void_p]),
+    "ug_eval_set_io": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int]),
+    "ug_eval_load_graph": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "ug_eval_load_checkpoint": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "ug_eval_ready": (C.c_int, [C.c_void_p]),
+    "ug_eval_has_weights": (C.c_int, [C.c_void_p]),
+    "ug_eval_set_value_transform": (C.c_int, [C.c_void_p, C.c_int]),
+    "ug_eval_info": (C.c_int, [C.c_void_p, C.POINTER(NetInfo)]),
+    "ug_eval_set_conv_ctas": (C.c_int, [C.c_void_p, C.c_int]),
+    "ug_eval_run_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ug_eval_run_planes_hwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ug_eval_run_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ug_eval_run_packed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]),
+    "ug_eval_sync": (C.c_int, [C.c_void_p]),
+    "ug_encode_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ug_encode_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ug_transform_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "ug_eval_debug_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ug_eval_bench": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(BenchResult)]),
+    "ug_k_conv3x3_bf16": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ug_queue_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "ug_queue_destroy": (None, [C.c_void_p]),
+    "ug_queue_submit": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ug_queue_wait": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ug_queue_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "ug_queue_swap_checkpoint": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "ug_dlcfg_open": (C.c_void_p, [C.c_char_p]),
+    "ug_dlcfg_close": (None, [C.c_void_p]),
+    "ug_dlcfg_get": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+    "ug_dlcfg_value_transform": (C.c_int, [C.c_void_p]),
+    "ug_dlcfg_reuse_search_tree": (C.c_int, [C.c_void_p]),
+    "ug_dlcfg_network_outputs": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
+    "ug_inspect_model": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+    "ug_version": (C.c_char_p, []),
+    "ug_crc32c": (C.c_uint32, [C.c_void_p, C.c_size_t]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libugeval.so and bind every declared symbol; raises if the library or a symbol is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the export is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

@@ -1,0 +1,25 @@
+// Launch interface of the tcgen05 implicit-GEMM 3x3 convolution (conv3x3_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace ug {
+
+struct ConvArgs {
+  const float* bias;              // [cout] folded batch-norm offset (fp32)
+  const __nv_bfloat16* residual;  // [M][cout] skip connection or nullptr
+  __nv_bfloat16* out;             // [M][cout]
+  int M;                          // n * 361 output pixels
+  int cin;                        // input channels as stored (multiple of ck)
+  int cout;                       // <= 256, multiple of 16 (32 for the 2-CTA variant)
+  int relu;
+  int num_tiles;                  // filled by the launcher
+};
+
+// tmA: im2col map over the input activations, tmB: tiled map over packed weights (see tmap.h).
+// ck = channels per k-step (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B); ctas = 1 or 2 (cta_group).
+cudaError_t conv3x3_tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvArgs a, int ck, int ctas,
+                              int sms, cudaStream_t stream);
+
+}  // namespace ug

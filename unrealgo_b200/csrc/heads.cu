@@ -1,0 +1,245 @@
+// K5-K7 — policy and value heads.
+//
+// In the reference these are the tail of the TensorFlow graph run by Session::Run
+// (funcapproximator/DlTFNetworkEvaluator.cc:295) plus the value_transform switch (.cc:300-310) and,
+// optionally, UctSearch::UpdatePrior's legal-move renormalisation (search/UctSearch.cpp:1257-1270).
+//
+// Stage 1 (head_conv): both 1x1 convolutions (+ folded batch-norm + ReLU) in one pass over the final tower
+//   activation: one warp per board point, 16-byte loads, warp-shuffle reduction.  HBM-bound: reads
+//   361*C*2 bytes per position, writes 361*(pc+vc) floats.
+// Stage 2 (head_fc): per CTA kPosPerCta positions: policy FC -> softmax (optionally masked and
+//   renormalised), value FC -> ReLU -> FC -> tanh -> value_transform.  Weights stream once per CTA from L2.
+#include <math_constants.h>
+
+#include "kernels.h"
+
+namespace ug {
+
+namespace {
+
+constexpr int kPoints = UG_NUM_POINTS;
+constexpr int kMoves = UG_NUM_MOVES;
+constexpr int kMaxHeadCh = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <typename T>
+struct Load8;
+template <>
+struct Load8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+};
+template <>
+struct Load8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+
+// feat[point][h] = relu(sum_c act[point][c] * w[h][c] + b[h]);  HC = pc+vc <= 8, C % 8 == 0
+template <typename T, int HC>
+__global__ void __launch_bounds__(256) head_conv_kernel(const T* __restrict__ act, const float* __restrict__ w,
+                                                        const float* __restrict__ b, float* __restrict__ feat,
+                                                        long total_points, int C) {
+  extern __shared__ float sw[];  // [HC][C]
+  for (int i = threadIdx.x; i < HC * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long warp_global = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long warp_stride = (long)gridDim.x * (blockDim.x >> 5);
+  const int chunks = C >> 3;
+  for (long pt = warp_global; pt < total_points; pt += warp_stride) {
+    float acc[HC];
+#pragma unroll
+    for (int h = 0; h < HC; ++h) acc[h] = 0.f;
+    const T* row = act + pt * C;
+    for (int ch = lane; ch < chunks; ch += 32) {
+      float x[8];
+      Load8<T>::load(row + ch * 8, x);
+#pragma unroll
+      for (int h = 0; h < HC; ++h) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + h * C + ch * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + h * C + ch * 8 + 4);
+        acc[h] += x[0] * w0.x + x[1] * w0.y + x[2] * w0.z + x[3] * w0.w + x[4] * w1.x + x[5] * w1.y +
+                  x[6] * w1.z + x[7] * w1.w;
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < HC; ++h) acc[h] = warp_sum(acc[h]);
+    if (lane == 0) {
+#pragma unroll
+      for (int h = 0; h < HC; ++h) feat[pt * HC + h] = fmaxf(acc[h] + __ldg(b + h), 0.f);
+    }
+  }
+}
+
+constexpr int kPosPerCta = 4;
+constexpr int kFcThreads = 384;
+
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();  // scratch reuse
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  float r = (lane < nw) ? scratch[lane] : (is_max ? -CUDART_INF_F : 0.f);
+  r = is_max ? warp_max(r) : warp_sum(r);
+  return r;
+}
+
+// feat layout per position: [361][pc+vc] (policy channels first).  Policy FC input index = point*pc + c,
+// value FC input index = point*vc + c (the NHWC flatten TensorFlow's Reshape produces).
+__global__ void __launch_bounds__(kFcThreads) head_fc_kernel(const float* __restrict__ feat, HeadWeights hw,
+                                                             const uint32_t* __restrict__ legal, int vt,
+                                                             float* __restrict__ policy,
+                                                             float* __restrict__ value, int n) {
+  extern __shared__ float sm[];
+  const int pc = hw.pc, vc = hw.vc, hc = pc + vc, H = hw.H;
+  const int pin = kPoints * pc, vin = kPoints * vc;
+  float* fp = sm;                          // [kPosPerCta][pin]
+  float* fv = fp + kPosPerCta * pin;       // [kPosPerCta][vin]
+  float* hid = fv + kPosPerCta * vin;      // [kPosPerCta][H]
+  float* scratch = hid + kPosPerCta * H;   // [32]
+  const int p0 = blockIdx.x * kPosPerCta;
+  const int np = min(kPosPerCta, n - p0);
+
+  for (int i = threadIdx.x; i < kPosPerCta * kPoints * hc; i += blockDim.x) {
+    const int p = i / (kPoints * hc);
+    const int r = i - p * (kPoints * hc);
+    const int point = r / hc, c = r - point * hc;
+    const float v = (p < np) ? __ldg(feat + (size_t)(p0 + p) * kPoints * hc + r) : 0.f;
+    if (c < pc) fp[p * pin + point * pc + c] = v;
+    else fv[p * vin + point * vc + (c - pc)] = v;
+  }
+  __syncthreads();
+
+  // ---- policy: logits[j] = b[j] + sum_i f[i] * W[i][j]
+  const int j = threadIdx.x;
+  float logit[kPosPerCta];
+#pragma unroll
+  for (int p = 0; p < kPosPerCta; ++p) logit[p] = 0.f;
+  if (j < kMoves) {
+    const float* wcol = hw.pfc_w + j;
+#pragma unroll 4
+    for (int i = 0; i < pin; ++i) {
+      const float wv = __ldg(wcol + (size_t)i * kMoves);
+#pragma unroll
+      for (int p = 0; p < kPosPerCta; ++p) logit[p] = fmaf(fp[p * pin + i], wv, logit[p]);
+    }
+    const float bj = __ldg(hw.pfc_b + j);
+#pragma unroll
+    for (int p = 0; p < kPosPerCta; ++p) logit[p] += bj;
+  }
+  for (int p = 0; p < np; ++p) {
+    const float mx = block_reduce(j < kMoves ? logit[p] : -CUDART_INF_F, true, scratch);
+    float prob = logit[p];
+    if (hw.policy_softmax) {
+      const float e = (j < kMoves) ? expf(logit[p] - mx) : 0.f;
+      const float sum = block_reduce(e, false, scratch);
+      prob = e / sum;
+    }
+    if (legal != nullptr) {
+      // UpdatePrior: prior = p[idx] / sum over legal children of p[idx]; illegal moves get 0
+      const uint32_t* lm = legal + (size_t)(p0 + p) * UG_MASK_WORDS;
+      const bool ok = (j < kMoves) && ((__ldg(lm + (j >> 5)) >> (j & 31)) & 1u);
+      const float lsum = block_reduce(ok ? prob : 0.f, false, scratch);
+      prob = ok ? prob / lsum : 0.f;
+    }
+    if (j < kMoves) policy[(size_t)(p0 + p) * kMoves + j] = prob;
+  }
+
+  // ---- value: hidden = relu(W1^T f + b1); v = tanh(w2 . hidden + b2)
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float acc[kPosPerCta];
+#pragma unroll
+    for (int p = 0; p < kPosPerCta; ++p) acc[p] = 0.f;
+    const float* wcol = hw.v1_w + h;
+#pragma unroll 4
+    for (int i = 0; i < vin; ++i) {
+      const float wv = __ldg(wcol + (size_t)i * H);
+#pragma unroll
+      for (int p = 0; p < kPosPerCta; ++p) acc[p] = fmaf(fv[p * vin + i], wv, acc[p]);
+    }
+    const float b1 = __ldg(hw.v1_b + h);
+#pragma unroll
+    for (int p = 0; p < kPosPerCta; ++p) hid[p * H + h] = fmaxf(acc[p] + b1, 0.f);
+  }
+  __syncthreads();
+  for (int p = 0; p < np; ++p) {
+    float part = 0.f;
+    for (int h = threadIdx.x; h < H; h += blockDim.x) part = fmaf(hid[p * H + h], __ldg(hw.v2_w + h), part);
+    const float tot = block_reduce(part, false, scratch);
+    if (threadIdx.x == 0) {
+      float v = tot + __ldg(hw.v2_b);
+      if (hw.value_tanh) v = tanhf(v);
+      if (vt == UG_TR_FLIP_SIGN) v = -v;
+      else if (vt == UG_TR_FLIP_PROB) v = 1.f - v;
+      value[p0 + p] = v;
+    }
+  }
+}
+
+template <typename T>
+void head_conv_dispatch(const T* act, const HeadWeights& w, float* feat, int n, cudaStream_t s) {
+  const long total = (long)n * kPoints;
+  const int hc = w.pc + w.vc;
+  int grid = (int)((total + 7) / 8);
+  if (grid > 148 * 8) grid = 148 * 8;
+  const size_t smem = (size_t)hc * w.C * sizeof(float);
+  switch (hc) {
+#define UG_HC_CASE(N)                                                                                   \
+  case N:                                                                                               \
+    head_conv_kernel<T, N><<<grid, 256, smem, s>>>(act, w.conv_w, w.conv_b, feat, total, w.C);          \
+    break;
+    UG_HC_CASE(1) UG_HC_CASE(2) UG_HC_CASE(3) UG_HC_CASE(4) UG_HC_CASE(5) UG_HC_CASE(6) UG_HC_CASE(7)
+    UG_HC_CASE(8)
+#undef UG_HC_CASE
+    default: break;
+  }
+}
+
+}  // namespace
+
+void launch_head_conv(const void* act, int act_is_f32, const HeadWeights& w, float* feat, int n, cudaStream_t s) {
+  if (n <= 0) return;
+  if (act_is_f32) head_conv_dispatch<float>(static_cast<const float*>(act), w, feat, n, s);
+  else head_conv_dispatch<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(act), w, feat, n, s);
+}
+
+void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* legal, int vt, float* policy,
+                    float* value, int n, cudaStream_t s) {
+  if (n <= 0) return;
+  const size_t smem =
+      sizeof(float) * ((size_t)kPosPerCta * (kPoints * (w.pc + w.vc) + w.H) + 32);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaFuncSetAttribute(head_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  const int grid = (n + kPosPerCta - 1) / kPosPerCta;
+  head_fc_kernel<<<grid, kFcThreads, smem, s>>>(feat, w, legal, vt, policy, value, n);
+}
+
+}  // namespace ug

@@ -1,0 +1,93 @@
+// Host-only inspection of the model artefacts (no CUDA call): parses the graph, builds the network plan and,
+// when a checkpoint prefix is given, checks every variable the plan needs (presence, dtype, shape, crc32c).
+// Lets tooling and the CPU test-suite exercise the loader of LoadMetaGraph / UpdateCheckPointForMetaGraph
+// (funcapproximator/DlTFNetworkEvaluator.cc:115-200) without a GPU.
+#include <cstring>
+#include <sstream>
+
+#include "../../include/ugeval.h"
+#include "tfmodel.h"
+
+using namespace ug;
+
+namespace {
+void json_conv(std::ostringstream& o, const ConvPlan& c) {
+  o << "{\"kernel\":\"" << c.kernel << "\",\"bias\":\"" << c.bias << "\",\"bn\":" << (c.has_bn ? "true" : "false")
+    << ",\"gamma\":\"" << c.gamma << "\",\"beta\":\"" << c.beta << "\",\"mean\":\"" << c.mean << "\",\"var\":\""
+    << c.var << "\",\"eps\":" << c.eps << "}";
+}
+int emit(const std::string& s, char* out, int cap) {
+  if (!out || cap <= 0) return -1;
+  const int n = (int)s.size() < cap - 1 ? (int)s.size() : cap - 1;
+  memcpy(out, s.data(), (size_t)n);
+  out[n] = 0;
+  return n;
+}
+}  // namespace
+
+extern "C" int ug_inspect_model(const char* graph_path, const char* ckpt_prefix, const char* input,
+                                const char* policy_out, const char* value_out, char* out, int cap) {
+  const std::string gp = graph_path ? graph_path : "";
+  const bool meta = gp.size() >= 5 && gp.compare(gp.size() - 5, 5, ".meta") == 0;
+  const bool pb = gp.size() >= 3 && gp.compare(gp.size() - 3, 3, ".pb") == 0;
+  if (!meta && !pb) { emit("graph path must end in .meta or .pb", out, cap); return 1; }
+  std::vector<uint8_t> bytes;
+  std::string err;
+  if (!read_file(gp, &bytes)) { emit("Error reading graph definition from " + gp, out, cap); return -1; }
+  TfGraph g;
+  if (!parse_tf_graph(bytes, meta, &g, &err)) { emit(err, out, cap); return -1; }
+  NetPlan plan;
+  if (!build_net_plan(g, input ? input : "feature_input",
+                      policy_out ? policy_out : "resnet/tower_0/policy_head/policy_predict",
+                      value_out ? value_out : "resnet/tower_0/value_head/reward_predict", &plan, &err)) {
+    emit("unsupported graph: " + err, out, cap);
+    return -1;
+  }
+  std::ostringstream o;
+  o << "{\"nodes\":" << g.nodes.size() << ",\"input\":\"" << plan.input << "\",\"input_dtype\":" << plan.input_dtype
+    << ",\"blocks\":" << plan.tower.size() / 2 << ",\"policy_softmax\":" << (plan.policy_softmax ? "true" : "false")
+    << ",\"value_tanh\":" << (plan.value_tanh ? "true" : "false") << ",\"saver_filename_tensor\":\""
+    << g.saver_filename_tensor << "\",\"saver_restore_op\":\"" << g.saver_restore_op << "\",\"stem\":";
+  json_conv(o, plan.stem);
+  o << ",\"tower\":[";
+  for (size_t i = 0; i < plan.tower.size(); ++i) { if (i) o << ","; json_conv(o, plan.tower[i]); }
+  o << "],\"policy_conv\":";
+  json_conv(o, plan.policy_conv);
+  o << ",\"value_conv\":";
+  json_conv(o, plan.value_conv);
+  o << ",\"policy_fc\":{\"kernel\":\"" << plan.policy_fc.kernel << "\",\"bias\":\"" << plan.policy_fc.bias << "\"}"
+    << ",\"value_fc1\":{\"kernel\":\"" << plan.value_fc1.kernel << "\",\"bias\":\"" << plan.value_fc1.bias << "\"}"
+    << ",\"value_fc2\":{\"kernel\":\"" << plan.value_fc2.kernel << "\",\"bias\":\"" << plan.value_fc2.bias << "\"}";
+  if (ckpt_prefix && ckpt_prefix[0]) {
+    TfBundle ck;
+    if (!ck.open(ckpt_prefix, &err)) { emit(err, out, cap); return 2; }
+    std::vector<std::string> need;
+    auto add_conv = [&](const ConvPlan& c) {
+      need.push_back(c.kernel);
+      if (!c.bias.empty()) need.push_back(c.bias);
+      if (c.has_bn) { need.push_back(c.gamma); need.push_back(c.beta); need.push_back(c.mean); need.push_back(c.var); }
+    };
+    add_conv(plan.stem);
+    for (const ConvPlan& c : plan.tower) add_conv(c);
+    add_conv(plan.policy_conv);
+    add_conv(plan.value_conv);
+    for (const DensePlan* d : {&plan.policy_fc, &plan.value_fc1, &plan.value_fc2}) {
+      need.push_back(d->kernel);
+      if (!d->bias.empty()) need.push_back(d->bias);
+    }
+    size_t params = 0;
+    std::vector<float> tmp;
+    std::vector<int64_t> shape;
+    for (const std::string& k : need) {
+      if (!ck.read_float(k, &tmp, &shape, &err)) { emit(err, out, cap); return 2; }
+      params += tmp.size();
+    }
+    const BundleEntry* stem = ck.find(plan.stem.kernel);
+    o << ",\"checkpoint\":{\"entries\":" << ck.entries().size() << ",\"variables_used\":" << need.size()
+      << ",\"parameters\":" << params << ",\"filters\":" << (stem && stem->shape.size() == 4 ? stem->shape[3] : 0)
+      << "}";
+  }
+  o << "}";
+  emit(o.str(), out, cap);
+  return 0;
+}

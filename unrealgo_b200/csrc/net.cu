@@ -1,0 +1,715 @@
+// Evaluator: load (graph plan + checkpoint -> folded, packed, device-resident weights), workspace, and the
+// launch sequence encoder -> stem -> residual tower -> heads.  Mirrors DlTFNetworkEvaluator<T>
+// (funcapproximator/DlTFNetworkEvaluator.cc) behind the C ABI in include/ugeval.h.
+#include "net.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+
+#include "conv3x3_tc.h"
+#include "tmap.h"
+
+namespace ug {
+
+bool DevBuf::alloc(size_t n) {
+  release();
+  if (n == 0) n = 16;
+  if (cudaMalloc(&p, n) != cudaSuccess) { p = nullptr; return false; }
+  bytes = n;
+  return true;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+}
+
+HeadWeights Weights::head() const {
+  HeadWeights h{};
+  h.conv_w = head_conv_w.as<float>();
+  h.conv_b = head_conv_b.as<float>();
+  h.pc = pc; h.vc = vc; h.C = C;
+  h.pfc_w = pfc_w.as<float>(); h.pfc_b = pfc_b.as<float>();
+  h.v1_w = v1_w.as<float>(); h.v1_b = v1_b.as<float>();
+  h.v2_w = v2_w.as<float>(); h.v2_b = v2_b.as<float>();
+  h.H = H;
+  h.policy_softmax = policy_softmax ? 1 : 0;
+  h.value_tanh = value_tanh ? 1 : 0;
+  return h;
+}
+
+namespace {
+
+thread_local std::string g_create_error;
+
+bool upload(DevBuf* b, const void* src, size_t bytes) {
+  if (!b->alloc(bytes)) return false;
+  return cudaMemcpy(b->p, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
+uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  const uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return (uint16_t)(u >> 16);
+}
+
+struct HostConv {
+  std::vector<float> w;  // HWIO, folded
+  std::vector<float> b;  // [cout]
+  int k = 3, cin = 0, cout = 0;
+};
+
+// read conv (+bias) (+batch-norm) variables and fold:  w' = w * g/sqrt(v+eps),  b' = beta + (bias - mean) * g/sqrt(v+eps)
+bool load_conv(const TfBundle& ck, const ConvPlan& p, int ksize, HostConv* out, std::string* err) {
+  std::vector<int64_t> shape;
+  if (!ck.read_float(p.kernel, &out->w, &shape, err)) return false;
+  if (shape.size() != 4 || shape[0] != ksize || shape[1] != ksize) {
+    *err = "conv kernel '" + p.kernel + "' is not " + std::to_string(ksize) + "x" + std::to_string(ksize) + " HWIO";
+    return false;
+  }
+  out->k = ksize;
+  out->cin = (int)shape[2];
+  out->cout = (int)shape[3];
+  const int cout = out->cout;
+  std::vector<float> bias(cout, 0.f);
+  if (!p.bias.empty()) {
+    std::vector<int64_t> bs;
+    if (!ck.read_float(p.bias, &bias, &bs, err)) return false;
+    if ((int)bias.size() != cout) { *err = "bias '" + p.bias + "' has wrong size"; return false; }
+  }
+  out->b.assign(cout, 0.f);
+  if (p.has_bn) {
+    std::vector<float> g, be, mu, var;
+    if (!ck.read_float(p.gamma, &g, nullptr, err) || !ck.read_float(p.beta, &be, nullptr, err) ||
+        !ck.read_float(p.mean, &mu, nullptr, err) || !ck.read_float(p.var, &var, nullptr, err))
+      return false;
+    if ((int)g.size() != cout || (int)be.size() != cout || (int)mu.size() != cout || (int)var.size() != cout) {
+      *err = "batch-norm variables of '" + p.kernel + "' have wrong size";
+      return false;
+    }
+    std::vector<float> scale(cout);
+    for (int c = 0; c < cout; ++c) {
+      scale[c] = g[c] / std::sqrt(var[c] + p.eps);
+      out->b[c] = be[c] + (bias[c] - mu[c]) * scale[c];
+    }
+    const size_t rows = out->w.size() / cout;
+    for (size_t r = 0; r < rows; ++r)
+      for (int c = 0; c < cout; ++c) out->w[r * cout + c] *= scale[c];
+  } else {
+    out->b = bias;
+  }
+  return true;
+}
+
+bool make_conv_layer(const HostConv& hc, int cin_pad, ConvLayer* L, std::string* err) {
+  L->cin = hc.cin;
+  L->cin_pad = cin_pad;
+  L->cout = hc.cout;
+  const int ktot = 9 * cin_pad;
+  std::vector<uint16_t> packed((size_t)hc.cout * ktot, 0);
+  for (int tap = 0; tap < 9; ++tap)
+    for (int ci = 0; ci < hc.cin; ++ci)
+      for (int co = 0; co < hc.cout; ++co)
+        packed[(size_t)co * ktot + tap * cin_pad + ci] =
+            f32_to_bf16_rn(hc.w[((size_t)tap * hc.cin + ci) * hc.cout + co]);
+  if (!upload(&L->w_bf16, packed.data(), packed.size() * 2) ||
+      !upload(&L->w_f32, hc.w.data(), hc.w.size() * 4) || !upload(&L->bias, hc.b.data(), hc.b.size() * 4)) {
+    *err = "out of device memory uploading weights";
+    return false;
+  }
+  const int ck = (cin_pad % 64 == 0) ? 64 : 32;
+  for (int ctas = 1; ctas <= 2; ++ctas)
+    if (!make_tmap_weights(&L->tm_w[ctas - 1], L->w_bf16.p, hc.cout, ktot, ck, hc.cout / ctas, err)) return false;
+  return true;
+}
+
+bool load_dense(const TfBundle& ck, const DensePlan& p, int in, std::vector<float>* w, std::vector<float>* b,
+                int* out_dim, std::string* err) {
+  std::vector<int64_t> shape;
+  if (!ck.read_float(p.kernel, w, &shape, err)) return false;
+  if (shape.size() != 2 || shape[0] != in) {
+    *err = "dense kernel '" + p.kernel + "' expected [" + std::to_string(in) + ", *]";
+    return false;
+  }
+  *out_dim = (int)shape[1];
+  b->assign(*out_dim, 0.f);
+  if (!p.bias.empty()) {
+    if (!ck.read_float(p.bias, b, nullptr, err)) return false;
+    if ((int)b->size() != *out_dim) { *err = "dense bias '" + p.bias + "' has wrong size"; return false; }
+  }
+  return true;
+}
+
+Weights* build_weights(const NetPlan& plan, const TfBundle& ck, std::string* err) {
+  std::unique_ptr<Weights> W(new Weights());
+  HostConv stem;
+  if (!load_conv(ck, plan.stem, 3, &stem, err)) return nullptr;
+  if (stem.cin != UG_NUM_PLANES) { *err = "stem conv expects " + std::to_string(stem.cin) + " input planes, the engine provides 17"; return nullptr; }
+  const int C = stem.cout;
+  if (C % 64 != 0 || C > 256) {
+    *err = "tower width " + std::to_string(C) + " unsupported (multiple of 64, <= 256)";
+    return nullptr;
+  }
+  W->C = C;
+  W->blocks = (int)plan.tower.size() / 2;
+  W->convs.resize(1 + plan.tower.size());
+  if (!make_conv_layer(stem, kCinPad, &W->convs[0], err)) return nullptr;
+  for (size_t i = 0; i < plan.tower.size(); ++i) {
+    HostConv hc;
+    if (!load_conv(ck, plan.tower[i], 3, &hc, err)) return nullptr;
+    if (hc.cin != C || hc.cout != C) { *err = "tower conv '" + plan.tower[i].kernel + "' is not C x C"; return nullptr; }
+    if (!make_conv_layer(hc, C, &W->convs[1 + i], err)) return nullptr;
+  }
+  HostConv pcv, vcv;
+  if (!load_conv(ck, plan.policy_conv, 1, &pcv, err) || !load_conv(ck, plan.value_conv, 1, &vcv, err)) return nullptr;
+  if (pcv.cin != C || vcv.cin != C) { *err = "head 1x1 convs do not take the tower width"; return nullptr; }
+  W->pc = pcv.cout;
+  W->vc = vcv.cout;
+  if (W->pc + W->vc > 8) { *err = "more than 8 head conv channels unsupported"; return nullptr; }
+  std::vector<float> hw((size_t)(W->pc + W->vc) * C), hb(W->pc + W->vc);
+  for (int h = 0; h < W->pc; ++h) {
+    for (int c = 0; c < C; ++c) hw[(size_t)h * C + c] = pcv.w[(size_t)c * W->pc + h];
+    hb[h] = pcv.b[h];
+  }
+  for (int h = 0; h < W->vc; ++h) {
+    for (int c = 0; c < C; ++c) hw[(size_t)(W->pc + h) * C + c] = vcv.w[(size_t)c * W->vc + h];
+    hb[W->pc + h] = vcv.b[h];
+  }
+  std::vector<float> w, b;
+  int od = 0;
+  if (!load_dense(ck, plan.policy_fc, UG_NUM_POINTS * W->pc, &w, &b, &od, err)) return nullptr;
+  if (od != UG_NUM_MOVES) { *err = "policy dense layer has " + std::to_string(od) + " outputs, expected 362"; return nullptr; }
+  bool ok = upload(&W->head_conv_w, hw.data(), hw.size() * 4) && upload(&W->head_conv_b, hb.data(), hb.size() * 4) &&
+            upload(&W->pfc_w, w.data(), w.size() * 4) && upload(&W->pfc_b, b.data(), b.size() * 4);
+  if (!load_dense(ck, plan.value_fc1, UG_NUM_POINTS * W->vc, &w, &b, &od, err)) return nullptr;
+  W->H = od;
+  ok = ok && upload(&W->v1_w, w.data(), w.size() * 4) && upload(&W->v1_b, b.data(), b.size() * 4);
+  if (!load_dense(ck, plan.value_fc2, W->H, &w, &b, &od, err)) return nullptr;
+  if (od != 1) { *err = "value output layer has " + std::to_string(od) + " outputs, expected 1"; return nullptr; }
+  ok = ok && upload(&W->v2_w, w.data(), w.size() * 4) && upload(&W->v2_b, b.data(), b.size() * 4);
+  if (!ok) { *err = "out of device memory uploading head weights"; return nullptr; }
+  W->policy_softmax = plan.policy_softmax;
+  W->value_tanh = plan.value_tanh;
+  return W.release();
+}
+
+bool ends_with(const std::string& s, const char* suf) {
+  const size_t n = strlen(suf);
+  return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+}  // namespace
+}  // namespace ug
+
+using namespace ug;
+
+// ------------------------------------------------------------------------------------------ ug_eval members
+ug_eval::~ug_eval() {
+  if (stream) cudaStreamSynchronize(stream);
+  drop_graphs();
+  delete weights;
+  if (h_pinned) cudaFreeHost(h_pinned);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+void ug_eval::drop_graphs() {
+  for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+  graphs.clear();
+}
+
+bool ug_eval::ensure_workspace(int C) {
+  if (ws_C == C) return true;
+  drop_graphs();
+  const size_t nb = (size_t)max_batch;
+  const size_t act_elems = nb * UG_NUM_POINTS * C;
+  bool ok = d_pos.alloc(nb * sizeof(ug_packed_pos)) && d_legal.alloc(nb * UG_MASK_WORDS * 4) &&
+            d_planes.alloc(nb * UG_NUM_PLANES * UG_NUM_POINTS) && d_bytes.alloc(nb * UG_NUM_PLANES * UG_NUM_POINTS) &&
+            d_in.alloc(nb * UG_NUM_POINTS * kCinPad * 2) && d_feat.alloc(nb * UG_NUM_POINTS * 8 * 4) &&
+            d_policy.alloc(nb * UG_NUM_MOVES * 4) && d_value.alloc(nb * 4);
+  for (int i = 0; i < 3 && ok; ++i) ok = d_act[i].alloc(act_elems * 2);
+  if (ok && precision == UG_PREC_FP32) {
+    ok = f_in.alloc(nb * UG_NUM_POINTS * UG_NUM_PLANES * 4);
+    for (int i = 0; i < 3 && ok; ++i) ok = f_act[i].alloc(act_elems * 4);
+  }
+  if (!ok) { last_error = "out of device memory allocating the workspace"; return false; }
+  // zero once so that rows past n (read by the tail tile) are finite
+  cudaMemset(d_in.p, 0, d_in.bytes);
+  for (int i = 0; i < 3; ++i) cudaMemset(d_act[i].p, 0, d_act[i].bytes);
+  std::string err;
+  if (!make_tmap_act_im2col(&tm_in, d_in.p, max_batch, kCinPad, 32, &err)) { last_error = err; return false; }
+  for (int i = 0; i < 3; ++i)
+    if (!make_tmap_act_im2col(&tm_act[i], d_act[i].p, max_batch, C, 64, &err)) { last_error = err; return false; }
+  if (!h_pinned) {
+    h_pinned_bytes = nb * (sizeof(ug_packed_pos) + UG_MASK_WORDS * 4 + UG_NUM_PLANES * UG_NUM_POINTS +
+                           (UG_NUM_MOVES + 1) * 4) + 256;
+    if (cudaMallocHost(&h_pinned, h_pinned_bytes) != cudaSuccess) {
+      h_pinned = nullptr;
+      last_error = "cannot allocate pinned staging memory";
+      return false;
+    }
+  }
+  ws_C = C;
+  return true;
+}
+
+int ug_eval::enqueue_encoder(Src kind, const void* d_src, int n, cudaStream_t s) {
+  __nv_bfloat16* in = d_in.as<__nv_bfloat16>();
+  if (kind == SRC_PACKED) launch_encode_packed_nhwc(static_cast<const ug_packed_pos*>(d_src), in, n, s);
+  else launch_planes_to_nhwc(static_cast<const int8_t*>(d_src), kind == SRC_HWC ? 1 : 0, in, n, s);
+  return 0;
+}
+
+int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act) {
+  const Weights& W = *weights;
+  const int C = W.C;
+  if (precision == UG_PREC_FP32) {
+    launch_nhwc_to_f32(d_in.as<__nv_bfloat16>(), f_in.as<float>(), n, s);
+    const ConvLayer& st = W.convs[0];
+    launch_conv3x3_f32(f_in.as<float>(), st.w_f32.as<float>(), st.bias.as<float>(), nullptr, f_act[0].as<float>(),
+                       n, UG_NUM_PLANES, C, 1, s);
+    int x = 0;
+    for (int b = 0; b < W.blocks; ++b) {
+      const int t = (x + 1) % 3, y = (x + 2) % 3;
+      const ConvLayer& c1 = W.convs[1 + 2 * b];
+      const ConvLayer& c2 = W.convs[2 + 2 * b];
+      launch_conv3x3_f32(f_act[x].as<float>(), c1.w_f32.as<float>(), c1.bias.as<float>(), nullptr,
+                         f_act[t].as<float>(), n, C, C, 1, s);
+      launch_conv3x3_f32(f_act[t].as<float>(), c2.w_f32.as<float>(), c2.bias.as<float>(), f_act[x].as<float>(),
+                         f_act[y].as<float>(), n, C, C, 1, s);
+      x = y;
+    }
+    *final_act = f_act[x].p;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
+  const int ctas = conv_ctas;
+  ConvArgs a{};
+  a.M = n * UG_NUM_POINTS;
+  a.relu = 1;
+  a.cout = C;
+  // stem: 32 stored input channels (17 planes + zeros), SWIZZLE_64B tiles
+  a.cin = kCinPad;
+  a.bias = W.convs[0].bias.as<float>();
+  a.residual = nullptr;
+  a.out = d_act[0].as<__nv_bfloat16>();
+  cudaError_t e = conv3x3_tc_launch(tm_in, W.convs[0].tm_w[ctas - 1], a, 32, ctas, sms, s);
+  if (e != cudaSuccess) return fail(-1, std::string("stem conv launch: ") + cudaGetErrorString(e));
+  int x = 0;
+  a.cin = C;
+  for (int b = 0; b < W.blocks; ++b) {
+    const int t = (x + 1) % 3, y = (x + 2) % 3;
+    const ConvLayer& c1 = W.convs[1 + 2 * b];
+    const ConvLayer& c2 = W.convs[2 + 2 * b];
+    a.bias = c1.bias.as<float>();
+    a.residual = nullptr;
+    a.out = d_act[t].as<__nv_bfloat16>();
+    e = conv3x3_tc_launch(tm_act[x], c1.tm_w[ctas - 1], a, 64, ctas, sms, s);
+    if (e != cudaSuccess) return fail(-1, std::string("tower conv launch: ") + cudaGetErrorString(e));
+    a.bias = c2.bias.as<float>();
+    a.residual = d_act[x].as<__nv_bfloat16>();
+    a.out = d_act[y].as<__nv_bfloat16>();
+    e = conv3x3_tc_launch(tm_act[t], c2.tm_w[ctas - 1], a, 64, ctas, sms, s);
+    if (e != cudaSuccess) return fail(-1, std::string("tower conv launch: ") + cudaGetErrorString(e));
+    x = y;
+  }
+  *final_act = d_act[x].p;
+  return 0;
+}
+
+int ug_eval::enqueue_heads(const void* act, int n, const uint32_t* d_leg, int vt, float* d_pol, float* d_val,
+                           cudaStream_t s) {
+  const HeadWeights hw = weights->head();
+  launch_head_conv(act, precision == UG_PREC_FP32 ? 1 : 0, hw, d_feat.as<float>(), n, s);
+  launch_head_fc(d_feat.as<float>(), hw, d_leg, vt, d_pol, d_val, n, s);
+  return cudaGetLastError() == cudaSuccess ? 0 : fail(-1, "head kernel launch failed");
+}
+
+int ug_eval::enqueue_raw(Src kind, const void* d_src, int n, const uint32_t* d_leg, int vt, float* d_pol,
+                         float* d_val, cudaStream_t s) {
+  int rc = enqueue_encoder(kind, d_src, n, s);
+  if (rc) return rc;
+  const void* act = nullptr;
+  rc = enqueue_tower(n, s, &act);
+  if (rc) return rc;
+  return enqueue_heads(act, n, d_leg, vt, d_pol, d_val, s);
+}
+
+int ug_eval::enqueue(Src kind, const void* d_src, int n, const uint32_t* d_leg, int vt, float* d_pol,
+                     float* d_val, cudaStream_t s) {
+  if (!weights) return fail(-1, "no network loaded (LoadGraph + UpdateCheckPoint first)");
+  if (n <= 0 || n > max_batch) return fail(-1, "batch size " + std::to_string(n) + " outside [1, max_batch]");
+  if (!use_graphs) return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
+  const GraphKey key((int)kind, n, d_src, (const void*)d_leg, (const void*)d_pol, (const void*)d_val, vt,
+                     conv_ctas * 4 + precision);
+  auto it = graphs.find(key);
+  if (it == graphs.end()) {
+    if (graphs.size() > 256) drop_graphs();
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+      return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
+    const int rc = enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
+    const cudaError_t ee = cudaStreamEndCapture(s, &g);
+    if (rc != 0 || ee != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      return rc ? rc : fail(-1, std::string("graph capture failed: ") + cudaGetErrorString(ee));
+    }
+    cudaGraphExec_t ex = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) return fail(-1, std::string("graph instantiate failed: ") + cudaGetErrorString(ie));
+    it = graphs.emplace(key, ex).first;
+  }
+  const cudaError_t le = cudaGraphLaunch(it->second, s);
+  return le == cudaSuccess ? 0 : fail(-1, std::string("graph launch failed: ") + cudaGetErrorString(le));
+}
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* ug_version(void) { return "ugeval sm_100a " __DATE__; }
+
+uint32_t ug_crc32c(const void* p, size_t n) { return ug::crc32c(static_cast<const uint8_t*>(p), n); }
+
+const char* ug_last_error(const ug_eval* h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+
+ug_eval* ug_eval_create(int device, int precision, int max_batch) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    g_create_error = "no CUDA device: libugeval has no CPU fallback";
+    return nullptr;
+  }
+  if (device < 0 || device >= count) { g_create_error = "bad device ordinal"; return nullptr; }
+  if (precision != UG_PREC_BF16 && precision != UG_PREC_FP32) { g_create_error = "bad precision"; return nullptr; }
+  if (max_batch <= 0 || max_batch > 65536) { g_create_error = "max_batch outside [1, 65536]"; return nullptr; }
+  cudaDeviceProp prop;
+  cudaSetDevice(device);
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+    g_create_error = "device is not sm_100 (Blackwell B200): this library is built for sm_100a only";
+    return nullptr;
+  }
+  ug_eval* h = new ug_eval();
+  h->device = device;
+  h->precision = precision;
+  h->max_batch = max_batch;
+  h->sms = prop.multiProcessorCount;
+  const char* ng = getenv("UGEVAL_NO_GRAPH");
+  h->use_graphs = !(ng && ng[0] == '1');
+  const char* cc = getenv("UGEVAL_CONV_CTAS");
+  if (cc && (cc[0] == '1' || cc[0] == '2')) h->conv_ctas = cc[0] - '0';
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_error = "cannot create stream";
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+
+void ug_eval_destroy(ug_eval* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  delete h;
+}
+
+int ug_eval_set_io(ug_eval* h, const char* input, const char* const* outputs, int n_outputs) {
+  if (!h) return -1;
+  if (input) h->input_name = input;
+  if (outputs) {
+    h->outputs.clear();
+    for (int i = 0; i < n_outputs; ++i) h->outputs.emplace_back(outputs[i] ? outputs[i] : "");
+  }
+  h->plan_ready = false;
+  return 0;
+}
+
+static int rebuild_plan(ug_eval* h) {
+  if (h->outputs.size() < 2) return h->fail(-1, "nn_outputs must name the policy and the value node");
+  std::string err;
+  if (!build_net_plan(h->graph, h->input_name, h->outputs[0], h->outputs[1], &h->plan, &err))
+    return h->fail(-1, "unsupported graph: " + err);
+  h->plan_ready = true;
+  return 0;
+}
+
+int ug_eval_load_graph(ug_eval* h, const char* path) {
+  if (!h) return -1;
+  const std::string p = path ? path : "";
+  const bool meta = ends_with(p, ".meta");
+  const bool pb = ends_with(p, ".pb");
+  if (!meta && !pb) return 1;  // reference: LoadGraph returns false for any other suffix (.cc:77-83)
+  std::vector<uint8_t> bytes;
+  if (!read_file(p, &bytes)) return h->fail(-1, "Error reading graph definition from " + p);
+  std::string err;
+  TfGraph g;
+  if (!parse_tf_graph(bytes, meta, &g, &err)) return h->fail(-1, "Error reading graph definition from " + p + ": " + err);
+  h->graph = std::move(g);
+  h->graph_loaded = true;
+  h->plan_ready = false;
+  const int rc = rebuild_plan(h);
+  if (rc) { h->graph_loaded = false; return rc; }
+  return 0;
+}
+
+int ug_eval_load_checkpoint(ug_eval* h, const char* prefix) {
+  if (!h) return 1;
+  if (prefix && prefix[0]) h->ckpt_prefix = prefix;
+  if (h->ckpt_prefix.empty()) return h->fail(1, "empty checkpoint path");
+  if (!h->graph_loaded) return h->fail(1, "UpdateCheckPoint before LoadGraph");
+  if (!h->plan_ready && rebuild_plan(h) != 0) return 1;
+  cudaSetDevice(h->device);
+  std::string err;
+  TfBundle ck;
+  if (!ck.open(h->ckpt_prefix, &err)) return h->fail(1, err);
+  Weights* W = build_weights(h->plan, ck, &err);
+  if (!W) return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err);
+  if (!h->ensure_workspace(W->C)) { delete W; return 1; }
+  cudaStreamSynchronize(h->stream);
+  h->drop_graphs();  // graphs bake weight pointers
+  delete h->weights;
+  h->weights = W;
+  return 0;
+}
+
+int ug_eval_ready(const ug_eval* h) { return h && h->graph_loaded ? 1 : 0; }
+int ug_eval_has_weights(const ug_eval* h) { return h && h->weights ? 1 : 0; }
+
+int ug_eval_set_value_transform(ug_eval* h, int vt) {
+  if (!h) return -1;
+  h->value_transform = (vt == UG_TR_FLIP_SIGN || vt == UG_TR_FLIP_PROB) ? vt : UG_TR_IDENTITY;
+  return 0;
+}
+
+int ug_eval_set_conv_ctas(ug_eval* h, int ctas) {
+  if (!h || (ctas != 1 && ctas != 2)) return -1;
+  h->conv_ctas = ctas;
+  return 0;
+}
+
+int ug_eval_info(const ug_eval* h, ug_net_info* out) {
+  if (!h || !out || !h->weights) return -1;
+  const Weights& W = *h->weights;
+  out->blocks = W.blocks;
+  out->filters = W.C;
+  out->policy_channels = W.pc;
+  out->value_channels = W.vc;
+  out->value_hidden = W.H;
+  out->input_planes = UG_NUM_PLANES;
+  const double C = W.C, P = UG_NUM_POINTS;
+  out->flops_per_position = 2 * P * 9 * 17 * C + W.blocks * 2.0 * (2 * P * 9 * C * C) + 2 * P * C * W.pc +
+                            2.0 * (P * W.pc) * UG_NUM_MOVES + 2 * P * C * W.vc + 2.0 * (P * W.vc) * W.H + 2.0 * W.H;
+  out->conv_ctas = h->conv_ctas;
+  out->sm_count = h->sms;
+  return 0;
+}
+
+int ug_eval_sync(ug_eval* h) {
+  if (!h) return -1;
+  const cudaError_t e = cudaStreamSynchronize(h->stream);
+  return e == cudaSuccess ? 0 : h->fail(-1, std::string("CUDA error: ") + cudaGetErrorString(e));
+}
+
+// shared by the two reference-facing overloads
+static int run_planes_common(ug_eval* h, const int8_t* planes, int hwc, int n, double* policy, double* value) {
+  if (!h) return -1;
+  if (!h->weights) return h->fail(-1, "Running model failed: no network loaded");
+  if (n <= 0 || n > h->max_batch) return h->fail(-1, "Running model failed: bad batch size");
+  cudaSetDevice(h->device);
+  const size_t in_bytes = (size_t)n * UG_NUM_PLANES * UG_NUM_POINTS;
+  uint8_t* stage = static_cast<uint8_t*>(h->h_pinned);
+  float* out_stage = reinterpret_cast<float*>(stage + (((size_t)h->max_batch * UG_NUM_PLANES * UG_NUM_POINTS + 255) & ~size_t(255)));
+  memcpy(stage, planes, in_bytes);
+  cudaStream_t s = h->stream;
+  cudaMemcpyAsync(h->d_planes.p, stage, in_bytes, cudaMemcpyHostToDevice, s);
+  // value_transform is applied below in double, exactly as the reference does after widening (.cc:298-310)
+  int rc = h->enqueue(hwc ? ug_eval::SRC_HWC : ug_eval::SRC_CHW, h->d_planes.p, n, nullptr, UG_TR_IDENTITY,
+                      h->d_policy.as<float>(), h->d_value.as<float>(), s);
+  if (rc) return rc;
+  cudaMemcpyAsync(out_stage, h->d_policy.p, (size_t)n * UG_NUM_MOVES * 4, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(out_stage + (size_t)n * UG_NUM_MOVES, h->d_value.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s);
+  const cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return h->fail(-1, std::string("Running model failed: ") + cudaGetErrorString(e));
+  for (size_t i = 0; i < (size_t)n * UG_NUM_MOVES; ++i) policy[i] = (double)out_stage[i];  // DlTensorUtil::GetValue
+  const float* v = out_stage + (size_t)n * UG_NUM_MOVES;
+  for (int i = 0; i < n; ++i) {
+    double d = (double)v[i];
+    if (h->value_transform == UG_TR_FLIP_SIGN) d = -d;
+    else if (h->value_transform == UG_TR_FLIP_PROB) d = 1 - d;
+    value[i] = d;
+  }
+  return 0;
+}
+
+int ug_eval_run_planes(ug_eval* h, const int8_t* chw, int n, double* policy, double* value) {
+  return run_planes_common(h, chw, 0, n, policy, value);
+}
+int ug_eval_run_planes_hwc(ug_eval* h, const int8_t* hwc, int n, double* policy, double* value) {
+  return run_planes_common(h, hwc, 1, n, policy, value);
+}
+
+int ug_eval_run_packed(ug_eval* h, const ug_packed_pos* pos, int n, const uint32_t* legal, float* policy,
+                       float* value) {
+  if (!h) return -1;
+  if (!h->weights) return h->fail(-1, "no network loaded");
+  if (n <= 0 || n > h->max_batch) return h->fail(-1, "bad batch size");
+  cudaSetDevice(h->device);
+  uint8_t* stage = static_cast<uint8_t*>(h->h_pinned);
+  const size_t pos_bytes = (size_t)n * sizeof(ug_packed_pos);
+  const size_t legal_off = (size_t)h->max_batch * sizeof(ug_packed_pos);
+  const size_t out_off = legal_off + (size_t)h->max_batch * UG_MASK_WORDS * 4;
+  memcpy(stage, pos, pos_bytes);
+  cudaStream_t s = h->stream;
+  cudaMemcpyAsync(h->d_pos.p, stage, pos_bytes, cudaMemcpyHostToDevice, s);
+  const uint32_t* d_legal = nullptr;
+  if (legal) {
+    memcpy(stage + legal_off, legal, (size_t)n * UG_MASK_WORDS * 4);
+    cudaMemcpyAsync(h->d_legal.p, stage + legal_off, (size_t)n * UG_MASK_WORDS * 4, cudaMemcpyHostToDevice, s);
+    d_legal = h->d_legal.as<uint32_t>();
+  }
+  int rc = h->enqueue(ug_eval::SRC_PACKED, h->d_pos.p, n, d_legal, h->value_transform, h->d_policy.as<float>(),
+                      h->d_value.as<float>(), s);
+  if (rc) return rc;
+  float* out_stage = reinterpret_cast<float*>(stage + out_off);
+  cudaMemcpyAsync(out_stage, h->d_policy.p, (size_t)n * UG_NUM_MOVES * 4, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(out_stage + (size_t)n * UG_NUM_MOVES, h->d_value.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s);
+  const cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return h->fail(-1, std::string("CUDA error: ") + cudaGetErrorString(e));
+  memcpy(policy, out_stage, (size_t)n * UG_NUM_MOVES * 4);
+  memcpy(value, out_stage + (size_t)n * UG_NUM_MOVES, (size_t)n * 4);
+  return 0;
+}
+
+int ug_eval_run_packed_device(ug_eval* h, const ug_packed_pos* d_pos, int n, const uint32_t* d_legal,
+                              float* d_policy, float* d_value, void* stream) {
+  if (!h) return -1;
+  cudaSetDevice(h->device);
+  cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  return h->enqueue(ug_eval::SRC_PACKED, d_pos, n, d_legal, h->value_transform, d_policy, d_value, s);
+}
+
+// ---- encoder hooks
+static int encode_common(ug_eval* h, int what, const void* src, size_t src_bytes, int n, int8_t* out) {
+  if (!h) return -1;
+  if (n <= 0 || n > h->max_batch) return h->fail(-1, "bad batch size");
+  cudaSetDevice(h->device);
+  if (!h->ensure_workspace(h->ws_C ? h->ws_C : 64)) return -1;
+  cudaStream_t s = h->stream;
+  const size_t out_bytes = (size_t)n * UG_NUM_PLANES * UG_NUM_POINTS;
+  void* d_src = (what == 2) ? h->d_planes.p : h->d_pos.p;
+  cudaMemcpyAsync(d_src, src, src_bytes, cudaMemcpyHostToDevice, s);
+  if (what == 0) {
+    launch_encode_packed_chw(h->d_pos.as<ug_packed_pos>(), h->d_bytes.as<int8_t>(), n, s);
+  } else {
+    if (what == 1) launch_encode_packed_nhwc(h->d_pos.as<ug_packed_pos>(), h->d_in.as<__nv_bfloat16>(), n, s);
+    else launch_planes_to_nhwc(h->d_planes.as<int8_t>(), 0, h->d_in.as<__nv_bfloat16>(), n, s);
+    launch_nhwc_to_bytes(h->d_in.as<__nv_bfloat16>(), h->d_bytes.as<int8_t>(), n, s);
+  }
+  cudaMemcpyAsync(out, h->d_bytes.p, out_bytes, cudaMemcpyDeviceToHost, s);
+  const cudaError_t e = cudaStreamSynchronize(s);
+  return e == cudaSuccess ? 0 : h->fail(-1, std::string("CUDA error: ") + cudaGetErrorString(e));
+}
+int ug_encode_planes(ug_eval* h, const ug_packed_pos* pos, int n, int8_t* chw_out) {
+  return encode_common(h, 0, pos, (size_t)n * sizeof(ug_packed_pos), n, chw_out);
+}
+int ug_encode_nhwc(ug_eval* h, const ug_packed_pos* pos, int n, int8_t* hwc_out) {
+  return encode_common(h, 1, pos, (size_t)n * sizeof(ug_packed_pos), n, hwc_out);
+}
+int ug_transform_planes(ug_eval* h, const int8_t* chw, int n, int8_t* hwc_out) {
+  return encode_common(h, 2, chw, (size_t)n * UG_NUM_PLANES * UG_NUM_POINTS, n, hwc_out);
+}
+
+int ug_eval_debug_layer(ug_eval* h, int layer, int n, float* out) {
+  if (!h || !h->weights) return -1;
+  const Weights& W = *h->weights;
+  if (layer < 0 || layer > 2 * W.blocks || n <= 0 || n > h->max_batch) return h->fail(-1, "bad layer or n");
+  // re-run the tower up to `layer` is unnecessary: buffers rotate x -> (x+2)%3 per block, recompute the index
+  int idx = 0;
+  if (layer > 0) {
+    int x = 0;
+    for (int b = 0; b < W.blocks; ++b) {
+      const int t = (x + 1) % 3, y = (x + 2) % 3;
+      if (layer == 1 + 2 * b) { idx = t; break; }
+      if (layer == 2 + 2 * b) { idx = y; break; }
+      x = y;
+    }
+  }
+  cudaSetDevice(h->device);
+  const size_t count = (size_t)n * UG_NUM_POINTS * W.C;
+  cudaStream_t s = h->stream;
+  if (h->precision == UG_PREC_FP32) {
+    cudaMemcpyAsync(out, h->f_act[idx].p, count * 4, cudaMemcpyDeviceToHost, s);
+  } else {
+    DevBuf tmp;
+    if (!tmp.alloc(count * 4)) return h->fail(-1, "out of memory");
+    launch_bf16_to_f32(h->d_act[idx].as<__nv_bfloat16>(), tmp.as<float>(), count, s);
+    cudaMemcpyAsync(out, tmp.p, count * 4, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+  }
+  const cudaError_t e = cudaStreamSynchronize(s);
+  return e == cudaSuccess ? W.C : h->fail(-1, std::string("CUDA error: ") + cudaGetErrorString(e));
+}
+
+int ug_eval_bench(ug_eval* h, const ug_packed_pos* host_pos, int n, int iters, ug_bench_result* out) {
+  if (!h || !out) return -1;
+  if (!h->weights) return h->fail(-1, "no network loaded");
+  if (n <= 0 || n > h->max_batch || iters <= 0) return h->fail(-1, "bad arguments");
+  cudaSetDevice(h->device);
+  cudaStream_t s = h->stream;
+  cudaMemcpyAsync(h->d_pos.p, host_pos, (size_t)n * sizeof(ug_packed_pos), cudaMemcpyHostToDevice, s);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  auto timed = [&](const std::function<int()>& body, float* ms_avg) -> int {
+    int rc = body();  // warm
+    if (rc) return rc;
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < iters && rc == 0; ++i) rc = body();
+    cudaEventRecord(e1, s);
+    if (cudaEventSynchronize(e1) != cudaSuccess) return h->fail(-1, "CUDA error in bench");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_avg = ms / iters;
+    return rc;
+  };
+  float full = 0.f;
+  int rc = timed([&] { return h->enqueue(ug_eval::SRC_PACKED, h->d_pos.p, n, nullptr, h->value_transform,
+                                         h->d_policy.as<float>(), h->d_value.as<float>(), s); }, &full);
+  const void* act = nullptr;
+  if (!rc) rc = timed([&] { return h->enqueue_encoder(ug_eval::SRC_PACKED, h->d_pos.p, n, s); }, &out->ms_encoder);
+  if (!rc) rc = timed([&] { return h->enqueue_tower(n, s, &act); }, &out->ms_tower);
+  if (!rc) rc = timed([&] { return h->enqueue_heads(act, n, nullptr, h->value_transform, h->d_policy.as<float>(),
+                                                    h->d_value.as<float>(), s); }, &out->ms_heads);
+  out->ms_total = full * iters;
+  out->launches_per_pass = 1 + (h->precision == UG_PREC_FP32 ? 1 : 0) + 1 + 2 * h->weights->blocks + 2;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
+}
+
+int ug_k_conv3x3_bf16(int device, const void* d_in, const void* d_w, const float* d_bias, const void* d_res,
+                      void* d_out, int n, int cin, int cout, int relu, int ck, int ctas) {
+  cudaSetDevice(device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+  std::string err;
+  CUtensorMap ta, tb;
+  if (!make_tmap_act_im2col(&ta, d_in, n, cin, ck, &err)) { g_create_error = err; return -2; }
+  if (!make_tmap_weights(&tb, d_w, cout, 9 * cin, ck, cout / ctas, &err)) { g_create_error = err; return -3; }
+  ConvArgs a{};
+  a.bias = d_bias;
+  a.residual = static_cast<const __nv_bfloat16*>(d_res);
+  a.out = static_cast<__nv_bfloat16*>(d_out);
+  a.M = n * UG_NUM_POINTS;
+  a.cin = cin;
+  a.cout = cout;
+  a.relu = relu;
+  cudaError_t e = conv3x3_tc_launch(ta, tb, a, ck, ctas, prop.multiProcessorCount, 0);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return -4; }
+  return 0;
+}
+
+}  // extern "C"

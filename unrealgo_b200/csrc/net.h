@@ -1,0 +1,103 @@
+// The evaluator object behind the C ABI: graph plan + resident weights + workspace + launch sequence.
+// Host-side mirror of tensorflow::DlTFNetworkEvaluator<T> (funcapproximator/DlTFNetworkEvaluator.h:33-83).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/ugeval.h"
+#include "kernels.h"
+#include "tfmodel.h"
+
+namespace ug {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  bool alloc(size_t n);
+  void release();
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct ConvLayer {
+  int cin = 0, cin_pad = 0, cout = 0;
+  DevBuf w_bf16;   // [cout][9*cin_pad] K-major, batch-norm folded
+  DevBuf w_f32;    // [3][3][cin][cout] folded (fp32 validation path)
+  DevBuf bias;     // [cout] fp32
+  CUtensorMap tm_w[2];  // index = ctas-1 (box rows differ)
+};
+
+struct Weights {
+  int blocks = 0, C = 0, pc = 0, vc = 0, H = 0;
+  bool policy_softmax = true, value_tanh = true;
+  std::vector<ConvLayer> convs;  // [0] stem, then 2 per block
+  DevBuf head_conv_w, head_conv_b, pfc_w, pfc_b, v1_w, v1_b, v2_w, v2_b;
+  HeadWeights head() const;
+};
+
+}  // namespace ug
+
+struct ug_eval {
+  int device = 0;
+  int precision = UG_PREC_BF16;
+  int max_batch = 0;
+  int sms = 148;
+  int conv_ctas = 2;
+  int value_transform = UG_TR_IDENTITY;
+  bool use_graphs = true;
+  mutable std::string last_error;
+
+  std::string input_name = "feature_input";
+  std::vector<std::string> outputs = {"resnet/tower_0/policy_head/policy_predict",
+                                      "resnet/tower_0/value_head/reward_predict"};
+  std::string ckpt_prefix = "bootstrap-ckpt";
+  bool graph_loaded = false;
+  bool plan_ready = false;
+  ug::TfGraph graph;
+  ug::NetPlan plan;
+  ug::Weights* weights = nullptr;  // swapped atomically by load_checkpoint
+
+  cudaStream_t stream = nullptr;
+  // workspace (allocated once the architecture is known)
+  int ws_C = 0;
+  ug::DevBuf d_pos, d_legal, d_planes, d_in, d_act[3], d_feat, d_policy, d_value, d_bytes;
+  ug::DevBuf f_in, f_act[3];
+  CUtensorMap tm_in, tm_act[3];
+  void* h_pinned = nullptr;  // staging for host-buffer entry points
+  size_t h_pinned_bytes = 0;
+
+  // cuda graphs keyed by (kind, n, legal?, ctas, pointers)
+  typedef std::tuple<int, int, const void*, const void*, const void*, const void*, int, int> GraphKey;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+
+  ~ug_eval();
+  int fail(int code, const std::string& msg) const { last_error = msg; return code; }
+  bool ensure_workspace(int C);
+  void drop_graphs();
+  // source kinds for enqueue()
+  enum Src { SRC_PACKED = 0, SRC_CHW = 1, SRC_HWC = 2 };
+  // enqueue encoder + tower + heads on `s`; all pointers are device pointers
+  int enqueue(Src kind, const void* d_src, int n, const uint32_t* d_legal, int vt, float* d_policy,
+              float* d_value, cudaStream_t s);
+  int enqueue_raw(Src kind, const void* d_src, int n, const uint32_t* d_legal, int vt, float* d_policy,
+                  float* d_value, cudaStream_t s);
+  int enqueue_encoder(Src kind, const void* d_src, int n, cudaStream_t s);
+  int enqueue_tower(int n, cudaStream_t s, const void** final_act);
+  int enqueue_heads(const void* act, int n, const uint32_t* d_legal, int vt, float* d_policy, float* d_value,
+                    cudaStream_t s);
+};

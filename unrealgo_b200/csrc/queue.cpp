@@ -1,0 +1,328 @@
+// Q1 — leaf-batching queue.
+//
+// Replaces the reference's hand-off between search threads and the evaluator:
+//   producer: UctSearch::ExpandAndBackup writes EvalBuffer::feature_buf[threadId], raises state_ready and
+//             blocks on a per-thread condvar (search/UctSearch.cpp:511-520, :88-91);
+//   consumer: NetworkEvalThread spins, always evaluates all num_threads slots, and marks whichever slots
+//             are ready *after* the evaluation as evaluated (search/UctSearch.cpp:164-205) — a slot that
+//             became ready mid-evaluation gets a stale result, and the batch is capped at MAX_BATCHES=16.
+// Here: a bounded multi-producer ring with per-slot sequence numbers (claim = one fetch_add, no lock), a
+// gather thread that snapshots *published* leaves only (so every ticket gets exactly its own result), flushes
+// on max_batch or timeout, and double-buffered pinned staging: the H2D copy of batch k+1 and the D2H copy of
+// batch k-1 run on their own streams while batch k is in the tower.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "net.h"
+
+namespace {
+
+struct Slot {
+  std::atomic<uint64_t> seq;   // == ticket: free for that ticket; ticket+1: published; ticket+2: result ready
+  ug_packed_pos pos;
+  uint32_t legal[UG_MASK_WORDS];
+  uint32_t has_legal;
+  float policy[UG_NUM_MOVES];
+  float value;
+};
+
+struct Staging {
+  ug_packed_pos* h_pos = nullptr;   // pinned
+  uint32_t* h_legal = nullptr;      // pinned
+  float* h_out = nullptr;           // pinned: policy[n][362] then value[n]
+  ug_packed_pos* d_pos = nullptr;
+  uint32_t* d_legal = nullptr;
+  float* d_policy = nullptr;
+  float* d_value = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+  uint64_t first_ticket = 0;
+  int n = 0;
+  bool any_legal = false;
+  bool busy = false;
+};
+
+inline void cpu_relax() {
+#if defined(__x86_64__)
+  __builtin_ia32_pause();
+#endif
+}
+
+}  // namespace
+
+struct ug_queue {
+  ug_eval* eval = nullptr;
+  int max_batch = 0;
+  int timeout_us = 0;
+  uint64_t capacity = 0, mask = 0;
+  std::vector<Slot> slots;
+  std::atomic<uint64_t> tail{0};   // next ticket to hand out
+  uint64_t head = 0;               // next ticket to gather (gather thread only)
+  Staging st[2];
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::thread gather_thread, complete_thread;
+  std::mutex mu;                    // protects inflight, st[].busy, paused
+  std::condition_variable cv_inflight, cv_free, cv_results, cv_pause;
+  std::deque<int> inflight;         // staging indices in submission order
+  std::atomic<bool> quit{false};
+  bool pause_req = false, paused = false;
+  std::atomic<uint64_t> n_batches{0}, n_leaves{0}, n_timeouts{0};
+  std::atomic<int> error{0};
+
+  void gather_loop();
+  void complete_loop();
+};
+
+void ug_queue::gather_loop() {
+  cudaSetDevice(eval->device);
+  int which = 0;
+  while (!quit.load(std::memory_order_acquire)) {
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      if (pause_req) {
+        cv_free.wait(lk, [&] { return inflight.empty() || quit.load(); });
+        paused = true;
+        cv_pause.notify_all();
+        cv_pause.wait(lk, [&] { return !pause_req || quit.load(); });
+        paused = false;
+        continue;
+      }
+    }
+    // wait for the first published leaf
+    Slot& first = slots[head & mask];
+    if (first.seq.load(std::memory_order_acquire) != head + 1) {
+      for (int i = 0; i < 64; ++i) cpu_relax();
+      if (first.seq.load(std::memory_order_acquire) != head + 1) {
+        std::this_thread::sleep_for(std::chrono::microseconds(5));
+        continue;
+      }
+    }
+    // a staging buffer must be free before leaves are pulled out of the ring
+    Staging& S = st[which];
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv_free.wait(lk, [&] { return !S.busy || quit.load(); });
+      if (quit.load()) break;
+      S.busy = true;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    int n = 0;
+    bool timed_out = false;
+    S.any_legal = false;
+    S.first_ticket = head;
+    while (n < max_batch) {
+      Slot& sl = slots[(head + n) & mask];
+      if (sl.seq.load(std::memory_order_acquire) == head + n + 1) {
+        memcpy(&S.h_pos[n], &sl.pos, sizeof(ug_packed_pos));
+        if (sl.has_legal) {
+          memcpy(&S.h_legal[(size_t)n * UG_MASK_WORDS], sl.legal, sizeof(sl.legal));
+          S.any_legal = true;
+        } else {
+          memset(&S.h_legal[(size_t)n * UG_MASK_WORDS], 0xff, sizeof(sl.legal));
+        }
+        ++n;
+        continue;
+      }
+      const auto dt = std::chrono::steady_clock::now() - t0;
+      if (std::chrono::duration_cast<std::chrono::microseconds>(dt).count() >= timeout_us) { timed_out = true; break; }
+      cpu_relax();
+    }
+    if (timed_out) n_timeouts.fetch_add(1, std::memory_order_relaxed);
+    S.n = n;
+    head += n;
+    // H2D on the copy-in stream, tower on the evaluator stream, D2H on the copy-out stream
+    cudaMemcpyAsync(S.d_pos, S.h_pos, (size_t)n * sizeof(ug_packed_pos), cudaMemcpyHostToDevice, s_in);
+    if (S.any_legal)
+      cudaMemcpyAsync(S.d_legal, S.h_legal, (size_t)n * UG_MASK_WORDS * 4, cudaMemcpyHostToDevice, s_in);
+    cudaEventRecord(S.ev_in, s_in);
+    cudaStreamWaitEvent(eval->stream, S.ev_in, 0);
+    const int rc = ug_eval_run_packed_device(eval, S.d_pos, n, S.any_legal ? S.d_legal : nullptr, S.d_policy,
+                                             S.d_value, eval->stream);
+    if (rc != 0) error.store(rc);
+    cudaEventRecord(S.ev_done, eval->stream);
+    cudaStreamWaitEvent(s_out, S.ev_done, 0);
+    cudaMemcpyAsync(S.h_out, S.d_policy, (size_t)n * UG_NUM_MOVES * 4, cudaMemcpyDeviceToHost, s_out);
+    cudaMemcpyAsync(S.h_out + (size_t)n * UG_NUM_MOVES, S.d_value, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out);
+    cudaEventRecord(S.ev_out, s_out);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      inflight.push_back(which);
+    }
+    cv_inflight.notify_one();
+    n_batches.fetch_add(1, std::memory_order_relaxed);
+    n_leaves.fetch_add((uint64_t)n, std::memory_order_relaxed);
+    which ^= 1;
+  }
+}
+
+void ug_queue::complete_loop() {
+  cudaSetDevice(eval->device);
+  for (;;) {
+    int which;
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv_inflight.wait(lk, [&] { return !inflight.empty() || quit.load(); });
+      if (inflight.empty()) return;  // quit and drained
+      which = inflight.front();
+    }
+    Staging& S = st[which];
+    if (cudaEventSynchronize(S.ev_out) != cudaSuccess) error.store(-1);
+    for (int i = 0; i < S.n; ++i) {
+      const uint64_t ticket = S.first_ticket + (uint64_t)i;
+      Slot& sl = slots[ticket & mask];
+      memcpy(sl.policy, S.h_out + (size_t)i * UG_NUM_MOVES, sizeof(sl.policy));
+      sl.value = S.h_out[(size_t)S.n * UG_NUM_MOVES + i];
+      sl.seq.store(ticket + 2, std::memory_order_release);
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      inflight.pop_front();
+      S.busy = false;
+    }
+    cv_free.notify_all();
+    cv_results.notify_all();
+  }
+}
+
+extern "C" {
+
+ug_queue* ug_queue_create(ug_eval* h, int max_batch, int timeout_us, int capacity) {
+  if (!h) return nullptr;
+  if (max_batch <= 0 || max_batch > h->max_batch) { h->fail(-1, "queue max_batch exceeds the evaluator's"); return nullptr; }
+  uint64_t cap = 1;
+  while (cap < (uint64_t)(capacity > 2 * max_batch ? capacity : 2 * max_batch)) cap <<= 1;
+  cudaSetDevice(h->device);
+  ug_queue* q = new ug_queue();
+  q->eval = h;
+  q->max_batch = max_batch;
+  q->timeout_us = timeout_us < 0 ? 0 : timeout_us;
+  q->capacity = cap;
+  q->mask = cap - 1;
+  q->slots = std::vector<Slot>(cap);
+  for (uint64_t i = 0; i < cap; ++i) q->slots[i].seq.store(i, std::memory_order_relaxed);
+  bool ok = cudaStreamCreateWithFlags(&q->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&q->s_out, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2 && ok; ++i) {
+    Staging& S = q->st[i];
+    const size_t nb = (size_t)max_batch;
+    ok = cudaMallocHost((void**)&S.h_pos, nb * sizeof(ug_packed_pos)) == cudaSuccess &&
+         cudaMallocHost((void**)&S.h_legal, nb * UG_MASK_WORDS * 4) == cudaSuccess &&
+         cudaMallocHost((void**)&S.h_out, nb * (UG_NUM_MOVES + 1) * 4) == cudaSuccess &&
+         cudaMalloc((void**)&S.d_pos, nb * sizeof(ug_packed_pos)) == cudaSuccess &&
+         cudaMalloc((void**)&S.d_legal, nb * UG_MASK_WORDS * 4) == cudaSuccess &&
+         cudaMalloc((void**)&S.d_policy, nb * UG_NUM_MOVES * 4) == cudaSuccess &&
+         cudaMalloc((void**)&S.d_value, nb * 4) == cudaSuccess &&
+         cudaEventCreateWithFlags(&S.ev_in, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&S.ev_out, cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) {
+    h->fail(-1, "queue: cannot allocate staging buffers");
+    ug_queue_destroy(q);
+    return nullptr;
+  }
+  q->gather_thread = std::thread([q] { q->gather_loop(); });
+  q->complete_thread = std::thread([q] { q->complete_loop(); });
+  return q;
+}
+
+void ug_queue_destroy(ug_queue* q) {
+  if (!q) return;
+  q->quit.store(true, std::memory_order_release);
+  {
+    std::lock_guard<std::mutex> lk(q->mu);
+    q->pause_req = false;
+  }
+  q->cv_free.notify_all();
+  q->cv_pause.notify_all();
+  if (q->gather_thread.joinable()) q->gather_thread.join();
+  q->cv_inflight.notify_all();
+  if (q->complete_thread.joinable()) q->complete_thread.join();
+  q->cv_results.notify_all();
+  cudaSetDevice(q->eval->device);
+  for (int i = 0; i < 2; ++i) {
+    Staging& S = q->st[i];
+    if (S.h_pos) cudaFreeHost(S.h_pos);
+    if (S.h_legal) cudaFreeHost(S.h_legal);
+    if (S.h_out) cudaFreeHost(S.h_out);
+    if (S.d_pos) cudaFree(S.d_pos);
+    if (S.d_legal) cudaFree(S.d_legal);
+    if (S.d_policy) cudaFree(S.d_policy);
+    if (S.d_value) cudaFree(S.d_value);
+    if (S.ev_in) cudaEventDestroy(S.ev_in);
+    if (S.ev_done) cudaEventDestroy(S.ev_done);
+    if (S.ev_out) cudaEventDestroy(S.ev_out);
+  }
+  if (q->s_in) cudaStreamDestroy(q->s_in);
+  if (q->s_out) cudaStreamDestroy(q->s_out);
+  delete q;
+}
+
+int64_t ug_queue_submit(ug_queue* q, const ug_packed_pos* pos, const uint32_t* legal) {
+  if (!q || !pos) return -1;
+  const uint64_t ticket = q->tail.fetch_add(1, std::memory_order_acq_rel);
+  Slot& sl = q->slots[ticket & q->mask];
+  // the slot is ours once the previous lap's owner has consumed its result
+  int spins = 0;
+  while (sl.seq.load(std::memory_order_acquire) != ticket) {
+    if (q->quit.load(std::memory_order_acquire)) return -1;
+    if (++spins < 256) cpu_relax(); else std::this_thread::yield();
+  }
+  memcpy(&sl.pos, pos, sizeof(ug_packed_pos));
+  sl.has_legal = legal ? 1u : 0u;
+  if (legal) memcpy(sl.legal, legal, sizeof(sl.legal));
+  sl.seq.store(ticket + 1, std::memory_order_release);
+  return (int64_t)ticket;
+}
+
+int ug_queue_wait(ug_queue* q, int64_t ticket, float* policy, float* value) {
+  if (!q || ticket < 0) return -1;
+  const uint64_t t = (uint64_t)ticket;
+  Slot& sl = q->slots[t & q->mask];
+  int spins = 0;
+  while (sl.seq.load(std::memory_order_acquire) != t + 2) {
+    if (q->quit.load(std::memory_order_acquire)) return -1;
+    if (++spins < 2000) { cpu_relax(); continue; }
+    std::unique_lock<std::mutex> lk(q->mu);
+    q->cv_results.wait_for(lk, std::chrono::microseconds(200));
+  }
+  if (policy) memcpy(policy, sl.policy, sizeof(sl.policy));
+  if (value) *value = sl.value;
+  sl.seq.store(t + q->capacity, std::memory_order_release);  // free for the next lap
+  return q->error.load() ? -1 : 0;
+}
+
+int ug_queue_stats(ug_queue* q, uint64_t* batches, uint64_t* leaves, uint64_t* flush_timeouts) {
+  if (!q) return -1;
+  if (batches) *batches = q->n_batches.load();
+  if (leaves) *leaves = q->n_leaves.load();
+  if (flush_timeouts) *flush_timeouts = q->n_timeouts.load();
+  return 0;
+}
+
+int ug_queue_swap_checkpoint(ug_queue* q, const char* prefix) {
+  if (!q) return -1;
+  {
+    std::unique_lock<std::mutex> lk(q->mu);
+    q->pause_req = true;
+    q->cv_free.notify_all();
+    q->cv_pause.wait(lk, [&] { return q->paused; });
+  }
+  cudaSetDevice(q->eval->device);
+  const int rc = ug_eval_load_checkpoint(q->eval, prefix);
+  {
+    std::lock_guard<std::mutex> lk(q->mu);
+    q->pause_req = false;
+  }
+  q->cv_pause.notify_all();
+  return rc;
+}
+
+}  // extern "C"

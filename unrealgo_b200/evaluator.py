@@ -1,0 +1,287 @@
+"""Python mirror of the reference's evaluator interface, over the C ABI (include/ugeval.h).
+
+Names, argument meaning and error behaviour follow
+  tensorflow::DlTFNetworkEvaluator<T>  funcapproximator/DlTFNetworkEvaluator.h:33-83, .cc:27-352
+  UctBoardEvaluator                    search/UctBoardEvaluator.cpp:6-33
+  DlConfig                             funcapproximator/DlConfig.cc:13-41, :164-246
+so that the parity tests read like the reference's own call sites.  All arithmetic happens in libugeval.so on
+the GPU; these classes only marshal numpy buffers.
+"""
+import ctypes as C
+import json
+
+import numpy as np
+
+from . import _lib
+from ._lib import (MASK_WORDS, NUM_MOVES, NUM_PLANES, NUM_POINTS, PACKED_POS_BYTES, PREC_BF16, PREC_FP32,  # noqa: F401
+                   TR_FLIP_PROB, TR_FLIP_SIGN, TR_IDENTITY)
+
+DF_HWC, DF_CHW = 0, 1
+MAX_BATCHES = 16  # funcapproximator/DlTFNetworkEvaluator.h:15 (the reference's cap; not a limit here)
+
+
+class DlConfig:
+    """dlcfg-<size> reader (funcapproximator/DlConfig.cc)."""
+
+    def __init__(self, filename):
+        self._lib = _lib.load()
+        self._c = self._lib.ug_dlcfg_open(filename.encode())
+
+    def __del__(self):
+        if getattr(self, "_c", None):
+            self._lib.ug_dlcfg_close(self._c)
+            self._c = None
+
+    def get(self, key, default=""):
+        buf = C.create_string_buffer(4096)
+        self._lib.ug_dlcfg_get(self._c, key.encode(), default.encode(), buf, len(buf))
+        return buf.value.decode()
+
+    def get_metagraph(self):
+        return self.get("meta_graph", "bootstrap-ckpt.meta")
+
+    def default_checkpoint(self):
+        return self.get("checkpoint", "bootstrap-ckpt")
+
+    def get_network_input(self):
+        return self.get("nn_input", "input")
+
+    def get_network_outputs(self):
+        cap, mx = 512, 8
+        buf = C.create_string_buffer(cap * mx)
+        n = self._lib.ug_dlcfg_network_outputs(self._c, buf, cap, mx)
+        return [buf.raw[i * cap:(i + 1) * cap].split(b"\0", 1)[0].decode() for i in range(max(n, 0))]
+
+    def reuse_search_tree(self):
+        return bool(self._lib.ug_dlcfg_reuse_search_tree(self._c))
+
+    def get_value_transform(self):
+        return self._lib.ug_dlcfg_value_transform(self._c)
+
+
+def inspect_model(graph_path, ckpt_prefix=None, input_name=None, outputs=None):
+    """host-only description of a graph (+checkpoint): dict, or raises RuntimeError with the loader's message"""
+    lib = _lib.load()
+    buf = C.create_string_buffer(1 << 22)
+    rc = lib.ug_inspect_model(graph_path.encode(), ckpt_prefix.encode() if ckpt_prefix else None,
+                              input_name.encode() if input_name else None,
+                              outputs[0].encode() if outputs else None, outputs[1].encode() if outputs else None,
+                              buf, len(buf))
+    if rc != 0:
+        raise RuntimeError(buf.value.decode())
+    return json.loads(buf.value.decode())
+
+
+class DlTFNetworkEvaluator:
+    """DlTFNetworkEvaluator<bool>: LoadGraph / UpdateCheckPoint / Evaluate, plus the native packed entry points."""
+
+    def __init__(self, graphPath="", df=DF_HWC, feature_input=None, outputs=None, device=0, precision=PREC_BF16,
+                 max_batch=256):
+        self._lib = _lib.load()
+        self._h = self._lib.ug_eval_create(device, precision, max_batch)
+        if not self._h:
+            raise RuntimeError("ug_eval_create failed: " + (self._lib.ug_last_error(None) or b"").decode())
+        self.max_batch = max_batch
+        self.m_dataFormat = df
+        if feature_input is not None or outputs is not None:
+            self._set_io(feature_input, outputs)
+        self.LoadGraph(graphPath)  # empty path is legal: returns False, object usable later (.cc:77-83)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ug_eval_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _err(self):
+        return (self._lib.ug_last_error(self._h) or b"").decode()
+
+    def _set_io(self, feature_input, outputs):
+        arr = None
+        n = 0
+        if outputs is not None:
+            n = len(outputs)
+            arr = (C.c_char_p * n)(*[o.encode() for o in outputs])
+        self._lib.ug_eval_set_io(self._h, feature_input.encode() if feature_input is not None else None, arr, n)
+
+    def SetNetworkInput(self, name):
+        self._set_io(name, None)
+
+    def SetNetworkOutput(self, outputs):
+        self._set_io(None, list(outputs))
+
+    def LoadGraph(self, graphPath):
+        rc = self._lib.ug_eval_load_graph(self._h, graphPath.encode())
+        if rc < 0:
+            raise RuntimeError(self._err())  # the reference throws std::runtime_error (.cc:91,:132,:158)
+        return rc == 0
+
+    def UpdateCheckPoint(self, checkpointPath=""):
+        return self._lib.ug_eval_load_checkpoint(self._h, checkpointPath.encode()) == 0
+
+    def MetaGraphLoaded(self):
+        return bool(self._lib.ug_eval_ready(self._h))
+
+    def set_value_transform(self, vt):
+        self._lib.ug_eval_set_value_transform(self._h, int(vt))
+
+    def set_conv_ctas(self, ctas):
+        if self._lib.ug_eval_set_conv_ctas(self._h, ctas) != 0:
+            raise ValueError("ctas must be 1 or 2")
+
+    def info(self):
+        ni = _lib.NetInfo()
+        if self._lib.ug_eval_info(self._h, C.byref(ni)) != 0:
+            raise RuntimeError("no network loaded")
+        return {f: getattr(ni, f) for f, _ in _lib.NetInfo._fields_}
+
+    def Evaluate(self, feature, policies_, value_, numBatches=None):
+        """feature: int8 [n][17][19][19] (or [n][19][19][17]); policies_: float64 [n][362]; value_: float64 [n].
+        As in the reference a failed run logs and leaves the outputs untouched (.cc:315-317); returns bool."""
+        feature = np.ascontiguousarray(feature, np.int8)
+        n = feature.shape[0] if numBatches is None else numBatches
+        hwc = feature.ndim == 4 and feature.shape[-1] == NUM_PLANES and feature.shape[1] == 19
+        assert policies_.dtype == np.float64 and value_.dtype == np.float64
+        assert policies_.flags.c_contiguous and value_.flags.c_contiguous
+        fn = self._lib.ug_eval_run_planes_hwc if hwc else self._lib.ug_eval_run_planes
+        rc = fn(self._h, feature.ctypes.data, n, policies_.ctypes.data, value_.ctypes.data)
+        if rc != 0:
+            import sys
+            print("Running model failed:", self._err(), file=sys.stderr)
+        return rc == 0
+
+    def evaluate_packed(self, packed, legal=None):
+        """packed: uint32 [n][196] (ug_packed_pos); legal: optional uint32 [n][12].  -> (float32 [n][362], [n])"""
+        packed = np.ascontiguousarray(packed, np.uint32).reshape(-1, PACKED_POS_BYTES // 4)
+        n = packed.shape[0]
+        pol = np.empty((n, NUM_MOVES), np.float32)
+        val = np.empty(n, np.float32)
+        lp = None
+        if legal is not None:
+            legal = np.ascontiguousarray(legal, np.uint32).reshape(n, MASK_WORDS)
+            lp = legal.ctypes.data
+        rc = self._lib.ug_eval_run_packed(self._h, packed.ctypes.data, n, lp, pol.ctypes.data, val.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(self._err())
+        return pol, val
+
+    def run_packed_device(self, d_pos, n, d_policy, d_value, d_legal=None, stream=None):
+        rc = self._lib.ug_eval_run_packed_device(self._h, d_pos, n, d_legal, d_policy, d_value, stream)
+        if rc != 0:
+            raise RuntimeError(self._err())
+
+    def sync(self):
+        if self._lib.ug_eval_sync(self._h) != 0:
+            raise RuntimeError(self._err())
+
+    # ---- encoder seam (CollectFeatures / TransformFeature)
+    def encode_planes(self, packed):
+        packed = np.ascontiguousarray(packed, np.uint32).reshape(-1, PACKED_POS_BYTES // 4)
+        out = np.empty((packed.shape[0], NUM_PLANES, 19, 19), np.int8)
+        if self._lib.ug_encode_planes(self._h, packed.ctypes.data, packed.shape[0], out.ctypes.data) != 0:
+            raise RuntimeError(self._err())
+        return out
+
+    def encode_nhwc(self, packed):
+        packed = np.ascontiguousarray(packed, np.uint32).reshape(-1, PACKED_POS_BYTES // 4)
+        out = np.empty((packed.shape[0], 19, 19, NUM_PLANES), np.int8)
+        if self._lib.ug_encode_nhwc(self._h, packed.ctypes.data, packed.shape[0], out.ctypes.data) != 0:
+            raise RuntimeError(self._err())
+        return out
+
+    def TransformFeature(self, feature):
+        feature = np.ascontiguousarray(feature, np.int8)
+        out = np.empty((feature.shape[0], 19, 19, NUM_PLANES), np.int8)
+        if self._lib.ug_transform_planes(self._h, feature.ctypes.data, feature.shape[0], out.ctypes.data) != 0:
+            raise RuntimeError(self._err())
+        return out
+
+    def debug_layer(self, layer, n):
+        c = self.info()["filters"]
+        out = np.empty((n, NUM_POINTS, c), np.float32)
+        rc = self._lib.ug_eval_debug_layer(self._h, layer, n, out.ctypes.data)
+        if rc < 0:
+            raise RuntimeError(self._err())
+        return out
+
+    def bench(self, packed, iters):
+        packed = np.ascontiguousarray(packed, np.uint32).reshape(-1, PACKED_POS_BYTES // 4)
+        res = _lib.BenchResult()
+        if self._lib.ug_eval_bench(self._h, packed.ctypes.data, packed.shape[0], iters, C.byref(res)) != 0:
+            raise RuntimeError(self._err())
+        return {f: getattr(res, f) for f, _ in _lib.BenchResult._fields_}
+
+
+class UctBoardEvaluator:
+    """search/UctBoardEvaluator.cpp:6-33 — config -> evaluator wiring + forwarding."""
+
+    def __init__(self, graphPath=None, checkpoint=None, config=None, **kw):
+        if graphPath is None:
+            # default ctor: DlTFNetworkEvaluator<bool>("", DF_HWC) + names from DlConfig (.cpp:6-11)
+            self.m_evaluator = DlTFNetworkEvaluator("", DF_HWC, **kw)
+            if config is not None:
+                self.m_evaluator.SetNetworkInput(config.get_network_input())
+                outs = config.get_network_outputs()
+                self.m_evaluator.SetNetworkOutput(outs)
+                self.m_evaluator.set_value_transform(config.get_value_transform())
+        else:
+            self.m_evaluator = DlTFNetworkEvaluator(graphPath, **kw)
+            if checkpoint:
+                self.m_evaluator.UpdateCheckPoint(checkpoint)
+
+    def LoadGraph(self, graphPath):
+        self.m_evaluator.LoadGraph(graphPath)
+
+    def UpdateCheckPoint(self, checkpoint):
+        self.m_evaluator.UpdateCheckPoint(checkpoint)
+
+    def EvaluateState(self, feature, actions_, value_, numBatches=None):
+        self.m_evaluator.Evaluate(feature, actions_, value_, numBatches)
+
+    def GraphLoaded(self):
+        return self.m_evaluator.MetaGraphLoaded()
+
+
+class LeafQueue:
+    """ug_queue_*: multi-producer leaf batching in front of one evaluator."""
+
+    def __init__(self, evaluator, max_batch, timeout_us=200, capacity=0):
+        self._lib = _lib.load()
+        self._ev = evaluator
+        self._q = self._lib.ug_queue_create(evaluator._h, max_batch, timeout_us, capacity)
+        if not self._q:
+            raise RuntimeError("ug_queue_create failed: " + evaluator._err())
+
+    def close(self):
+        if getattr(self, "_q", None):
+            self._lib.ug_queue_destroy(self._q)
+            self._q = None
+
+    __del__ = close
+
+    def submit(self, packed_row, legal=None):
+        row = np.ascontiguousarray(packed_row, np.uint32)
+        lp = None
+        if legal is not None:
+            legal = np.ascontiguousarray(legal, np.uint32)
+            lp = legal.ctypes.data
+        t = self._lib.ug_queue_submit(self._q, row.ctypes.data, lp)
+        if t < 0:
+            raise RuntimeError("queue closed")
+        return t
+
+    def wait(self, ticket):
+        pol = np.empty(NUM_MOVES, np.float32)
+        val = C.c_float()
+        if self._lib.ug_queue_wait(self._q, ticket, pol.ctypes.data, C.byref(val)) != 0:
+            raise RuntimeError("queue evaluation failed: " + self._ev._err())
+        return pol, val.value
+
+    def stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._lib.ug_queue_stats(self._q, C.byref(a), C.byref(b), C.byref(c))
+        return {"batches": a.value, "leaves": b.value, "flush_timeouts": c.value}
+
+    def swap_checkpoint(self, prefix):
+        return self._lib.ug_queue_swap_checkpoint(self._q, prefix.encode()) == 0
