@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py — positions/s of the batched network-evaluation path (BASELINE.json metric) on N B200s.
+
+A "step" is one pass of the hot path (GPU encoder -> 41 tcgen05 convs -> heads) over one batch of 256 synthetic
+positions on the 20-block x 256-filter net (BASELINE.json configs[1]), weights from a seeded synthetic
+TF-format checkpoint (the bootstrap checkpoint is an un-fetched LFS object).  `value` = positions/s with inputs
+resident in HBM; `e2e` = the same through the reference-facing Evaluate() entry (ug_eval_run_planes) with host
+buffers.  `--impl reference` times the CPU restatement of the reference's TF-CPU evaluator (oracle/) instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "nn_positions_per_s_batch256_20block"
+UNIT = "positions/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ugeval", choices=["ugeval", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--blocks", type=int, default=20)
+    ap.add_argument("--filters", type=int, default=256)
+    ap.add_argument("--ctas", type=int, default=0, help="tower kernel cta_group (1/2); 0 = library default")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def checkpoint(blocks, filters):
+    from unrealgo_b200 import tfformat
+    d = f"/tmp/ugeval_bench_ckpt_{blocks}x{filters}_{os.getpid() if os.environ.get('RANK') else 'x'}"
+    meta = os.path.join(d, "bootstrap-ckpt.meta")
+    if not os.path.exists(os.path.join(d, "bootstrap-ckpt.index")):
+        tfformat.write_synthetic_checkpoint(d, blocks, filters, seed=20260119)
+    return meta, os.path.join(d, "bootstrap-ckpt")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows),
+                "reasons": sorted(reasons)}
+
+
+def cpu_reference(args, seconds, batch):
+    """times the oracle (fp32 torch-CPU interpretation of the same graph) on all host threads"""
+    import numpy as np
+    import torch
+    from oracle.net_oracle import GraphOracle
+    from unrealgo_b200 import synth
+    meta, prefix = checkpoint(args.blocks, args.filters)
+    orc = GraphOracle(meta, prefix)
+    planes = synth.packed_to_planes(synth.synthetic_packed_positions(batch, seed=7))
+    cores = torch.get_num_threads()
+    orc.evaluate_reference(planes[:1])  # warm
+    t0 = time.perf_counter()
+    done = 0
+    while True:
+        orc.evaluate_reference(planes)
+        done += batch
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    return {"value": done / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{done} positions in batches of {batch} ({args.blocks}x{args.filters}), fp32 torch-CPU "
+                      f"graph interpreter restating the reference's TF-CPU Session::Run; {el:.1f} s"}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 16  # MAX_BATCHES: the largest batch the reference evaluator can express
+    per_step = max(args.cpu_seconds / max(args.steps + args.warmup, 1), 0.5)
+    import numpy as np
+    import torch
+    from oracle.net_oracle import GraphOracle
+    from unrealgo_b200 import synth
+    meta, prefix = checkpoint(args.blocks, args.filters)
+    orc = GraphOracle(meta, prefix)
+    planes = synth.packed_to_planes(synth.synthetic_packed_positions(batch, seed=7))
+    for _ in range(args.warmup):
+        orc.evaluate_reference(planes[:4])
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        ts = time.perf_counter()
+        while True:
+            orc.evaluate_reference(planes)
+            done += batch
+            if time.perf_counter() - ts >= per_step * 0.5:
+                break
+    el = time.perf_counter() - t0
+    v = done / el
+    cb = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+          "sample": f"{done} positions, batch {batch}, {args.blocks}x{args.filters}, fp32 torch-CPU restatement "
+                    f"(TensorFlow and the bootstrap checkpoint are unavailable offline)"}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * el / args.steps,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic",
+                      "config": {"workload": f"{args.blocks}x{args.filters} dlcfg-19 net, batch {batch} on host cores"},
+                      "cpu_baseline": cb,
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return main_reference(args)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from unrealgo_b200 import DlTFNetworkEvaluator, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.batch
+    meta, prefix = checkpoint(args.blocks, args.filters)
+    ev = DlTFNetworkEvaluator(meta, device=local, max_batch=B)
+    assert ev.UpdateCheckPoint(prefix), ev._err()
+    if args.ctas:
+        ev.set_conv_ctas(args.ctas)
+    info = ev.info()
+
+    # 8 different input batches, rotated, so no step re-reads the inputs of the previous one
+    nrot = 8
+    host_packed = [synth.synthetic_packed_positions(B, seed=100 + rank * 16 + i) for i in range(nrot)]
+    d_pos = [torch.from_numpy(p.view(np.int32)).cuda() for p in host_packed]
+    d_pol = torch.empty(B, 362, dtype=torch.float32, device="cuda")
+    d_val = torch.empty(B, dtype=torch.float32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(i):
+        ev.run_packed_device(d_pos[i % nrot].data_ptr(), B, d_pol.data_ptr(), d_val.data_ptr(), stream=stream)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()  # evict L2 between timed iterations (outside the event bracket)
+        evs[i][0].record()
+        step(i)
+        evs[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    assert torch.isfinite(d_pol).all() and torch.isfinite(d_val).all()
+
+    # end to end through the reference-facing entry: host int8 planes in, host double policy/value out
+    planes = [synth.packed_to_planes(p) for p in host_packed[:2]]
+    pol = np.empty((B, 362), np.float64)
+    val = np.empty(B, np.float64)
+    for i in range(3):
+        assert ev.Evaluate(planes[i % 2], pol, val, B)
+    if world > 1:
+        dist.barrier()
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        assert ev.Evaluate(planes[i % 2], pol, val, B)
+    e2e_s = time.perf_counter() - t0
+    # native packed host entry as a second data point
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        ev.evaluate_packed(host_packed[i % nrot])
+    e2e_packed_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s, e2e_packed_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s, e2e_packed_s = (float(x) for x in te.tolist())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # roofline of the dominant kernel (3x3 CxC tower conv): CUDA-event brackets inside the library, on its stream
+    br = ev.bench(host_packed[0], 20)
+    ev.set_debug_stop(0)
+    br_stem = ev.bench(host_packed[0], 20)
+    ev.set_debug_stop(-1)
+    conv_launches = 2 * info["blocks"]
+    conv_ms = (br["ms_tower"] - br_stem["ms_tower"]) / conv_launches
+    C = info["filters"]
+    conv_flops = 2.0 * B * 361 * 9 * C * C
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    burst = peaks.get("bf16_tflops", 1590.0)
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    if rank == 0:
+        value = world * B * args.steps / (dev_ms * 1e-3)
+        e2e_v = world * B * e2e_steps / e2e_s
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"batched evaluation of {B} synthetic 19x19 positions per GPU, "
+                                   f"{info['blocks']}-block x {C}-filter dlcfg-19 net (BASELINE configs[1]), "
+                                   "seeded synthetic TF-format checkpoint",
+                       "batch": B, "blocks": info["blocks"], "filters": C, "conv_cta_group": info["conv_ctas"],
+                       "l2": "flushed between timed steps (256 MiB write outside the event bracket); 8 input batches rotated",
+                       "flops_per_position": info["flops_per_position"],
+                       "tensor_frac_of_burst_peak_whole_step": value / world * info["flops_per_position"] / (burst * 1e12),
+                       "e2e_packed_positions_per_s": world * B * e2e_steps / e2e_packed_s,
+                       "kernel_group_ms": {"encoder": br["ms_encoder"], "tower": br["ms_tower"], "heads": br["ms_heads"],
+                                           "stem": br_stem["ms_tower"]}},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": B * 17 * 361, "d2h_bytes_per_step": B * 363 * 4,
+                    "api": "DlTFNetworkEvaluator::Evaluate (ug_eval_run_planes): host int8 planes -> host double policy/value"},
+            "gpu_launches": (3 + 1 + conv_launches) * args.steps,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "frac_of_burst": achieved / burst,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long loop)"
+                                        if peaks else "fallback",
+                         "kernel": f"conv3x3_tc_kernel<64,{info['conv_ctas']}> (3x3 {C}->{C}, M={B * 361})",
+                         "flops_per_launch": conv_flops, "ms_per_launch": conv_ms, "traffic": None},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                out["cpu_baseline"] = cpu_reference(args, args.cpu_seconds, 16)
+            except Exception as e:  # the baseline is reported beside the result, never part of it
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                       "sample": f"failed: {e!r}"}
+        print(json.dumps(out))
+    ev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -124,6 +124,9 @@ int ug_transform_planes(ug_eval* h, const int8_t* chw, int n, int8_t* hwc_out);
 /* After a run call: copy the fp32 image of intermediate tensor `layer` to host as [n][361][channels].
  * layer 0 = stem output, 1..2*blocks = tower convs in order; returns channels or <0. */
 int ug_eval_debug_layer(ug_eval* h, int layer, int n, float* out);
+/* Stop the tower after `layer` on subsequent run calls (-1 = run everything), so ug_eval_debug_layer can read it
+ * before later blocks reuse the buffer.  Outputs of truncated runs are meaningless. */
+int ug_eval_set_debug_stop(ug_eval* h, int layer);
 /* Device-buffer kernel timings of the last ug_eval_bench call. */
 typedef struct ug_bench_result {
   float ms_total;    /* CUDA-event time of `iters` full passes (encoder+tower+heads), device-resident inputs */

@@ -66,21 +66,35 @@ def test_bf16_small(small_ckpt, positions, n, ctas):
 
 @pytest.mark.parametrize("ctas", [1, 2])
 def test_bf16_wide_layers_and_outputs(wide_ckpt, positions, ctas):
-    """256 filters (the production tile) — per-layer comparison against the fp32 validation build and
-    end-to-end against the oracle."""
+    """256 filters (the production tile shape) — every layer of the fp32 validation build against the oracle's
+    graph interpreter, every layer of the bf16 tcgen05 build against the fp32 build, then end to end."""
+    import oracle
     from unrealgo_b200 import PREC_BF16, PREC_FP32
     packed, planes = positions
     n = 40  # 40*361 = 14440 rows: tail tile for both 128- and 256-row tiles
     ev16 = _evaluator(wide_ckpt, PREC_BF16, ctas=ctas)
     ev32 = _evaluator(wide_ckpt, PREC_FP32)
+    orc = _oracle(wide_ckpt)
+    t = "resnet/tower_0"
+    names = [f"{t}/init_conv/Relu"]
+    for b in range(3):
+        names += [f"{t}/unit_res_{b}/sub1/conv1/Relu", f"{t}/unit_res_{b}/Relu"]
+    nhwc = oracle.transform_feature(planes[:n], 0, True)
+    _, _, fetched = orc.run(nhwc, fetch=names)
+    for layer, name in enumerate(names):
+        for ev in (ev16, ev32):
+            ev.set_debug_stop(layer)
+            ev.evaluate_packed(packed[:n])
+        a16, a32 = ev16.debug_layer(layer, n), ev32.debug_layer(layer, n)
+        want = fetched[name].reshape(n, 361, 256)
+        scale = np.abs(want).max()
+        assert np.abs(a32 - want).max() <= 1e-4 * scale, (layer, "fp32 vs oracle", np.abs(a32 - want).max(), scale)
+        assert np.abs(a16 - a32).max() <= 0.02 * scale, (layer, "bf16 vs fp32", np.abs(a16 - a32).max(), scale)
+    for ev in (ev16, ev32):
+        ev.set_debug_stop(-1)
     p16, v16 = ev16.evaluate_packed(packed[:n])
     p32, v32 = ev32.evaluate_packed(packed[:n])
-    for layer in range(0, 7):
-        a16 = ev16.debug_layer(layer, n)
-        a32 = ev32.debug_layer(layer, n)
-        scale = np.abs(a32).max()
-        assert np.abs(a16 - a32).max() <= 0.02 * scale + 1e-3, (layer, np.abs(a16 - a32).max(), scale)
-    want_p, want_v = _oracle(wide_ckpt).evaluate_reference(planes[:n])
+    want_p, want_v = orc.evaluate_reference(planes[:n])
     assert np.abs(p32 - want_p).max() <= FP32_POL and np.abs(v32 - want_v).max() <= FP32_VAL
     assert np.abs(p16 - want_p).max() <= BF16_POL and np.abs(v16 - want_v).max() <= BF16_VAL
     ev16.close()

@@ -65,6 +65,7 @@ SIGNATURES = {
     "ug_encode_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ug_transform_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ug_eval_debug_layer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ug_eval_set_debug_stop": (C.c_int, [C.c_void_p, C.c_int]),
     "ug_eval_bench": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(BenchResult)]),
     "ug_k_conv3x3_bf16": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -175,7 +175,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== epilogue =====================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32)
     const __nv_bfloat16* __restrict__ res = args.residual;
+    const __nv_bfloat16* __restrict__ res_lo = args.residual_lo;
     __nv_bfloat16* __restrict__ out = args.out;
+    __nv_bfloat16* __restrict__ out_lo = args.out_lo;
     const float* __restrict__ bias = args.bias;
     int it = 0;
     for (int tile = cluster_id; tile < args.num_tiles; tile += num_clusters, ++it) {
@@ -192,17 +194,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_ld_wait();
         if (row_ok) {
           const size_t off = (size_t)row * cout + c0;
-          uint4 rr[4];
+          uint4 rr[4], rl[4];
           if (res != nullptr) {
             const uint4* rp = reinterpret_cast<const uint4*>(res + off);
 #pragma unroll
             for (int q = 0; q < 4; ++q) rr[q] = __ldg(rp + q);
+            if (res_lo != nullptr) {
+              const uint4* lp = reinterpret_cast<const uint4*>(res_lo + off);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) rl[q] = __ldg(lp + q);
+            }
           }
-          uint4 oo[4];
+          uint4 oo[4], ol[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint32_t packed[4];
+            uint32_t packed[4], packed_lo[4];
             const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rr[q]);
+            const uint32_t* lw = reinterpret_cast<const uint32_t*>(&rl[q]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int c = q * 8 + e * 2;
@@ -212,16 +220,32 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
                 f0 += __bfloat162float(r2.x);
                 f1 += __bfloat162float(r2.y);
+                if (res_lo != nullptr) {
+                  const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&lw[e]);
+                  f0 += __bfloat162float(l2.x);
+                  f1 += __bfloat162float(l2.y);
+                }
               }
               if (args.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
               const __nv_bfloat162 o2 = __floats2bfloat162_rn(f0, f1);
               packed[e] = *reinterpret_cast<const uint32_t*>(&o2);
+              if (out_lo != nullptr) {
+                const __nv_bfloat162 d2 =
+                    __floats2bfloat162_rn(f0 - __bfloat162float(o2.x), f1 - __bfloat162float(o2.y));
+                packed_lo[e] = *reinterpret_cast<const uint32_t*>(&d2);
+              }
             }
             oo[q] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            if (out_lo != nullptr) ol[q] = make_uint4(packed_lo[0], packed_lo[1], packed_lo[2], packed_lo[3]);
           }
           uint4* op = reinterpret_cast<uint4*>(out + off);
 #pragma unroll
           for (int q = 0; q < 4; ++q) op[q] = oo[q];
+          if (out_lo != nullptr) {
+            uint4* lp = reinterpret_cast<uint4*>(out_lo + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) lp[q] = ol[q];
+          }
         }
       }
       tc_fence_before();

@@ -8,8 +8,11 @@ namespace ug {
 
 struct ConvArgs {
   const float* bias;              // [cout] folded batch-norm offset (fp32)
-  const __nv_bfloat16* residual;  // [M][cout] skip connection or nullptr
-  __nv_bfloat16* out;             // [M][cout]
+  const __nv_bfloat16* residual;     // [M][cout] skip connection (high part) or nullptr
+  const __nv_bfloat16* residual_lo;  // optional low part: skip = float(hi) + float(lo)
+  __nv_bfloat16* out;                // [M][cout] bf16(result): the next conv's operand
+  __nv_bfloat16* out_lo;             // optional: bf16(result - float(out)), keeps the residual stream from
+                                     // being re-rounded to 8 mantissa bits every block
   int M;                          // n * 361 output pixels
   int cin;                        // input channels as stored (multiple of ck)
   int cout;                       // <= 256, multiple of 16 (32 for the 2-CTA variant)

@@ -59,7 +59,8 @@ struct Load8<float> {
 
 // feat[point][h] = relu(sum_c act[point][c] * w[h][c] + b[h]);  HC = pc+vc <= 8, C % 8 == 0
 template <typename T, int HC>
-__global__ void __launch_bounds__(256) head_conv_kernel(const T* __restrict__ act, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) head_conv_kernel(const T* __restrict__ act, const T* __restrict__ act_lo,
+                                                        const float* __restrict__ w,
                                                         const float* __restrict__ b, float* __restrict__ feat,
                                                         long total_points, int C) {
   extern __shared__ float sw[];  // [HC][C]
@@ -77,6 +78,12 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const T* __restrict__ ac
     for (int ch = lane; ch < chunks; ch += 32) {
       float x[8];
       Load8<T>::load(row + ch * 8, x);
+      if (act_lo != nullptr) {
+        float xl[8];
+        Load8<T>::load(act_lo + pt * C + ch * 8, xl);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] += xl[i];
+      }
 #pragma unroll
       for (int h = 0; h < HC; ++h) {
         const float4 w0 = *reinterpret_cast<const float4*>(sw + h * C + ch * 8);
@@ -152,7 +159,9 @@ __global__ void __launch_bounds__(kFcThreads) head_fc_kernel(const float* __rest
 #pragma unroll
     for (int p = 0; p < kPosPerCta; ++p) logit[p] += bj;
   }
-  for (int p = 0; p < np; ++p) {
+#pragma unroll
+  for (int p = 0; p < kPosPerCta; ++p) {
+    if (p >= np) break;  // np is block-uniform
     const float mx = block_reduce(j < kMoves ? logit[p] : -CUDART_INF_F, true, scratch);
     float prob = logit[p];
     if (hw.policy_softmax) {
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(kFcThreads) head_fc_kernel(const float* __rest
 }
 
 template <typename T>
-void head_conv_dispatch(const T* act, const HeadWeights& w, float* feat, int n, cudaStream_t s) {
+void head_conv_dispatch(const T* act, const T* act_lo, const HeadWeights& w, float* feat, int n, cudaStream_t s) {
   const long total = (long)n * kPoints;
   const int hc = w.pc + w.vc;
   int grid = (int)((total + 7) / 8);
@@ -211,7 +220,7 @@ void head_conv_dispatch(const T* act, const HeadWeights& w, float* feat, int n, 
   switch (hc) {
 #define UG_HC_CASE(N)                                                                                   \
   case N:                                                                                               \
-    head_conv_kernel<T, N><<<grid, 256, smem, s>>>(act, w.conv_w, w.conv_b, feat, total, w.C);          \
+    head_conv_kernel<T, N><<<grid, 256, smem, s>>>(act, act_lo, w.conv_w, w.conv_b, feat, total, w.C);          \
     break;
     UG_HC_CASE(1) UG_HC_CASE(2) UG_HC_CASE(3) UG_HC_CASE(4) UG_HC_CASE(5) UG_HC_CASE(6) UG_HC_CASE(7)
     UG_HC_CASE(8)
@@ -222,10 +231,12 @@ void head_conv_dispatch(const T* act, const HeadWeights& w, float* feat, int n, 
 
 }  // namespace
 
-void launch_head_conv(const void* act, int act_is_f32, const HeadWeights& w, float* feat, int n, cudaStream_t s) {
+void launch_head_conv(const void* act, const void* act_lo, int act_is_f32, const HeadWeights& w, float* feat, int n,
+                      cudaStream_t s) {
   if (n <= 0) return;
-  if (act_is_f32) head_conv_dispatch<float>(static_cast<const float*>(act), w, feat, n, s);
-  else head_conv_dispatch<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(act), w, feat, n, s);
+  if (act_is_f32) head_conv_dispatch<float>(static_cast<const float*>(act), nullptr, w, feat, n, s);
+  else head_conv_dispatch<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(act),
+                                         static_cast<const __nv_bfloat16*>(act_lo), w, feat, n, s);
 }
 
 void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* legal, int vt, float* policy,

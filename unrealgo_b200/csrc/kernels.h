@@ -37,8 +37,9 @@ struct HeadWeights {
   int value_tanh;      // graph output is Tanh(fc2)
 };
 
-// K5/K6 stage 1: features[n][361][pc+vc] = relu(conv1x1(act)); act is bf16 or fp32 NHWC [n][361][C]
-void launch_head_conv(const void* act, int act_is_f32, const HeadWeights& w, float* feat, int n, cudaStream_t s);
+// K5/K6 stage 1: features[n][361][pc+vc] = relu(conv1x1(act)); act is bf16 (+ optional bf16 low part) or fp32
+// NHWC [n][361][C]
+void launch_head_conv(const void* act, const void* act_lo, int act_is_f32, const HeadWeights& w, float* feat, int n, cudaStream_t s);
 // K5-K7 stage 2: FC + softmax (optionally renormalised over a legal mask) and FC-ReLU-FC-tanh-value_transform
 void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* legal, int vt, float* policy,
                     float* value, int n, cudaStream_t s);

@@ -232,19 +232,22 @@ bool ug_eval::ensure_workspace(int C) {
             d_planes.alloc(nb * UG_NUM_PLANES * UG_NUM_POINTS) && d_bytes.alloc(nb * UG_NUM_PLANES * UG_NUM_POINTS) &&
             d_in.alloc(nb * UG_NUM_POINTS * kCinPad * 2) && d_feat.alloc(nb * UG_NUM_POINTS * 8 * 4) &&
             d_policy.alloc(nb * UG_NUM_MOVES * 4) && d_value.alloc(nb * 4);
-  for (int i = 0; i < 3 && ok; ++i) ok = d_act[i].alloc(act_elems * 2);
+  for (int i = 0; i < 2 && ok; ++i) ok = d_s_hi[i].alloc(act_elems * 2) && d_s_lo[i].alloc(act_elems * 2);
+  ok = ok && d_t.alloc(act_elems * 2);
   if (ok && precision == UG_PREC_FP32) {
-    ok = f_in.alloc(nb * UG_NUM_POINTS * UG_NUM_PLANES * 4);
-    for (int i = 0; i < 3 && ok; ++i) ok = f_act[i].alloc(act_elems * 4);
+    ok = f_in.alloc(nb * UG_NUM_POINTS * UG_NUM_PLANES * 4) && f_t.alloc(act_elems * 4);
+    for (int i = 0; i < 2 && ok; ++i) ok = f_s[i].alloc(act_elems * 4);
   }
   if (!ok) { last_error = "out of device memory allocating the workspace"; return false; }
   // zero once so that rows past n (read by the tail tile) are finite
   cudaMemset(d_in.p, 0, d_in.bytes);
-  for (int i = 0; i < 3; ++i) cudaMemset(d_act[i].p, 0, d_act[i].bytes);
+  for (int i = 0; i < 2; ++i) { cudaMemset(d_s_hi[i].p, 0, d_s_hi[i].bytes); cudaMemset(d_s_lo[i].p, 0, d_s_lo[i].bytes); }
+  cudaMemset(d_t.p, 0, d_t.bytes);
   std::string err;
   if (!make_tmap_act_im2col(&tm_in, d_in.p, max_batch, kCinPad, 32, &err)) { last_error = err; return false; }
-  for (int i = 0; i < 3; ++i)
-    if (!make_tmap_act_im2col(&tm_act[i], d_act[i].p, max_batch, C, 64, &err)) { last_error = err; return false; }
+  for (int i = 0; i < 2; ++i)
+    if (!make_tmap_act_im2col(&tm_s[i], d_s_hi[i].p, max_batch, C, 64, &err)) { last_error = err; return false; }
+  if (!make_tmap_act_im2col(&tm_t, d_t.p, max_batch, C, 64, &err)) { last_error = err; return false; }
   if (!h_pinned) {
     h_pinned_bytes = nb * (sizeof(ug_packed_pos) + UG_MASK_WORDS * 4 + UG_NUM_PLANES * UG_NUM_POINTS +
                            (UG_NUM_MOVES + 1) * 4) + 256;
@@ -265,26 +268,30 @@ int ug_eval::enqueue_encoder(Src kind, const void* d_src, int n, cudaStream_t s)
   return 0;
 }
 
-int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act) {
+int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act, const void** final_lo) {
   const Weights& W = *weights;
   const int C = W.C;
+  // block b: x = S[b&1] (stream), t = T, y = S[(b+1)&1]
   if (precision == UG_PREC_FP32) {
     launch_nhwc_to_f32(d_in.as<__nv_bfloat16>(), f_in.as<float>(), n, s);
     const ConvLayer& st = W.convs[0];
-    launch_conv3x3_f32(f_in.as<float>(), st.w_f32.as<float>(), st.bias.as<float>(), nullptr, f_act[0].as<float>(),
+    launch_conv3x3_f32(f_in.as<float>(), st.w_f32.as<float>(), st.bias.as<float>(), nullptr, f_s[0].as<float>(),
                        n, UG_NUM_PLANES, C, 1, s);
-    int x = 0;
-    for (int b = 0; b < W.blocks; ++b) {
-      const int t = (x + 1) % 3, y = (x + 2) % 3;
+    *final_act = f_s[0].p;
+    *final_lo = nullptr;
+    for (int b = 0; b < W.blocks && debug_stop != 0; ++b) {
+      const int x = b & 1, y = x ^ 1;
       const ConvLayer& c1 = W.convs[1 + 2 * b];
       const ConvLayer& c2 = W.convs[2 + 2 * b];
-      launch_conv3x3_f32(f_act[x].as<float>(), c1.w_f32.as<float>(), c1.bias.as<float>(), nullptr,
-                         f_act[t].as<float>(), n, C, C, 1, s);
-      launch_conv3x3_f32(f_act[t].as<float>(), c2.w_f32.as<float>(), c2.bias.as<float>(), f_act[x].as<float>(),
-                         f_act[y].as<float>(), n, C, C, 1, s);
-      x = y;
+      launch_conv3x3_f32(f_s[x].as<float>(), c1.w_f32.as<float>(), c1.bias.as<float>(), nullptr, f_t.as<float>(),
+                         n, C, C, 1, s);
+      *final_act = f_t.p;
+      if (debug_stop == 2 * b + 1) break;
+      launch_conv3x3_f32(f_t.as<float>(), c2.w_f32.as<float>(), c2.bias.as<float>(), f_s[x].as<float>(),
+                         f_s[y].as<float>(), n, C, C, 1, s);
+      *final_act = f_s[y].p;
+      if (debug_stop == 2 * b + 2) break;
     }
-    *final_act = f_act[x].p;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   }
   const int ctas = conv_ctas;
@@ -292,39 +299,48 @@ int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act) {
   a.M = n * UG_NUM_POINTS;
   a.relu = 1;
   a.cout = C;
-  // stem: 32 stored input channels (17 planes + zeros), SWIZZLE_64B tiles
+  // stem: 32 stored input channels (17 planes + zeros), SWIZZLE_64B tiles; its output opens the residual stream
   a.cin = kCinPad;
   a.bias = W.convs[0].bias.as<float>();
-  a.residual = nullptr;
-  a.out = d_act[0].as<__nv_bfloat16>();
+  a.out = d_s_hi[0].as<__nv_bfloat16>();
+  a.out_lo = d_s_lo[0].as<__nv_bfloat16>();
   cudaError_t e = conv3x3_tc_launch(tm_in, W.convs[0].tm_w[ctas - 1], a, 32, ctas, sms, s);
   if (e != cudaSuccess) return fail(-1, std::string("stem conv launch: ") + cudaGetErrorString(e));
-  int x = 0;
   a.cin = C;
-  for (int b = 0; b < W.blocks; ++b) {
-    const int t = (x + 1) % 3, y = (x + 2) % 3;
+  *final_act = d_s_hi[0].p;
+  *final_lo = d_s_lo[0].p;
+  for (int b = 0; b < W.blocks && debug_stop != 0; ++b) {
+    const int x = b & 1, y = x ^ 1;
     const ConvLayer& c1 = W.convs[1 + 2 * b];
     const ConvLayer& c2 = W.convs[2 + 2 * b];
     a.bias = c1.bias.as<float>();
     a.residual = nullptr;
-    a.out = d_act[t].as<__nv_bfloat16>();
-    e = conv3x3_tc_launch(tm_act[x], c1.tm_w[ctas - 1], a, 64, ctas, sms, s);
+    a.residual_lo = nullptr;
+    a.out = d_t.as<__nv_bfloat16>();
+    a.out_lo = nullptr;
+    e = conv3x3_tc_launch(tm_s[x], c1.tm_w[ctas - 1], a, 64, ctas, sms, s);
     if (e != cudaSuccess) return fail(-1, std::string("tower conv launch: ") + cudaGetErrorString(e));
+    *final_act = d_t.p;
+    *final_lo = nullptr;
+    if (debug_stop == 2 * b + 1) break;
     a.bias = c2.bias.as<float>();
-    a.residual = d_act[x].as<__nv_bfloat16>();
-    a.out = d_act[y].as<__nv_bfloat16>();
-    e = conv3x3_tc_launch(tm_act[t], c2.tm_w[ctas - 1], a, 64, ctas, sms, s);
+    a.residual = d_s_hi[x].as<__nv_bfloat16>();
+    a.residual_lo = d_s_lo[x].as<__nv_bfloat16>();
+    a.out = d_s_hi[y].as<__nv_bfloat16>();
+    a.out_lo = d_s_lo[y].as<__nv_bfloat16>();
+    e = conv3x3_tc_launch(tm_t, c2.tm_w[ctas - 1], a, 64, ctas, sms, s);
     if (e != cudaSuccess) return fail(-1, std::string("tower conv launch: ") + cudaGetErrorString(e));
-    x = y;
+    *final_act = d_s_hi[y].p;
+    *final_lo = d_s_lo[y].p;
+    if (debug_stop == 2 * b + 2) break;
   }
-  *final_act = d_act[x].p;
   return 0;
 }
 
-int ug_eval::enqueue_heads(const void* act, int n, const uint32_t* d_leg, int vt, float* d_pol, float* d_val,
-                           cudaStream_t s) {
+int ug_eval::enqueue_heads(const void* act, const void* act_lo, int n, const uint32_t* d_leg, int vt, float* d_pol,
+                           float* d_val, cudaStream_t s) {
   const HeadWeights hw = weights->head();
-  launch_head_conv(act, precision == UG_PREC_FP32 ? 1 : 0, hw, d_feat.as<float>(), n, s);
+  launch_head_conv(act, act_lo, precision == UG_PREC_FP32 ? 1 : 0, hw, d_feat.as<float>(), n, s);
   launch_head_fc(d_feat.as<float>(), hw, d_leg, vt, d_pol, d_val, n, s);
   return cudaGetLastError() == cudaSuccess ? 0 : fail(-1, "head kernel launch failed");
 }
@@ -334,9 +350,10 @@ int ug_eval::enqueue_raw(Src kind, const void* d_src, int n, const uint32_t* d_l
   int rc = enqueue_encoder(kind, d_src, n, s);
   if (rc) return rc;
   const void* act = nullptr;
-  rc = enqueue_tower(n, s, &act);
+  const void* act_lo = nullptr;
+  rc = enqueue_tower(n, s, &act, &act_lo);
   if (rc) return rc;
-  return enqueue_heads(act, n, d_leg, vt, d_pol, d_val, s);
+  return enqueue_heads(act, act_lo, n, d_leg, vt, d_pol, d_val, s);
 }
 
 int ug_eval::enqueue(Src kind, const void* d_src, int n, const uint32_t* d_leg, int vt, float* d_pol,
@@ -345,7 +362,7 @@ int ug_eval::enqueue(Src kind, const void* d_src, int n, const uint32_t* d_leg, 
   if (n <= 0 || n > max_batch) return fail(-1, "batch size " + std::to_string(n) + " outside [1, max_batch]");
   if (!use_graphs) return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
   const GraphKey key((int)kind, n, d_src, (const void*)d_leg, (const void*)d_pol, (const void*)d_val, vt,
-                     conv_ctas * 4 + precision);
+                     conv_ctas * 4 + precision + (debug_stop + 1) * 16);
   auto it = graphs.find(key);
   if (it == graphs.end()) {
     if (graphs.size() > 256) drop_graphs();
@@ -480,6 +497,12 @@ int ug_eval_has_weights(const ug_eval* h) { return h && h->weights ? 1 : 0; }
 int ug_eval_set_value_transform(ug_eval* h, int vt) {
   if (!h) return -1;
   h->value_transform = (vt == UG_TR_FLIP_SIGN || vt == UG_TR_FLIP_PROB) ? vt : UG_TR_IDENTITY;
+  return 0;
+}
+
+int ug_eval_set_debug_stop(ug_eval* h, int layer) {
+  if (!h) return -1;
+  h->debug_stop = layer < 0 ? -1 : layer;
   return 0;
 }
 
@@ -625,26 +648,19 @@ int ug_eval_debug_layer(ug_eval* h, int layer, int n, float* out) {
   if (!h || !h->weights) return -1;
   const Weights& W = *h->weights;
   if (layer < 0 || layer > 2 * W.blocks || n <= 0 || n > h->max_batch) return h->fail(-1, "bad layer or n");
-  // re-run the tower up to `layer` is unnecessary: buffers rotate x -> (x+2)%3 per block, recompute the index
-  int idx = 0;
-  if (layer > 0) {
-    int x = 0;
-    for (int b = 0; b < W.blocks; ++b) {
-      const int t = (x + 1) % 3, y = (x + 2) % 3;
-      if (layer == 1 + 2 * b) { idx = t; break; }
-      if (layer == 2 + 2 * b) { idx = y; break; }
-      x = y;
-    }
-  }
+  // layer 0 (stem) -> S[0]; conv1 of block b -> T; conv2 of block b -> S[(b+1)&1].  Buffers are reused by later
+  // blocks: run with ug_eval_set_debug_stop(h, layer) first so that `layer` is the last writer of its buffer.
+  const bool is_t = layer > 0 && (layer & 1);
+  const int sidx = layer == 0 ? 0 : ((layer / 2) & 1);
   cudaSetDevice(h->device);
   const size_t count = (size_t)n * UG_NUM_POINTS * W.C;
   cudaStream_t s = h->stream;
   if (h->precision == UG_PREC_FP32) {
-    cudaMemcpyAsync(out, h->f_act[idx].p, count * 4, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(out, is_t ? h->f_t.p : h->f_s[sidx].p, count * 4, cudaMemcpyDeviceToHost, s);
   } else {
     DevBuf tmp;
     if (!tmp.alloc(count * 4)) return h->fail(-1, "out of memory");
-    launch_bf16_to_f32(h->d_act[idx].as<__nv_bfloat16>(), tmp.as<float>(), count, s);
+    launch_bf16_to_f32(is_t ? h->d_t.as<__nv_bfloat16>() : h->d_s_hi[sidx].as<__nv_bfloat16>(), tmp.as<float>(), count, s);
     cudaMemcpyAsync(out, tmp.p, count * 4, cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
   }
@@ -678,9 +694,10 @@ int ug_eval_bench(ug_eval* h, const ug_packed_pos* host_pos, int n, int iters, u
   int rc = timed([&] { return h->enqueue(ug_eval::SRC_PACKED, h->d_pos.p, n, nullptr, h->value_transform,
                                          h->d_policy.as<float>(), h->d_value.as<float>(), s); }, &full);
   const void* act = nullptr;
+  const void* act_lo = nullptr;
   if (!rc) rc = timed([&] { return h->enqueue_encoder(ug_eval::SRC_PACKED, h->d_pos.p, n, s); }, &out->ms_encoder);
-  if (!rc) rc = timed([&] { return h->enqueue_tower(n, s, &act); }, &out->ms_tower);
-  if (!rc) rc = timed([&] { return h->enqueue_heads(act, n, nullptr, h->value_transform, h->d_policy.as<float>(),
+  if (!rc) rc = timed([&] { return h->enqueue_tower(n, s, &act, &act_lo); }, &out->ms_tower);
+  if (!rc) rc = timed([&] { return h->enqueue_heads(act, act_lo, n, nullptr, h->value_transform, h->d_policy.as<float>(),
                                                     h->d_value.as<float>(), s); }, &out->ms_heads);
   out->ms_total = full * iters;
   out->launches_per_pass = 1 + (h->precision == UG_PREC_FP32 ? 1 : 0) + 1 + 2 * h->weights->blocks + 2;

@@ -60,6 +60,7 @@ struct ug_eval {
   int conv_ctas = 2;
   int value_transform = UG_TR_IDENTITY;
   bool use_graphs = true;
+  int debug_stop = -1;  // >= 0: stop the tower after that layer (0 = stem, 2b+1 / 2b+2 = convs of block b)
   mutable std::string last_error;
 
   std::string input_name = "feature_input";
@@ -75,9 +76,11 @@ struct ug_eval {
   cudaStream_t stream = nullptr;
   // workspace (allocated once the architecture is known)
   int ws_C = 0;
-  ug::DevBuf d_pos, d_legal, d_planes, d_in, d_act[3], d_feat, d_policy, d_value, d_bytes;
-  ug::DevBuf f_in, f_act[3];
-  CUtensorMap tm_in, tm_act[3];
+  ug::DevBuf d_pos, d_legal, d_planes, d_in, d_feat, d_policy, d_value, d_bytes;
+  // residual stream ping-pong S[0]/S[1] as bf16 hi + bf16 lo (skip = hi + lo), block-internal tensor T (bf16)
+  ug::DevBuf d_s_hi[2], d_s_lo[2], d_t;
+  ug::DevBuf f_in, f_s[2], f_t;  // fp32 validation build
+  CUtensorMap tm_in, tm_s[2], tm_t;
   void* h_pinned = nullptr;  // staging for host-buffer entry points
   size_t h_pinned_bytes = 0;
 
@@ -97,7 +100,7 @@ struct ug_eval {
   int enqueue_raw(Src kind, const void* d_src, int n, const uint32_t* d_legal, int vt, float* d_policy,
                   float* d_value, cudaStream_t s);
   int enqueue_encoder(Src kind, const void* d_src, int n, cudaStream_t s);
-  int enqueue_tower(int n, cudaStream_t s, const void** final_act);
-  int enqueue_heads(const void* act, int n, const uint32_t* d_legal, int vt, float* d_policy, float* d_value,
+  int enqueue_tower(int n, cudaStream_t s, const void** final_act, const void** final_lo);
+  int enqueue_heads(const void* act, const void* act_lo, int n, const uint32_t* d_legal, int vt, float* d_policy, float* d_value,
                     cudaStream_t s);
 };

@@ -197,6 +197,9 @@ class DlTFNetworkEvaluator:
             raise RuntimeError(self._err())
         return out
 
+    def set_debug_stop(self, layer):
+        self._lib.ug_eval_set_debug_stop(self._h, layer)
+
     def debug_layer(self, layer, n):
         c = self.info()["filters"]
         out = np.empty((n, NUM_POINTS, c), np.float32)
