@@ -175,7 +175,12 @@ def main():
     d_pol = torch.empty(B, 362, dtype=torch.float32, device="cuda")
     d_val = torch.empty(B, dtype=torch.float32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    stream = torch.cuda.current_stream().cuda_stream
+    # a real (non-legacy) stream: the kernels are launched on it and the torch events below are recorded on it
+    tstream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step(i):
         ev.run_packed_device(d_pos[i % nrot].data_ptr(), B, d_pol.data_ptr(), d_val.data_ptr(), stream=stream)
