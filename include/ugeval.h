@@ -30,8 +30,10 @@ extern "C" {
 enum { UG_TR_IDENTITY = 0, UG_TR_FLIP_SIGN = 1, UG_TR_FLIP_PROB = 2 };
 /* DataFormat, funcapproximator/DataFormat.h:22-25 */
 enum { UG_DF_HWC = 0, UG_DF_CHW = 1 };
-/* arithmetic of the tower: bf16 tcgen05 path (product) or fp32 SIMT validation build */
-enum { UG_PREC_BF16 = 0, UG_PREC_FP32 = 1 };
+/* arithmetic of the tower.  BF16 / FP16: tcgen05 kind::f16 MMAs (same rate), fp32 accumulation, 16-bit operands
+ * — bf16 keeps fp32's range with an 8-bit mantissa, fp16 has an 11-bit mantissa and saturates at 65504.
+ * FP32: SIMT validation build (slow, for parity work only). */
+enum { UG_PREC_BF16 = 0, UG_PREC_FP32 = 1, UG_PREC_FP16 = 2 };
 
 /*
  * Packed search leaf: what a search thread hands to the GPU encoder instead of running

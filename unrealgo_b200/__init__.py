@@ -4,6 +4,6 @@ The product is the C-ABI CUDA library unrealgo_b200/lib/libugeval.so (include/ug
 sources (csrc/), the C++ host shim mirroring the reference classes (host/), and thin Python bindings used by
 the tests and bench.py.  No CPU fallback exists anywhere in this package.
 """
-from ._lib import PREC_BF16, PREC_FP32, TR_FLIP_PROB, TR_FLIP_SIGN, TR_IDENTITY  # noqa: F401
+from ._lib import PREC_BF16, PREC_FP16, PREC_FP32, TR_FLIP_PROB, TR_FLIP_SIGN, TR_IDENTITY  # noqa: F401
 from .evaluator import (DF_CHW, DF_HWC, DlConfig, DlTFNetworkEvaluator, LeafQueue, UctBoardEvaluator,  # noqa: F401
                         inspect_model)

@@ -17,7 +17,7 @@ MASK_WORDS = 12
 PACKED_POS_BYTES = 784
 
 TR_IDENTITY, TR_FLIP_SIGN, TR_FLIP_PROB = 0, 1, 2
-PREC_BF16, PREC_FP32 = 0, 1
+PREC_BF16, PREC_FP32, PREC_FP16 = 0, 1, 2
 
 
 class PackedPos(C.Structure):

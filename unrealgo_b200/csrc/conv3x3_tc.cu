@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 
 #include "conv3x3_tc.h"
+#include "numfmt.cuh"
 #include "ptx.cuh"
 
 namespace ug {
@@ -144,7 +145,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (leader && lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kTileM * CTAS, cout);
+      const uint32_t idesc = make_idesc_16(kTileM * CTAS, cout, args.f16);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -163,7 +164,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kMmaPerStep; ++k) {
             // +32 B along K inside the swizzle span (encoded >>4)
-            umma_bf16<CTAS>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+            umma_f16<CTAS>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
           }
           if constexpr (CTAS == 1) umma_commit(&empty_bar[stage]); else umma_commit_2sm(&empty_bar[stage], 3);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -179,6 +180,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __nv_bfloat16* __restrict__ out = args.out;
     __nv_bfloat16* __restrict__ out_lo = args.out_lo;
     const float* __restrict__ bias = args.bias;
+    const int f16 = args.f16;
     int it = 0;
     for (int tile = cluster_id; tile < args.num_tiles; tile += num_clusters, ++it) {
       const int as = it & 1;
@@ -217,22 +219,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               float f0 = __uint_as_float(v[c]) + __ldg(bias + c0 + c);
               float f1 = __uint_as_float(v[c + 1]) + __ldg(bias + c0 + c + 1);
               if (res != nullptr) {
-                const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
-                f0 += __bfloat162float(r2.x);
-                f1 += __bfloat162float(r2.y);
+                const float2 r2 = unpack2(rw[e], f16);
+                f0 += r2.x;
+                f1 += r2.y;
                 if (res_lo != nullptr) {
-                  const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&lw[e]);
-                  f0 += __bfloat162float(l2.x);
-                  f1 += __bfloat162float(l2.y);
+                  const float2 l2 = unpack2(lw[e], f16);
+                  f0 += l2.x;
+                  f1 += l2.y;
                 }
               }
               if (args.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-              const __nv_bfloat162 o2 = __floats2bfloat162_rn(f0, f1);
-              packed[e] = *reinterpret_cast<const uint32_t*>(&o2);
+              packed[e] = pack2(f0, f1, f16);
               if (out_lo != nullptr) {
-                const __nv_bfloat162 d2 =
-                    __floats2bfloat162_rn(f0 - __bfloat162float(o2.x), f1 - __bfloat162float(o2.y));
-                packed_lo[e] = *reinterpret_cast<const uint32_t*>(&d2);
+                const float2 hi = unpack2(packed[e], f16);
+                packed_lo[e] = pack2(f0 - hi.x, f1 - hi.y, f16);
               }
             }
             oo[q] = make_uint4(packed[0], packed[1], packed[2], packed[3]);

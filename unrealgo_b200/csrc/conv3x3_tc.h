@@ -17,6 +17,7 @@ struct ConvArgs {
   int cin;                        // input channels as stored (multiple of ck)
   int cout;                       // <= 256, multiple of 16 (32 for the 2-CTA variant)
   int relu;
+  int f16;                        // operands/outputs are fp16 (else bf16); see numfmt.cuh
   int num_tiles;                  // filled by the launcher
 };
 

@@ -11,6 +11,7 @@
 // HBM-bound integer work: 784 B in, 361*32*2 B out per position; every thread produces one 16-byte,
 // fully coalesced store (8 channels of one point).
 #include "kernels.h"
+#include "numfmt.cuh"
 
 namespace ug {
 
@@ -19,10 +20,10 @@ namespace {
 constexpr int kPoints = UG_NUM_POINTS;
 constexpr int kChunksPerPoint = kCinPad / 8;                  // 16-byte chunks per point
 constexpr int kChunksPerPos = kPoints * kChunksPerPoint;      // 1444
-constexpr uint32_t kOneBf16 = 0x3F80u;
 
 __global__ void __launch_bounds__(256) encode_packed_nhwc_kernel(const ug_packed_pos* __restrict__ pos,
-                                                                 __nv_bfloat16* __restrict__ out, int n) {
+                                                                 __nv_bfloat16* __restrict__ out, int n,
+                                                                 uint32_t kOneBf16) {
   __shared__ uint32_t masks[2][UG_HISTORY][UG_MASK_WORDS];  // [0] = side to move, [1] = opponent
   __shared__ uint32_t s_to_play;
   for (int p = blockIdx.x; p < n; p += gridDim.x) {
@@ -90,7 +91,8 @@ __global__ void __launch_bounds__(256) encode_packed_chw_kernel(const ug_packed_
 
 // reference planes -> NHWC bf16.  T=bool semantics of DlTFNetworkEvaluator<bool>: any non-zero byte is 1.
 __global__ void __launch_bounds__(256) planes_to_nhwc_kernel(const int8_t* __restrict__ planes, int hwc,
-                                                             __nv_bfloat16* __restrict__ out, int n) {
+                                                             __nv_bfloat16* __restrict__ out, int n,
+                                                             uint32_t kOneBf16) {
   __shared__ int8_t sp[UG_NUM_PLANES * kPoints + 7];
   for (int p = blockIdx.x; p < n; p += gridDim.x) {
     const int8_t* src = planes + (size_t)p * UG_NUM_PLANES * kPoints;
@@ -115,56 +117,59 @@ __global__ void __launch_bounds__(256) planes_to_nhwc_kernel(const int8_t* __res
   }
 }
 
-__global__ void nhwc_to_bytes_kernel(const __nv_bfloat16* __restrict__ in, int8_t* __restrict__ out, size_t total) {
+__global__ void nhwc_to_bytes_kernel(const __nv_bfloat16* __restrict__ in, int8_t* __restrict__ out, size_t total,
+                                     int f16) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const size_t point = i / UG_NUM_PLANES;
   const int ch = (int)(i - point * UG_NUM_PLANES);
-  out[i] = (int8_t)__bfloat162float(in[point * kCinPad + ch]);
+  out[i] = (int8_t)unpack1(reinterpret_cast<const uint16_t*>(in)[point * kCinPad + ch], f16);
 }
 
-__global__ void nhwc_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t total) {
+__global__ void nhwc_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t total,
+                                   int f16) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const size_t point = i / UG_NUM_PLANES;
   const int ch = (int)(i - point * UG_NUM_PLANES);
-  out[i] = __bfloat162float(in[point * kCinPad + ch]);
+  out[i] = unpack1(reinterpret_cast<const uint16_t*>(in)[point * kCinPad + ch], f16);
 }
 
-__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t count) {
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t count,
+                                   int f16) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) out[i] = __bfloat162float(in[i]);
+  if (i < count) out[i] = unpack1(reinterpret_cast<const uint16_t*>(in)[i], f16);
 }
 
 inline int pos_grid(int n) { return n < 148 * 16 ? n : 148 * 16; }
 
 }  // namespace
 
-void launch_encode_packed_nhwc(const ug_packed_pos* pos, __nv_bfloat16* out, int n, cudaStream_t s) {
+void launch_encode_packed_nhwc(const ug_packed_pos* pos, __nv_bfloat16* out, int n, int f16, cudaStream_t s) {
   if (n <= 0) return;
-  encode_packed_nhwc_kernel<<<pos_grid(n), 256, 0, s>>>(pos, out, n);
+  encode_packed_nhwc_kernel<<<pos_grid(n), 256, 0, s>>>(pos, out, n, one16(f16));
 }
 void launch_encode_packed_chw(const ug_packed_pos* pos, int8_t* out, int n, cudaStream_t s) {
   if (n <= 0) return;
   encode_packed_chw_kernel<<<pos_grid(n), 256, 0, s>>>(pos, out, n);
 }
-void launch_planes_to_nhwc(const int8_t* planes, int hwc, __nv_bfloat16* out, int n, cudaStream_t s) {
+void launch_planes_to_nhwc(const int8_t* planes, int hwc, __nv_bfloat16* out, int n, int f16, cudaStream_t s) {
   if (n <= 0) return;
-  planes_to_nhwc_kernel<<<pos_grid(n), 256, 0, s>>>(planes, hwc, out, n);
+  planes_to_nhwc_kernel<<<pos_grid(n), 256, 0, s>>>(planes, hwc, out, n, one16(f16));
 }
-void launch_nhwc_to_bytes(const __nv_bfloat16* in, int8_t* out, int n, cudaStream_t s) {
-  if (n <= 0) return;
-  const size_t total = (size_t)n * kPoints * UG_NUM_PLANES;
-  nhwc_to_bytes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, total);
-}
-void launch_nhwc_to_f32(const __nv_bfloat16* in, float* out, int n, cudaStream_t s) {
+void launch_nhwc_to_bytes(const __nv_bfloat16* in, int8_t* out, int n, int f16, cudaStream_t s) {
   if (n <= 0) return;
   const size_t total = (size_t)n * kPoints * UG_NUM_PLANES;
-  nhwc_to_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, total);
+  nhwc_to_bytes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, total, f16);
 }
-void launch_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t count, cudaStream_t s) {
+void launch_nhwc_to_f32(const __nv_bfloat16* in, float* out, int n, int f16, cudaStream_t s) {
+  if (n <= 0) return;
+  const size_t total = (size_t)n * kPoints * UG_NUM_PLANES;
+  nhwc_to_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, total, f16);
+}
+void launch_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t count, int f16, cudaStream_t s) {
   if (count == 0) return;
-  bf16_to_f32_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(in, out, count);
+  bf16_to_f32_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(in, out, count, f16);
 }
 
 }  // namespace ug

@@ -12,6 +12,7 @@
 #include <math_constants.h>
 
 #include "kernels.h"
+#include "numfmt.cuh"
 
 namespace ug {
 
@@ -35,13 +36,13 @@ __device__ __forceinline__ float warp_max(float v) {
 template <typename T>
 struct Load8;
 template <>
-struct Load8<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+struct Load8<__nv_bfloat16> {  // 16-bit storage: bf16 or fp16 selected by f16
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8], int f16) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&u);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 t = __bfloat1622float2(h[i]);
+      const float2 t = unpack2(w[i], f16);
       f[2 * i] = t.x;
       f[2 * i + 1] = t.y;
     }
@@ -49,7 +50,7 @@ struct Load8<__nv_bfloat16> {
 };
 template <>
 struct Load8<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[8], int) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p));
     const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
@@ -62,7 +63,7 @@ template <typename T, int HC>
 __global__ void __launch_bounds__(256) head_conv_kernel(const T* __restrict__ act, const T* __restrict__ act_lo,
                                                         const float* __restrict__ w,
                                                         const float* __restrict__ b, float* __restrict__ feat,
-                                                        long total_points, int C) {
+                                                        long total_points, int C, int f16) {
   extern __shared__ float sw[];  // [HC][C]
   for (int i = threadIdx.x; i < HC * C; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -77,10 +78,10 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const T* __restrict__ ac
     const T* row = act + pt * C;
     for (int ch = lane; ch < chunks; ch += 32) {
       float x[8];
-      Load8<T>::load(row + ch * 8, x);
+      Load8<T>::load(row + ch * 8, x, f16);
       if (act_lo != nullptr) {
         float xl[8];
-        Load8<T>::load(act_lo + pt * C + ch * 8, xl);
+        Load8<T>::load(act_lo + pt * C + ch * 8, xl, f16);
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] += xl[i];
       }
@@ -211,7 +212,8 @@ __global__ void __launch_bounds__(kFcThreads) head_fc_kernel(const float* __rest
 }
 
 template <typename T>
-void head_conv_dispatch(const T* act, const T* act_lo, const HeadWeights& w, float* feat, int n, cudaStream_t s) {
+void head_conv_dispatch(const T* act, const T* act_lo, int f16, const HeadWeights& w, float* feat, int n,
+                        cudaStream_t s) {
   const long total = (long)n * kPoints;
   const int hc = w.pc + w.vc;
   int grid = (int)((total + 7) / 8);
@@ -220,7 +222,7 @@ void head_conv_dispatch(const T* act, const T* act_lo, const HeadWeights& w, flo
   switch (hc) {
 #define UG_HC_CASE(N)                                                                                   \
   case N:                                                                                               \
-    head_conv_kernel<T, N><<<grid, 256, smem, s>>>(act, act_lo, w.conv_w, w.conv_b, feat, total, w.C);          \
+    head_conv_kernel<T, N><<<grid, 256, smem, s>>>(act, act_lo, w.conv_w, w.conv_b, feat, total, w.C, f16);          \
     break;
     UG_HC_CASE(1) UG_HC_CASE(2) UG_HC_CASE(3) UG_HC_CASE(4) UG_HC_CASE(5) UG_HC_CASE(6) UG_HC_CASE(7)
     UG_HC_CASE(8)
@@ -231,12 +233,12 @@ void head_conv_dispatch(const T* act, const T* act_lo, const HeadWeights& w, flo
 
 }  // namespace
 
-void launch_head_conv(const void* act, const void* act_lo, int act_is_f32, const HeadWeights& w, float* feat, int n,
+void launch_head_conv(const void* act, const void* act_lo, int act_fmt, const HeadWeights& w, float* feat, int n,
                       cudaStream_t s) {
   if (n <= 0) return;
-  if (act_is_f32) head_conv_dispatch<float>(static_cast<const float*>(act), nullptr, w, feat, n, s);
+  if (act_fmt == 1) head_conv_dispatch<float>(static_cast<const float*>(act), nullptr, 0, w, feat, n, s);
   else head_conv_dispatch<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(act),
-                                         static_cast<const __nv_bfloat16*>(act_lo), w, feat, n, s);
+                                         static_cast<const __nv_bfloat16*>(act_lo), act_fmt == 2, w, feat, n, s);
 }
 
 void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* legal, int vt, float* policy,

@@ -11,15 +11,15 @@ namespace ug {
 constexpr int kCinPad = 32;  // stem input channels as stored (17 planes + zero padding)
 
 // K1+K2: packed leaves -> NHWC bf16 [n][361][kCinPad]   (CollectFeatures + TransformFeature in one pass)
-void launch_encode_packed_nhwc(const ug_packed_pos* pos, __nv_bfloat16* out, int n, cudaStream_t s);
+void launch_encode_packed_nhwc(const ug_packed_pos* pos, __nv_bfloat16* out, int n, int f16, cudaStream_t s);
 // K1 test hook: packed leaves -> int8 [n][17][19][19]
 void launch_encode_packed_chw(const ug_packed_pos* pos, int8_t* out, int n, cudaStream_t s);
 // K2: reference planes int8 [n][17][19][19] (hwc=0) or [n][19][19][17] (hwc=1) -> NHWC bf16 [n][361][kCinPad]
-void launch_planes_to_nhwc(const int8_t* planes, int hwc, __nv_bfloat16* out, int n, cudaStream_t s);
+void launch_planes_to_nhwc(const int8_t* planes, int hwc, __nv_bfloat16* out, int n, int f16, cudaStream_t s);
 // readback helper: NHWC bf16 [n][361][kCinPad] -> int8 [n][361][17]
-void launch_nhwc_to_bytes(const __nv_bfloat16* in, int8_t* out, int n, cudaStream_t s);
+void launch_nhwc_to_bytes(const __nv_bfloat16* in, int8_t* out, int n, int f16, cudaStream_t s);
 // fp32 validation input: NHWC bf16 [n][361][kCinPad] -> fp32 [n][361][17]
-void launch_nhwc_to_f32(const __nv_bfloat16* in, float* out, int n, cudaStream_t s);
+void launch_nhwc_to_f32(const __nv_bfloat16* in, float* out, int n, int f16, cudaStream_t s);
 
 struct HeadWeights {
   // 1x1 convs with batch-norm folded: rows [0,pc) policy, [pc,pc+vc) value
@@ -39,7 +39,7 @@ struct HeadWeights {
 
 // K5/K6 stage 1: features[n][361][pc+vc] = relu(conv1x1(act)); act is bf16 (+ optional bf16 low part) or fp32
 // NHWC [n][361][C]
-void launch_head_conv(const void* act, const void* act_lo, int act_is_f32, const HeadWeights& w, float* feat, int n, cudaStream_t s);
+void launch_head_conv(const void* act, const void* act_lo, int act_fmt /*0 bf16, 1 fp32, 2 fp16*/, const HeadWeights& w, float* feat, int n, cudaStream_t s);
 // K5-K7 stage 2: FC + softmax (optionally renormalised over a legal mask) and FC-ReLU-FC-tanh-value_transform
 void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* legal, int vt, float* policy,
                     float* value, int n, cudaStream_t s);
@@ -48,6 +48,6 @@ void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* leg
 void launch_conv3x3_f32(const float* in, const float* w_hwio, const float* bias, const float* res, float* out,
                         int n, int cin, int cout, int relu, cudaStream_t s);
 // bf16 <-> fp32 images for debug readback
-void launch_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t count, cudaStream_t s);
+void launch_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t count, int f16, cudaStream_t s);
 
 }  // namespace ug

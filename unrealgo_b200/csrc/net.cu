@@ -9,6 +9,8 @@
 #include <functional>
 #include <memory>
 
+#include <cuda_fp16.h>
+
 #include "conv3x3_tc.h"
 #include "tmap.h"
 
@@ -59,6 +61,13 @@ uint16_t f32_to_bf16_rn(float f) {
   return (uint16_t)(u >> 16);
 }
 
+uint16_t f32_to_f16_rn(float f) {
+  // clamp like the device path (numfmt.cuh): weights beyond the fp16 range saturate instead of becoming inf
+  if (f > 65504.f) f = 65504.f;
+  if (f < -65504.f) f = -65504.f;
+  return __half_as_ushort(__float2half_rn(f));
+}
+
 struct HostConv {
   std::vector<float> w;  // HWIO, folded
   std::vector<float> b;  // [cout]
@@ -107,7 +116,7 @@ bool load_conv(const TfBundle& ck, const ConvPlan& p, int ksize, HostConv* out, 
   return true;
 }
 
-bool make_conv_layer(const HostConv& hc, int cin_pad, ConvLayer* L, std::string* err) {
+bool make_conv_layer(const HostConv& hc, int cin_pad, bool f16, ConvLayer* L, std::string* err) {
   L->cin = hc.cin;
   L->cin_pad = cin_pad;
   L->cout = hc.cout;
@@ -117,7 +126,8 @@ bool make_conv_layer(const HostConv& hc, int cin_pad, ConvLayer* L, std::string*
     for (int ci = 0; ci < hc.cin; ++ci)
       for (int co = 0; co < hc.cout; ++co)
         packed[(size_t)co * ktot + tap * cin_pad + ci] =
-            f32_to_bf16_rn(hc.w[((size_t)tap * hc.cin + ci) * hc.cout + co]);
+            f16 ? f32_to_f16_rn(hc.w[((size_t)tap * hc.cin + ci) * hc.cout + co])
+                : f32_to_bf16_rn(hc.w[((size_t)tap * hc.cin + ci) * hc.cout + co]);
   if (!upload(&L->w_bf16, packed.data(), packed.size() * 2) ||
       !upload(&L->w_f32, hc.w.data(), hc.w.size() * 4) || !upload(&L->bias, hc.b.data(), hc.b.size() * 4)) {
     *err = "out of device memory uploading weights";
@@ -146,7 +156,7 @@ bool load_dense(const TfBundle& ck, const DensePlan& p, int in, std::vector<floa
   return true;
 }
 
-Weights* build_weights(const NetPlan& plan, const TfBundle& ck, std::string* err) {
+Weights* build_weights(const NetPlan& plan, const TfBundle& ck, bool f16, std::string* err) {
   std::unique_ptr<Weights> W(new Weights());
   HostConv stem;
   if (!load_conv(ck, plan.stem, 3, &stem, err)) return nullptr;
@@ -159,12 +169,12 @@ Weights* build_weights(const NetPlan& plan, const TfBundle& ck, std::string* err
   W->C = C;
   W->blocks = (int)plan.tower.size() / 2;
   W->convs.resize(1 + plan.tower.size());
-  if (!make_conv_layer(stem, kCinPad, &W->convs[0], err)) return nullptr;
+  if (!make_conv_layer(stem, kCinPad, f16, &W->convs[0], err)) return nullptr;
   for (size_t i = 0; i < plan.tower.size(); ++i) {
     HostConv hc;
     if (!load_conv(ck, plan.tower[i], 3, &hc, err)) return nullptr;
     if (hc.cin != C || hc.cout != C) { *err = "tower conv '" + plan.tower[i].kernel + "' is not C x C"; return nullptr; }
-    if (!make_conv_layer(hc, C, &W->convs[1 + i], err)) return nullptr;
+    if (!make_conv_layer(hc, C, f16, &W->convs[1 + i], err)) return nullptr;
   }
   HostConv pcv, vcv;
   if (!load_conv(ck, plan.policy_conv, 1, &pcv, err) || !load_conv(ck, plan.value_conv, 1, &vcv, err)) return nullptr;
@@ -263,8 +273,9 @@ bool ug_eval::ensure_workspace(int C) {
 
 int ug_eval::enqueue_encoder(Src kind, const void* d_src, int n, cudaStream_t s) {
   __nv_bfloat16* in = d_in.as<__nv_bfloat16>();
-  if (kind == SRC_PACKED) launch_encode_packed_nhwc(static_cast<const ug_packed_pos*>(d_src), in, n, s);
-  else launch_planes_to_nhwc(static_cast<const int8_t*>(d_src), kind == SRC_HWC ? 1 : 0, in, n, s);
+  const int f16 = precision == UG_PREC_FP16;
+  if (kind == SRC_PACKED) launch_encode_packed_nhwc(static_cast<const ug_packed_pos*>(d_src), in, n, f16, s);
+  else launch_planes_to_nhwc(static_cast<const int8_t*>(d_src), kind == SRC_HWC ? 1 : 0, in, n, f16, s);
   return 0;
 }
 
@@ -273,7 +284,7 @@ int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act, const 
   const int C = W.C;
   // block b: x = S[b&1] (stream), t = T, y = S[(b+1)&1]
   if (precision == UG_PREC_FP32) {
-    launch_nhwc_to_f32(d_in.as<__nv_bfloat16>(), f_in.as<float>(), n, s);
+    launch_nhwc_to_f32(d_in.as<__nv_bfloat16>(), f_in.as<float>(), n, 0, s);
     const ConvLayer& st = W.convs[0];
     launch_conv3x3_f32(f_in.as<float>(), st.w_f32.as<float>(), st.bias.as<float>(), nullptr, f_s[0].as<float>(),
                        n, UG_NUM_PLANES, C, 1, s);
@@ -298,6 +309,7 @@ int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act, const 
   ConvArgs a{};
   a.M = n * UG_NUM_POINTS;
   a.relu = 1;
+  a.f16 = precision == UG_PREC_FP16;
   a.cout = C;
   // stem: 32 stored input channels (17 planes + zeros), SWIZZLE_64B tiles; its output opens the residual stream
   a.cin = kCinPad;
@@ -340,7 +352,8 @@ int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act, const 
 int ug_eval::enqueue_heads(const void* act, const void* act_lo, int n, const uint32_t* d_leg, int vt, float* d_pol,
                            float* d_val, cudaStream_t s) {
   const HeadWeights hw = weights->head();
-  launch_head_conv(act, act_lo, precision == UG_PREC_FP32 ? 1 : 0, hw, d_feat.as<float>(), n, s);
+  launch_head_conv(act, act_lo, precision == UG_PREC_FP32 ? 1 : (precision == UG_PREC_FP16 ? 2 : 0), hw,
+                   d_feat.as<float>(), n, s);
   launch_head_fc(d_feat.as<float>(), hw, d_leg, vt, d_pol, d_val, n, s);
   return cudaGetLastError() == cudaSuccess ? 0 : fail(-1, "head kernel launch failed");
 }
@@ -401,7 +414,10 @@ ug_eval* ug_eval_create(int device, int precision, int max_batch) {
     return nullptr;
   }
   if (device < 0 || device >= count) { g_create_error = "bad device ordinal"; return nullptr; }
-  if (precision != UG_PREC_BF16 && precision != UG_PREC_FP32) { g_create_error = "bad precision"; return nullptr; }
+  if (precision != UG_PREC_BF16 && precision != UG_PREC_FP32 && precision != UG_PREC_FP16) {
+    g_create_error = "bad precision";
+    return nullptr;
+  }
   if (max_batch <= 0 || max_batch > 65536) { g_create_error = "max_batch outside [1, 65536]"; return nullptr; }
   cudaDeviceProp prop;
   cudaSetDevice(device);
@@ -481,7 +497,7 @@ int ug_eval_load_checkpoint(ug_eval* h, const char* prefix) {
   std::string err;
   TfBundle ck;
   if (!ck.open(h->ckpt_prefix, &err)) return h->fail(1, err);
-  Weights* W = build_weights(h->plan, ck, &err);
+  Weights* W = build_weights(h->plan, ck, h->precision == UG_PREC_FP16, &err);
   if (!W) return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err);
   if (!h->ensure_workspace(W->C)) { delete W; return 1; }
   cudaStreamSynchronize(h->stream);
@@ -626,9 +642,10 @@ static int encode_common(ug_eval* h, int what, const void* src, size_t src_bytes
   if (what == 0) {
     launch_encode_packed_chw(h->d_pos.as<ug_packed_pos>(), h->d_bytes.as<int8_t>(), n, s);
   } else {
-    if (what == 1) launch_encode_packed_nhwc(h->d_pos.as<ug_packed_pos>(), h->d_in.as<__nv_bfloat16>(), n, s);
-    else launch_planes_to_nhwc(h->d_planes.as<int8_t>(), 0, h->d_in.as<__nv_bfloat16>(), n, s);
-    launch_nhwc_to_bytes(h->d_in.as<__nv_bfloat16>(), h->d_bytes.as<int8_t>(), n, s);
+    const int f16 = h->precision == UG_PREC_FP16;
+    if (what == 1) launch_encode_packed_nhwc(h->d_pos.as<ug_packed_pos>(), h->d_in.as<__nv_bfloat16>(), n, f16, s);
+    else launch_planes_to_nhwc(h->d_planes.as<int8_t>(), 0, h->d_in.as<__nv_bfloat16>(), n, f16, s);
+    launch_nhwc_to_bytes(h->d_in.as<__nv_bfloat16>(), h->d_bytes.as<int8_t>(), n, f16, s);
   }
   cudaMemcpyAsync(out, h->d_bytes.p, out_bytes, cudaMemcpyDeviceToHost, s);
   const cudaError_t e = cudaStreamSynchronize(s);
@@ -660,7 +677,8 @@ int ug_eval_debug_layer(ug_eval* h, int layer, int n, float* out) {
   } else {
     DevBuf tmp;
     if (!tmp.alloc(count * 4)) return h->fail(-1, "out of memory");
-    launch_bf16_to_f32(is_t ? h->d_t.as<__nv_bfloat16>() : h->d_s_hi[sidx].as<__nv_bfloat16>(), tmp.as<float>(), count, s);
+    launch_bf16_to_f32(is_t ? h->d_t.as<__nv_bfloat16>() : h->d_s_hi[sidx].as<__nv_bfloat16>(), tmp.as<float>(), count,
+                       h->precision == UG_PREC_FP16, s);
     cudaMemcpyAsync(out, tmp.p, count * 4, cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
   }

@@ -142,9 +142,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate.
+// D[tmem] (+)= A[smem desc] * B[smem desc], 16-bit float inputs (format in idesc), fp32 accumulate.
 template <int CTAS>
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   if constexpr (CTAS == 1) {
     asm volatile(
@@ -207,9 +207,10 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   constexpr uint64_t layout = (ROW_BYTES == 128) ? 2 : 4;
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
-// kind::f16 instruction descriptor: C=f32, A=B=bf16, both K-major, M x N.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// kind::f16 instruction descriptor: C=f32, A and B both bf16 (format 1) or both fp16 (format 0), K-major, M x N.
+__host__ __device__ constexpr uint32_t make_idesc_16(int m, int n, int f16) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {

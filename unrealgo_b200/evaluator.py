@@ -13,7 +13,7 @@ import json
 import numpy as np
 
 from . import _lib
-from ._lib import (MASK_WORDS, NUM_MOVES, NUM_PLANES, NUM_POINTS, PACKED_POS_BYTES, PREC_BF16, PREC_FP32,  # noqa: F401
+from ._lib import (MASK_WORDS, NUM_MOVES, NUM_PLANES, NUM_POINTS, PACKED_POS_BYTES, PREC_BF16, PREC_FP16, PREC_FP32,  # noqa: F401
                    TR_FLIP_PROB, TR_FLIP_SIGN, TR_IDENTITY)
 
 DF_HWC, DF_CHW = 0, 1

@@ -1,0 +1,109 @@
+// Drop-in replacement for funcapproximator/DlTFNetworkEvaluator.h (reference lines :33-83) on top of the C ABI
+// in include/ugeval.h.  Same class name, namespace, template parameter, method names, argument types, return
+// values and throw behaviour, so search/UctBoardEvaluator.{h,cpp} and search/UctSearch.cpp compile unchanged
+// against it; no TensorFlow header is needed any more.
+//
+//   reference member (.cc line)                         C export
+//   DlTFNetworkEvaluator(graphPath, df)       :27-53    ug_eval_create + ug_eval_load_graph
+//   SetNetworkInput / SetNetworkOutput        :56-64    ug_eval_set_io
+//   LoadGraph                                 :77-83    ug_eval_load_graph   (<0 -> throw std::runtime_error)
+//   UpdateCheckPoint                          :230-236  ug_eval_load_checkpoint
+//   MetaGraphLoaded                           :239-241  ug_eval_ready
+//   Evaluate (CHW / HWC overloads)            :287-352  ug_eval_run_planes / ug_eval_run_planes_hwc
+//   ~DlTFNetworkEvaluator                     :67-69    ug_eval_destroy
+#ifndef UGEVAL_HOST_DLTFNETWORKEVALUATOR_H
+#define UGEVAL_HOST_DLTFNETWORKEVALUATOR_H
+
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ugeval.h"
+#include "DlConfig.h"
+
+#ifndef GO_MAX_SIZE
+static const int GO_MAX_SIZE = UG_BOARD_SIZE;
+static const int GO_MAX_MOVES = UG_NUM_MOVES;
+#endif
+const int BD_SIZE = UG_BOARD_SIZE;
+const int NUM_MAPS = UG_NUM_PLANES;
+const int FEATURE_SIZE = BD_SIZE * BD_SIZE * NUM_MAPS;
+// The reference caps batches at 16 (DlTFNetworkEvaluator.h:15) because EvalBuffer is statically sized; the
+// evaluator below accepts up to UGEVAL_MAX_BATCH per call.
+const int MAX_BATCHES = 16;
+#ifndef UGEVAL_MAX_BATCH
+#define UGEVAL_MAX_BATCH 512
+#endif
+
+enum DataFormat { DF_HWC = UG_DF_HWC, DF_CHW = UG_DF_CHW };  // funcapproximator/DataFormat.h:22-25
+
+namespace tensorflow {  // kept so that `tensorflow::DlTFNetworkEvaluator<bool>` in UctBoardEvaluator.h still names it
+
+template <typename T>
+class DlTFNetworkEvaluator {
+ public:
+  explicit DlTFNetworkEvaluator(const std::string& graphPath, DataFormat _df = DF_HWC)
+      : m_dataFormat(_df), m_h(ug_eval_create(device_from_env(), UG_PREC_BF16, UGEVAL_MAX_BATCH)) {
+    if (!m_h) throw std::runtime_error(std::string("Could not create evaluator: ") + ug_last_error(nullptr));
+    LoadGraph(graphPath);
+  }
+  DlTFNetworkEvaluator(const std::string& graphPath, const std::string& feature_input,
+                       const std::vector<std::string>& outputs, DataFormat _df = DF_HWC)
+      : m_dataFormat(_df), m_h(ug_eval_create(device_from_env(), UG_PREC_BF16, UGEVAL_MAX_BATCH)) {
+    if (!m_h) throw std::runtime_error(std::string("Could not create evaluator: ") + ug_last_error(nullptr));
+    SetNetworkInput(feature_input);
+    std::vector<std::string> o(outputs);
+    SetNetworkOutput(o);
+    LoadGraph(graphPath);
+  }
+  ~DlTFNetworkEvaluator() { ug_eval_destroy(m_h); }
+  DlTFNetworkEvaluator(const DlTFNetworkEvaluator&) = delete;
+  DlTFNetworkEvaluator& operator=(const DlTFNetworkEvaluator&) = delete;
+
+  void SetNetworkInput(std::string input) { ug_eval_set_io(m_h, input.c_str(), nullptr, 0); }
+  void SetNetworkOutput(std::vector<std::string>& output) {
+    std::vector<const char*> p;
+    for (const std::string& s : output) p.push_back(s.c_str());
+    // an empty list clears the names, like m_outputs.clear() in the reference
+    static const char* none = nullptr;
+    ug_eval_set_io(m_h, nullptr, p.empty() ? &none : p.data(), (int)p.size());
+  }
+
+  bool LoadGraph(const std::string& graphPath) {
+    const int rc = ug_eval_load_graph(m_h, graphPath.c_str());
+    if (rc < 0) throw std::runtime_error(ug_last_error(m_h));
+    return rc == 0;
+  }
+  bool UpdateCheckPoint(const std::string& checkpointPath) {
+    return ug_eval_load_checkpoint(m_h, checkpointPath.c_str()) == 0;
+  }
+  bool MetaGraphLoaded() { return ug_eval_ready(m_h) != 0; }
+
+  // value_transform comes from the DlConfig singleton, as at DlTFNetworkEvaluator.cc:300
+  void Evaluate(char feature[][NUM_MAPS][BD_SIZE][BD_SIZE], double actions_[][GO_MAX_MOVES], double value_[],
+                int numBatches = MAX_BATCHES) {
+    ug_eval_set_value_transform(m_h, (int)DlConfig::GetInstance().get_value_transform());
+    const int rc = ug_eval_run_planes(m_h, reinterpret_cast<const int8_t*>(feature), numBatches, &actions_[0][0], value_);
+    if (rc != 0) fprintf(stderr, "Running model failed: %s\n", ug_last_error(m_h));  // outputs untouched (.cc:315-317)
+  }
+  void Evaluate(char feature[][BD_SIZE][BD_SIZE][NUM_MAPS], double actions_[][GO_MAX_MOVES], double value_[],
+                int batch_size = MAX_BATCHES) {
+    ug_eval_set_value_transform(m_h, (int)DlConfig::GetInstance().get_value_transform());
+    const int rc = ug_eval_run_planes_hwc(m_h, reinterpret_cast<const int8_t*>(feature), batch_size, &actions_[0][0], value_);
+    if (rc != 0) fprintf(stderr, "Running model failed: %s\n", ug_last_error(m_h));
+  }
+
+  ug_eval* handle() { return m_h; }  // for the leaf queue (ug_queue_create)
+
+ protected:
+  static int device_from_env() {
+    const char* d = getenv("UGEVAL_DEVICE");
+    return d ? atoi(d) : 0;
+  }
+  DataFormat m_dataFormat;
+  ug_eval* m_h;
+};
+
+}  // namespace tensorflow
+#endif
