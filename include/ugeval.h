@@ -154,10 +154,45 @@ void ug_queue_destroy(ug_queue* q);
 int64_t ug_queue_submit(ug_queue* q, const ug_packed_pos* pos, const uint32_t* legal);
 /* blocks until the ticket's own result is ready; policy[362], *value */
 int ug_queue_wait(ug_queue* q, int64_t ticket, float* policy, float* value);
-/* counters: batches run, leaves evaluated, sum of batch sizes, timeouts */
+/* non-blocking variant: 1 = result copied (ticket consumed), 0 = not ready yet, <0 = error */
+int ug_queue_poll(ug_queue* q, int64_t ticket, float* policy, float* value);
+/* counters: batches run, leaves evaluated, flushes caused by the timeout */
 int ug_queue_stats(ug_queue* q, uint64_t* batches, uint64_t* leaves, uint64_t* flush_timeouts);
 /* pause the consumer, swap the checkpoint, resume (hot swap between searches, search/UctSearch.cpp:178-182) */
 int ug_queue_swap_checkpoint(ug_queue* q, const char* prefix);
+
+/* ------------------------------------------------------------------ self-play driver (the path's caller) */
+/* UctDeepPlayer::SelfPlayOneGame / DoSearch / UctSearch::DeepUctSearchTree (search/UctDeepPlayer.cpp:61-121,
+ * :288-349; search/UctSearch.cpp:803-854) for `games` independent games multiplexed over `threads` host threads
+ * and one leaf queue: every playout expands and evaluates one leaf (1 network evaluation per playout). */
+typedef struct ug_selfplay_config {
+  int games;               /* concurrent games on this evaluator (sharding unit across GPUs) */
+  int threads;             /* host threads driving them */
+  int playouts_per_move;   /* MAX_SEARCH_ITERATIONS is 4000 in the reference (search/UctDeepPlayer.cpp:15) */
+  int max_moves;           /* per game; 0 = 722 (m_maxGameLength, search/UctDeepPlayer.cpp:30) */
+  int max_batch;           /* leaf-queue batch cap (<= evaluator max_batch) */
+  int timeout_us;          /* leaf-queue flush timeout */
+  int reuse_tree;          /* dlcfg reuse_searchtree */
+  int random_opening_moves;/* harness option: first k moves uniformly random (0 = reference behaviour) */
+  float puct;              /* 0 = 2.5 (search/UctSearch.cpp:370) */
+  uint64_t seed;
+} ug_selfplay_config;
+typedef struct ug_selfplay_stats {
+  uint64_t playouts, evaluations, batches, flush_timeouts, moves, games_finished, terminal_leaves;
+  double seconds, playouts_per_s, mean_batch, mean_tree_nodes;
+} ug_selfplay_stats;
+/* moves_out (optional): [games][max_moves or 722] policy indices (361 = pass); n_moves_out: [games] */
+int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg, ug_selfplay_stats* stats, int16_t* moves_out,
+                    int* n_moves_out);
+
+/* test hooks: the driver's incremental board (goboard.h), to be checked against the oracle's restated GoBoard */
+void* ug_board_new(void);
+void ug_board_free(void* b);
+int ug_board_legal(void* b, int idx);
+void ug_board_play(void* b, int idx);
+void ug_board_pack(void* b, ug_packed_pos* out);
+int ug_board_generate(void* b, uint16_t* moves, uint32_t* legal);
+int ug_board_to_play(void* b);
 
 /* ------------------------------------------------------------------ dlcfg (DlConfig) */
 /* DlConfig(filename) + parse(), funcapproximator/DlConfig.cc:20-41. A missing file yields an empty map. */

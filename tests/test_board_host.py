@@ -1,0 +1,63 @@
+"""Host side of the path, no GPU: the self-play driver's incremental board (csrc/goboard.h) against the
+oracle's restatement of GoBoard + CollectFeatures' undo/replay walk.  Integer work => bit-exact."""
+import numpy as np
+
+import oracle
+from unrealgo_b200 import ProductBoard
+
+
+def _random_game(seed, length, pass_prob):
+    rng = np.random.default_rng(seed)
+    ob, pb = oracle.Board(), ProductBoard()
+    assert np.array_equal(pb.pack(), ob.pack())
+    for step in range(length):
+        # legality agrees on every point (simple ko, suicide, captures)
+        if step % 7 == 0:
+            for p in range(361):
+                assert pb.legal(p) == ob.is_legal(p), (seed, step, p)
+        if rng.random() < pass_prob:
+            mv = 361
+        else:
+            mv = 361
+            for _ in range(60):
+                p = int(rng.integers(0, 361))
+                if ob.is_legal(p):
+                    mv = p
+                    break
+        ob.play(mv)
+        pb.play(mv)
+        assert pb.to_play == ob.to_play
+        # the ring of packed positions == the masks the reference's undo/replay walk would visit
+        assert np.array_equal(pb.pack(), ob.pack()), (seed, step)
+    return ob, pb
+
+
+def test_incremental_history_matches_undo_walk():
+    for seed, length, pp in [(1, 40, 0.0), (2, 300, 0.02), (3, 450, 0.05), (4, 12, 0.3), (5, 600, 0.01)]:
+        _random_game(seed, length, pp)
+
+
+def test_generate_moves_excludes_eyes_and_illegal():
+    ob, pb = _random_game(9, 260, 0.0)
+    moves, mask = pb.generate()
+    assert moves[-1] == 361 and len(set(moves.tolist())) == len(moves)
+    for m in moves[:-1]:
+        assert ob.is_legal(int(m))
+        assert (mask[m >> 5] >> (m & 31)) & 1
+    legal_pts = {p for p in range(361) if ob.is_legal(p)}
+    dropped = legal_pts - set(int(m) for m in moves[:-1])
+    colors = ob.colors().reshape(19, 19)
+    me = ob.to_play
+    for p in dropped:  # every legal point that was not generated is a simple eye: all neighbours are own stones
+        y, x = divmod(p, 19)
+        for yy, xx in ((y - 1, x), (y + 1, x), (y, x - 1), (y, x + 1)):
+            if 0 <= yy < 19 and 0 <= xx < 19:
+                assert colors[yy, xx] == me
+
+
+def test_two_passes_end_move_generation():
+    pb = ProductBoard()
+    pb.play(361)
+    assert len(pb.generate()[0]) == 362 - 0  # empty board: every point + pass
+    pb.play(361)
+    assert len(pb.generate()[0]) == 0

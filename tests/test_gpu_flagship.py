@@ -19,7 +19,7 @@ def test_flagship_batch256_parity_and_properties(flagship):
     from oracle.net_oracle import GraphOracle
     from unrealgo_b200 import DlTFNetworkEvaluator
     packed, planes = oracle.synthetic_positions(256, seed=20260119)
-    ev = DlTFNetworkEvaluator(flagship[0], max_batch=256)
+    ev = DlTFNetworkEvaluator(flagship[0], max_batch=256)  # default arithmetic: fp16 operands, fp32 accumulate
     assert ev.UpdateCheckPoint(flagship[1])
     info = ev.info()
     assert (info["blocks"], info["filters"]) == (20, 256)
@@ -46,3 +46,12 @@ def test_flagship_batch256_parity_and_properties(flagship):
         pc, vc = ev.evaluate_packed(packed)
         assert np.array_equal(pc, p2) and np.array_equal(vc, v2)
     ev.close()
+    # bf16-operand mode on the same inputs: documented looser bound (8-bit mantissa through 41 convolutions)
+    from unrealgo_b200 import PREC_BF16
+    evb = DlTFNetworkEvaluator(flagship[0], max_batch=256, precision=PREC_BF16)
+    assert evb.UpdateCheckPoint(flagship[1])
+    pb, vb = evb.evaluate_packed(packed)
+    dpb, dvb = np.abs(pb - want_p).max(), np.abs(vb - want_v).max()
+    print(f"flagship bf16 mode: max|dpolicy|={dpb:.3e} max|dvalue|={dvb:.3e} mean|dpolicy|={np.abs(pb - want_p).mean():.3e}")
+    assert dpb <= 5e-3 and dvb <= 3e-2 and np.abs(pb - want_p).mean() <= 1e-5
+    evb.close()

@@ -1,0 +1,130 @@
+"""Q1 (leaf-batching queue) and the self-play driver on the GPU.
+
+Queue property the reference violates (SURVEY.md 3.1 defect 1, A.6.7): every submitted leaf gets exactly its
+own result — under many producer threads, random arrival, flush-on-timeout and a checkpoint swap mid-stream.
+Self-play: per-game search is sequential PUCT, so move sequences are a pure function of the weights — they must
+not depend on how many games/threads share the GPU (batch composition), which checks queue + evaluator +
+driver end to end."""
+import threading
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ev(ckpt, max_batch=128):
+    from unrealgo_b200 import DlTFNetworkEvaluator
+    ev = DlTFNetworkEvaluator(ckpt[0], max_batch=max_batch)
+    assert ev.UpdateCheckPoint(ckpt[1])
+    return ev
+
+
+def test_queue_every_leaf_gets_its_own_result(small_ckpt):
+    import oracle
+    from unrealgo_b200 import LeafQueue
+    packed, _ = oracle.synthetic_positions(400, seed=5)
+    ev = _ev(small_ckpt)
+    want_p, want_v = ev.evaluate_packed(packed[:128])
+    for lo in range(128, 400, 128):
+        p, v = ev.evaluate_packed(packed[lo:lo + 128])
+        want_p, want_v = np.concatenate([want_p, p]), np.concatenate([want_v, v])
+    q = LeafQueue(ev, max_batch=64, timeout_us=300)
+    errors = []
+    n_threads = 32
+
+    def producer(tid):
+        rng = np.random.default_rng(tid)
+        try:
+            for rep in range(40):
+                idx = int(rng.integers(0, 400))
+                if rng.random() < 0.3:
+                    time.sleep(float(rng.random()) * 2e-3)  # random arrival -> partial batches, timeouts
+                t = q.submit(packed[idx])
+                pol, val = q.wait(t)
+                if not (np.array_equal(pol, want_p[idx]) and val == want_v[idx]):
+                    errors.append((tid, rep, idx))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=producer, args=(i,)) for i in range(n_threads)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    st = q.stats()
+    assert not errors, errors[:5]
+    assert st["leaves"] == n_threads * 40 and st["batches"] >= st["leaves"] / 64
+    q.close()
+    ev.close()
+
+
+def test_queue_checkpoint_swap_midstream(small_ckpt, small_ckpt_b):
+    import oracle
+    from unrealgo_b200 import LeafQueue
+    packed, _ = oracle.synthetic_positions(64, seed=6)
+    ev_a, ev_b = _ev(small_ckpt), _ev(small_ckpt_b)
+    pa, va = ev_a.evaluate_packed(packed)
+    pb, vb = ev_b.evaluate_packed(packed)
+    ev_b.close()
+    q = LeafQueue(ev_a, max_batch=32, timeout_us=200)
+    stop = threading.Event()
+    bad = []
+
+    def producer(tid):
+        rng = np.random.default_rng(100 + tid)
+        while not stop.is_set():
+            idx = int(rng.integers(0, 64))
+            pol, val = q.wait(q.submit(packed[idx]))
+            is_a = np.array_equal(pol, pa[idx]) and val == va[idx]
+            is_b = np.array_equal(pol, pb[idx]) and val == vb[idx]
+            if not (is_a or is_b):  # never a mixture or a stale neighbour's result
+                bad.append((tid, idx))
+
+    threads = [threading.Thread(target=producer, args=(i,)) for i in range(8)]
+    for t in threads:
+        t.start()
+    time.sleep(0.2)
+    assert q.swap_checkpoint(small_ckpt_b[1])
+    time.sleep(0.2)
+    stop.set()
+    for t in threads:
+        t.join()
+    pol, val = q.wait(q.submit(packed[3]))
+    assert np.array_equal(pol, pb[3]) and val == vb[3]  # the new weights are live
+    assert not bad, bad[:5]
+    q.close()
+    ev_a.close()
+
+
+def test_selfplay_is_deterministic_and_batch_independent(small_ckpt):
+    from unrealgo_b200 import selfplay
+    ev = _ev(small_ckpt, max_batch=64)
+    kw = dict(playouts_per_move=24, max_moves=14, random_opening_moves=3, seed=7, record_moves=True, max_batch=64)
+    st1, g1 = selfplay(ev, games=6, threads=1, **kw)
+    st2, g2 = selfplay(ev, games=24, threads=4, **kw)
+    assert g2[:6] == g1                       # same seeds -> same games, whatever shares the batch
+    assert len({tuple(g) for g in g2}) > 1    # the random openings do diversify
+    assert st1["moves"] == 6 * 14 and st2["moves"] == 24 * 14
+    assert st2["playouts"] == st2["evaluations"] + st2["terminal_leaves"] == 24 * 14 * 24
+    assert st2["mean_batch"] > st1["mean_batch"]
+    # without tree reuse each move searches from scratch: still deterministic, generally different visit counts
+    st3, g3 = selfplay(ev, games=6, threads=2, reuse_tree=False, **kw)
+    st4, g4 = selfplay(ev, games=6, threads=1, reuse_tree=False, **kw)
+    assert g3 == g4
+    ev.close()
+
+
+def test_selfplay_moves_are_legal_and_follow_visit_counts(small_ckpt):
+    import oracle
+    from unrealgo_b200 import selfplay
+    ev = _ev(small_ckpt, max_batch=64)
+    _, games = selfplay(ev, games=4, threads=2, playouts_per_move=16, max_moves=40, random_opening_moves=6, seed=3,
+                        record_moves=True, max_batch=64)
+    for g in games:
+        b = oracle.Board()
+        for mv in g:
+            assert b.is_legal(mv), (g, mv)   # legality judged by the oracle's board, not the driver's
+            b.play(mv)
+    ev.close()

@@ -37,6 +37,19 @@ class NetInfo(C.Structure):
     ]
 
 
+class SelfplayConfig(C.Structure):
+    _fields_ = [("games", C.c_int), ("threads", C.c_int), ("playouts_per_move", C.c_int), ("max_moves", C.c_int),
+                ("max_batch", C.c_int), ("timeout_us", C.c_int), ("reuse_tree", C.c_int),
+                ("random_opening_moves", C.c_int), ("puct", C.c_float), ("seed", C.c_uint64)]
+
+
+class SelfplayStats(C.Structure):
+    _fields_ = [("playouts", C.c_uint64), ("evaluations", C.c_uint64), ("batches", C.c_uint64),
+                ("flush_timeouts", C.c_uint64), ("moves", C.c_uint64), ("games_finished", C.c_uint64),
+                ("terminal_leaves", C.c_uint64), ("seconds", C.c_double), ("playouts_per_s", C.c_double),
+                ("mean_batch", C.c_double), ("mean_tree_nodes", C.c_double)]
+
+
 class BenchResult(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_encoder", C.c_float), ("ms_tower", C.c_float),
                 ("ms_heads", C.c_float), ("launches_per_pass", C.c_int)]
@@ -73,6 +86,15 @@ SIGNATURES = {
     "ug_queue_destroy": (None, [C.c_void_p]),
     "ug_queue_submit": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ug_queue_wait": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ug_queue_poll": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ug_selfplay_run": (C.c_int, [C.c_void_p, C.POINTER(SelfplayConfig), C.POINTER(SelfplayStats), C.c_void_p, C.c_void_p]),
+    "ug_board_new": (C.c_void_p, []),
+    "ug_board_free": (None, [C.c_void_p]),
+    "ug_board_legal": (C.c_int, [C.c_void_p, C.c_int]),
+    "ug_board_play": (None, [C.c_void_p, C.c_int]),
+    "ug_board_pack": (None, [C.c_void_p, C.c_void_p]),
+    "ug_board_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ug_board_to_play": (C.c_int, [C.c_void_p]),
     "ug_queue_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ug_queue_swap_checkpoint": (C.c_int, [C.c_void_p, C.c_char_p]),
     "ug_dlcfg_open": (C.c_void_p, [C.c_char_p]),

@@ -197,7 +197,7 @@ ug_queue* ug_queue_create(ug_eval* h, int max_batch, int timeout_us, int capacit
   if (!h) return nullptr;
   if (max_batch <= 0 || max_batch > h->max_batch) { h->fail(-1, "queue max_batch exceeds the evaluator's"); return nullptr; }
   uint64_t cap = 1;
-  while (cap < (uint64_t)(capacity > 2 * max_batch ? capacity : 2 * max_batch)) cap <<= 1;
+  while (cap < (uint64_t)(capacity > 2 * max_batch ? capacity : 2 * max_batch) || cap < 4) cap <<= 1;
   cudaSetDevice(h->device);
   ug_queue* q = new ug_queue();
   q->eval = h;
@@ -297,6 +297,17 @@ int ug_queue_wait(ug_queue* q, int64_t ticket, float* policy, float* value) {
   if (value) *value = sl.value;
   sl.seq.store(t + q->capacity, std::memory_order_release);  // free for the next lap
   return q->error.load() ? -1 : 0;
+}
+
+int ug_queue_poll(ug_queue* q, int64_t ticket, float* policy, float* value) {
+  if (!q || ticket < 0) return -1;
+  const uint64_t t = (uint64_t)ticket;
+  Slot& sl = q->slots[t & q->mask];
+  if (sl.seq.load(std::memory_order_acquire) != t + 2) return q->quit.load(std::memory_order_acquire) ? -1 : 0;
+  if (policy) memcpy(policy, sl.policy, sizeof(sl.policy));
+  if (value) *value = sl.value;
+  sl.seq.store(t + q->capacity, std::memory_order_release);
+  return q->error.load() ? -1 : 1;
 }
 
 int ug_queue_stats(ug_queue* q, uint64_t* batches, uint64_t* leaves, uint64_t* flush_timeouts) {

@@ -75,7 +75,7 @@ def inspect_model(graph_path, ckpt_prefix=None, input_name=None, outputs=None):
 class DlTFNetworkEvaluator:
     """DlTFNetworkEvaluator<bool>: LoadGraph / UpdateCheckPoint / Evaluate, plus the native packed entry points."""
 
-    def __init__(self, graphPath="", df=DF_HWC, feature_input=None, outputs=None, device=0, precision=PREC_BF16,
+    def __init__(self, graphPath="", df=DF_HWC, feature_input=None, outputs=None, device=0, precision=PREC_FP16,
                  max_batch=256):
         self._lib = _lib.load()
         self._h = self._lib.ug_eval_create(device, precision, max_batch)
@@ -288,3 +288,57 @@ class LeafQueue:
 
     def swap_checkpoint(self, prefix):
         return self._lib.ug_queue_swap_checkpoint(self._q, prefix.encode()) == 0
+
+
+class ProductBoard:
+    """test hook over the self-play driver's incremental board (csrc/goboard.h)"""
+
+    def __init__(self):
+        self._lib = _lib.load()
+        self._b = self._lib.ug_board_new()
+
+    def __del__(self):
+        if getattr(self, "_b", None):
+            self._lib.ug_board_free(self._b)
+            self._b = None
+
+    @property
+    def to_play(self):
+        return self._lib.ug_board_to_play(self._b)
+
+    def legal(self, idx):
+        return bool(self._lib.ug_board_legal(self._b, idx))
+
+    def play(self, idx):
+        self._lib.ug_board_play(self._b, idx)
+
+    def pack(self):
+        out = np.zeros(PACKED_POS_BYTES // 4, np.uint32)
+        self._lib.ug_board_pack(self._b, out.ctypes.data)
+        return out
+
+    def generate(self):
+        moves = np.zeros(NUM_MOVES, np.uint16)
+        legal = np.zeros(MASK_WORDS, np.uint32)
+        n = self._lib.ug_board_generate(self._b, moves.ctypes.data, legal.ctypes.data)
+        return moves[:n].copy(), legal
+
+
+def selfplay(evaluator, games, playouts_per_move, threads=4, max_moves=0, max_batch=256, timeout_us=200,
+             reuse_tree=True, random_opening_moves=0, puct=0.0, seed=1, record_moves=False):
+    """ug_selfplay_run: returns (stats dict, list of move lists or None)"""
+    lib = _lib.load()
+    cfg = _lib.SelfplayConfig(games, threads, playouts_per_move, max_moves, max_batch, timeout_us,
+                              1 if reuse_tree else 0, random_opening_moves, puct, seed)
+    st = _lib.SelfplayStats()
+    cap = max_moves if max_moves > 0 else 722
+    moves = n_moves = None
+    if record_moves:
+        moves = np.zeros((games, cap), np.int16)
+        n_moves = np.zeros(games, np.int32)
+    rc = lib.ug_selfplay_run(evaluator._h, C.byref(cfg), C.byref(st), moves.ctypes.data if record_moves else None,
+                             n_moves.ctypes.data if record_moves else None)
+    if rc != 0:
+        raise RuntimeError(f"ug_selfplay_run failed ({rc}): " + evaluator._err())
+    stats = {f: getattr(st, f) for f, _ in _lib.SelfplayStats._fields_}
+    return stats, ([moves[i, :n_moves[i]].tolist() for i in range(games)] if record_moves else None)

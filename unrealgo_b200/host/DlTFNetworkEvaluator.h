@@ -15,6 +15,8 @@
 #define UGEVAL_HOST_DLTFNETWORKEVALUATOR_H
 
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -44,13 +46,13 @@ template <typename T>
 class DlTFNetworkEvaluator {
  public:
   explicit DlTFNetworkEvaluator(const std::string& graphPath, DataFormat _df = DF_HWC)
-      : m_dataFormat(_df), m_h(ug_eval_create(device_from_env(), UG_PREC_BF16, UGEVAL_MAX_BATCH)) {
+      : m_dataFormat(_df), m_h(ug_eval_create(device_from_env(), precision_from_env(), UGEVAL_MAX_BATCH)) {
     if (!m_h) throw std::runtime_error(std::string("Could not create evaluator: ") + ug_last_error(nullptr));
     LoadGraph(graphPath);
   }
   DlTFNetworkEvaluator(const std::string& graphPath, const std::string& feature_input,
                        const std::vector<std::string>& outputs, DataFormat _df = DF_HWC)
-      : m_dataFormat(_df), m_h(ug_eval_create(device_from_env(), UG_PREC_BF16, UGEVAL_MAX_BATCH)) {
+      : m_dataFormat(_df), m_h(ug_eval_create(device_from_env(), precision_from_env(), UGEVAL_MAX_BATCH)) {
     if (!m_h) throw std::runtime_error(std::string("Could not create evaluator: ") + ug_last_error(nullptr));
     SetNetworkInput(feature_input);
     std::vector<std::string> o(outputs);
@@ -97,6 +99,13 @@ class DlTFNetworkEvaluator {
   ug_eval* handle() { return m_h; }  // for the leaf queue (ug_queue_create)
 
  protected:
+  // default arithmetic: fp16 operands / fp32 accumulation (meets the stated tolerance); UGEVAL_PRECISION=bf16|fp32
+  static int precision_from_env() {
+    const char* p = getenv("UGEVAL_PRECISION");
+    if (p && !strcmp(p, "bf16")) return UG_PREC_BF16;
+    if (p && !strcmp(p, "fp32")) return UG_PREC_FP32;
+    return UG_PREC_FP16;
+  }
   static int device_from_env() {
     const char* d = getenv("UGEVAL_DEVICE");
     return d ? atoi(d) : 0;
