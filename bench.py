@@ -32,6 +32,13 @@ def parse():
     ap.add_argument("--blocks", type=int, default=20)
     ap.add_argument("--filters", type=int, default=256)
     ap.add_argument("--ctas", type=int, default=0, help="tower kernel cta_group (1/2); 0 = library default")
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
+                    help="operand format of the tcgen05 tower (same MMA rate; fp16 meets the parity tolerance)")
+    ap.add_argument("--no-selfplay", action="store_true")
+    ap.add_argument("--sp-games", type=int, default=512, help="concurrent self-play games per GPU")
+    ap.add_argument("--sp-threads", type=int, default=0, help="search threads per GPU (0 = auto)")
+    ap.add_argument("--sp-playouts", type=int, default=1600, help="playouts per move (BASELINE configs[2])")
+    ap.add_argument("--sp-moves", type=int, default=2, help="moves per game in the bounded self-play sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -152,7 +159,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from unrealgo_b200 import DlTFNetworkEvaluator, synth
+    from unrealgo_b200 import PREC_BF16, PREC_FP16, DlTFNetworkEvaluator, selfplay, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -162,7 +169,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
     meta, prefix = checkpoint(args.blocks, args.filters)
-    ev = DlTFNetworkEvaluator(meta, device=local, max_batch=B)
+    ev = DlTFNetworkEvaluator(meta, device=local, max_batch=B,
+                              precision=PREC_FP16 if args.precision == "fp16" else PREC_BF16)
     assert ev.UpdateCheckPoint(prefix), ev._err()
     if args.ctas:
         ev.set_conv_ctas(args.ctas)
@@ -234,6 +242,28 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # self-play playouts/s (BASELINE configs[2]/[3]): games sharded per GPU, no collective on the data path
+    sp = None
+    if not args.no_selfplay:
+        threads = args.sp_threads or max(2, min(12, (os.cpu_count() or 8) // max(world, 1) - 2))
+        if world > 1:
+            dist.barrier()
+        st, _ = selfplay(ev, games=args.sp_games, threads=threads, playouts_per_move=args.sp_playouts,
+                         max_moves=args.sp_moves, max_batch=B, timeout_us=300, reuse_tree=True,
+                         random_opening_moves=1, seed=1000 + rank)
+        tsp = torch.tensor([float(st["playouts"]), float(st["evaluations"])], dtype=torch.float64, device="cuda")
+        tsec = torch.tensor([st["seconds"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tsp, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+        sp = {"playouts_per_s": float(tsp[0].item()) / float(tsec.item()), "unit": "playouts/s",
+              "evaluations_per_s": float(tsp[1].item()) / float(tsec.item()), "seconds": float(tsec.item()),
+              "games_per_gpu": args.sp_games, "search_threads_per_gpu": threads, "host_cpus": os.cpu_count(),
+              "playouts_per_move": args.sp_playouts, "moves_per_game_sampled": args.sp_moves,
+              "mean_batch_rank0": st["mean_batch"], "flush_timeouts_rank0": st["flush_timeouts"],
+              "mean_tree_nodes_rank0": st["mean_tree_nodes"], "reuse_searchtree": True,
+              "sharding": "independent games per GPU, weights replicated, no collective"}
+
     # roofline of the dominant kernel (3x3 CxC tower conv): CUDA-event brackets inside the library, on its stream
     br = ev.bench(host_packed[0], 20)
     ev.set_debug_stop(0)
@@ -257,11 +287,13 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "bf16", "data": "synthetic",
             "config": {"workload": f"batched evaluation of {B} synthetic 19x19 positions per GPU, "
                                    f"{info['blocks']}-block x {C}-filter dlcfg-19 net (BASELINE configs[1]), "
                                    "seeded synthetic TF-format checkpoint",
                        "batch": B, "blocks": info["blocks"], "filters": C, "conv_cta_group": info["conv_ctas"],
+                       "arithmetic": f"{args.precision} operands (tcgen05 kind::f16), fp32 accumulation in TMEM, "
+                                     "fp32 bias/residual epilogue, residual stream carried as hi+lo 16-bit pair",
                        "l2": "flushed between timed steps (256 MiB write outside the event bracket); 8 input batches rotated",
                        "flops_per_position": info["flops_per_position"],
                        "tensor_frac_of_burst_peak_whole_step": value / world * info["flops_per_position"] / (burst * 1e12),
@@ -279,6 +311,8 @@ def main():
                          "kernel": f"conv3x3_tc_kernel<64,{info['conv_ctas']}> (3x3 {C}->{C}, M={B * 361})",
                          "flops_per_launch": conv_flops, "ms_per_launch": conv_ms, "traffic": None},
         }
+        if sp is not None:
+            out["selfplay"] = sp
         if not args.no_cpu_baseline and world == 1:
             try:
                 out["cpu_baseline"] = cpu_reference(args, args.cpu_seconds, 16)
