@@ -94,6 +94,8 @@ int ug_eval_set_value_transform(ug_eval* h, int vt);
 int ug_eval_info(const ug_eval* h, ug_net_info* out);
 /* use cta_group::1 or ::2 tower kernels (default 2); testing/benchmark knob */
 int ug_eval_set_conv_ctas(ug_eval* h, int ctas);
+/* carry the residual stream as a hi+lo pair of 16-bit tensors (1) or as one 16-bit tensor (0); numerics knob */
+int ug_eval_set_residual_split(ug_eval* h, int on);
 
 /* Evaluate(char feature[][17][19][19], double policies[][362], double value[], n), .cc:287-318.
  * HOST buffers, synchronous.  On failure outputs are left untouched (as .cc:315-317) and <0 is returned. */

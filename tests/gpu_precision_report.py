@@ -15,9 +15,11 @@ for blocks, filters, n, seed in [(2, 64, 64, 11), (3, 256, 64, 13), (10, 128, 12
     d = tempfile.mkdtemp()
     meta, prefix = tfformat.write_synthetic_checkpoint(d, blocks, filters, seed=seed)
     want_p, want_v = GraphOracle(meta, prefix).evaluate_reference(planes[:n])
-    for name, prec in [("bf16", PREC_BF16), ("fp16", PREC_FP16), ("fp32", PREC_FP32)]:
+    for name, prec, split in [("bf16", PREC_BF16, 1), ("bf16-nosplit", PREC_BF16, 0), ("fp16", PREC_FP16, 1),
+                              ("fp16-nosplit", PREC_FP16, 0), ("fp32", PREC_FP32, 1)]:
         ev = DlTFNetworkEvaluator(meta, precision=prec, max_batch=n)
         assert ev.UpdateCheckPoint(prefix)
+        ev.set_residual_split(split)
         p, v = ev.evaluate_packed(packed[:n])
         dp, dv = np.abs(p - want_p), np.abs(v - want_v)
         print(f"{blocks}x{filters} seed {seed} n={n} {name}: max|dp|={dp.max():.3e} mean|dp|={dp.mean():.3e} "

@@ -315,12 +315,13 @@ int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act, const 
   a.cin = kCinPad;
   a.bias = W.convs[0].bias.as<float>();
   a.out = d_s_hi[0].as<__nv_bfloat16>();
-  a.out_lo = d_s_lo[0].as<__nv_bfloat16>();
+  const bool split = resid_split;
+  a.out_lo = split ? d_s_lo[0].as<__nv_bfloat16>() : nullptr;
   cudaError_t e = conv3x3_tc_launch(tm_in, W.convs[0].tm_w[ctas - 1], a, 32, ctas, sms, s);
   if (e != cudaSuccess) return fail(-1, std::string("stem conv launch: ") + cudaGetErrorString(e));
   a.cin = C;
   *final_act = d_s_hi[0].p;
-  *final_lo = d_s_lo[0].p;
+  *final_lo = split ? d_s_lo[0].p : nullptr;
   for (int b = 0; b < W.blocks && debug_stop != 0; ++b) {
     const int x = b & 1, y = x ^ 1;
     const ConvLayer& c1 = W.convs[1 + 2 * b];
@@ -337,13 +338,13 @@ int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act, const 
     if (debug_stop == 2 * b + 1) break;
     a.bias = c2.bias.as<float>();
     a.residual = d_s_hi[x].as<__nv_bfloat16>();
-    a.residual_lo = d_s_lo[x].as<__nv_bfloat16>();
+    a.residual_lo = split ? d_s_lo[x].as<__nv_bfloat16>() : nullptr;
     a.out = d_s_hi[y].as<__nv_bfloat16>();
-    a.out_lo = d_s_lo[y].as<__nv_bfloat16>();
+    a.out_lo = split ? d_s_lo[y].as<__nv_bfloat16>() : nullptr;
     e = conv3x3_tc_launch(tm_t, c2.tm_w[ctas - 1], a, 64, ctas, sms, s);
     if (e != cudaSuccess) return fail(-1, std::string("tower conv launch: ") + cudaGetErrorString(e));
     *final_act = d_s_hi[y].p;
-    *final_lo = d_s_lo[y].p;
+    *final_lo = split ? d_s_lo[y].p : nullptr;
     if (debug_stop == 2 * b + 2) break;
   }
   return 0;
@@ -375,7 +376,7 @@ int ug_eval::enqueue(Src kind, const void* d_src, int n, const uint32_t* d_leg, 
   if (n <= 0 || n > max_batch) return fail(-1, "batch size " + std::to_string(n) + " outside [1, max_batch]");
   if (!use_graphs) return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
   const GraphKey key((int)kind, n, d_src, (const void*)d_leg, (const void*)d_pol, (const void*)d_val, vt,
-                     conv_ctas * 4 + precision + (debug_stop + 1) * 16);
+                     conv_ctas * 4 + precision + (resid_split ? 8192 : 0) + (debug_stop + 1) * 16);
   auto it = graphs.find(key);
   if (it == graphs.end()) {
     if (graphs.size() > 256) drop_graphs();
@@ -434,6 +435,8 @@ ug_eval* ug_eval_create(int device, int precision, int max_batch) {
   h->use_graphs = !(ng && ng[0] == '1');
   const char* cc = getenv("UGEVAL_CONV_CTAS");
   if (cc && (cc[0] == '1' || cc[0] == '2')) h->conv_ctas = cc[0] - '0';
+  const char* rs = getenv("UGEVAL_RESID_SPLIT");
+  if (rs && (rs[0] == '0' || rs[0] == '1')) h->resid_split = rs[0] == '1';
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
     g_create_error = "cannot create stream";
     delete h;
@@ -525,6 +528,12 @@ int ug_eval_set_debug_stop(ug_eval* h, int layer) {
 int ug_eval_set_conv_ctas(ug_eval* h, int ctas) {
   if (!h || (ctas != 1 && ctas != 2)) return -1;
   h->conv_ctas = ctas;
+  return 0;
+}
+
+int ug_eval_set_residual_split(ug_eval* h, int on) {
+  if (!h) return -1;
+  h->resid_split = on != 0;
   return 0;
 }
 

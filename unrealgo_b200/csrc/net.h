@@ -58,6 +58,7 @@ struct ug_eval {
   int max_batch = 0;
   int sms = 148;
   int conv_ctas = 2;
+  bool resid_split = true;  // carry the residual stream as hi + lo 16-bit pair (numerics)
   int value_transform = UG_TR_IDENTITY;
   bool use_graphs = true;
   int debug_stop = -1;  // >= 0: stop the tower after that layer (0 = stem, 2b+1 / 2b+2 = convs of block b)

@@ -130,6 +130,9 @@ class DlTFNetworkEvaluator:
         if self._lib.ug_eval_set_conv_ctas(self._h, ctas) != 0:
             raise ValueError("ctas must be 1 or 2")
 
+    def set_residual_split(self, on):
+        self._lib.ug_eval_set_residual_split(self._h, 1 if on else 0)
+
     def info(self):
         ni = _lib.NetInfo()
         if self._lib.ug_eval_info(self._h, C.byref(ni)) != 0:
