@@ -94,6 +94,9 @@ int ug_eval_set_value_transform(ug_eval* h, int vt);
 int ug_eval_info(const ug_eval* h, ug_net_info* out);
 /* use cta_group::1 or ::2 tower kernels (default 2); testing/benchmark knob */
 int ug_eval_set_conv_ctas(ug_eval* h, int ctas);
+/* tower kernel generation: 1 = TMA-im2col operand staging (conv3x3_tc.cu), 2 = shared-memory-resident input tile
+ * with shifted-descriptor taps and TMA-staged epilogue (conv3x3_v2.cu, default); testing/benchmark knob */
+int ug_eval_set_conv_impl(ug_eval* h, int impl);
 /* carry the residual stream as a hi+lo pair of 16-bit tensors (1) or as one 16-bit tensor (0); numerics knob */
 int ug_eval_set_residual_split(ug_eval* h, int on);
 
@@ -145,6 +148,14 @@ int ug_eval_bench(ug_eval* h, const ug_packed_pos* host_pos, int n, int iters, u
  * weights [cout][9*cin], fp32 bias, optional bf16 residual).  ck in {32,64}, ctas in {1,2}. */
 int ug_k_conv3x3_bf16(int device, const void* d_in, const void* d_w, const float* d_bias, const void* d_res,
                       void* d_out, int n, int cin, int cout, int relu, int ck, int ctas);
+
+/* Raw entry of the second-generation conv kernel (shared-memory-resident input tile, shifted-descriptor taps,
+ * TMA-staged epilogue): 16-bit NHWC in/out on device buffers of n_alloc*361 rows, optional hi/lo residual and
+ * lo output; runs once, then `iters` more times between CUDA events (ms_out = average launch time).
+ * d_prof (optional, device, [74][16] int64): per-cluster stall-cycle counters of the last launch. */
+int ug_k_conv3x3_v2(int device, const void* d_in, const void* d_w, const float* d_bias, const void* d_res_hi,
+                    const void* d_res_lo, void* d_out_hi, void* d_out_lo, int n, int n_alloc, int cin, int cout,
+                    int relu, int f16, int desc_mode, int iters, float* ms_out, long long* d_prof);
 
 /* ------------------------------------------------------------------ leaf-batching queue (Q1) */
 /* Replaces EvalBuffer/EvalMsg + NetworkEvalThread's spin loop (search/UctSearch.h:59-72,126-130;

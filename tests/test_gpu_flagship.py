@@ -53,5 +53,5 @@ def test_flagship_batch256_parity_and_properties(flagship):
     pb, vb = evb.evaluate_packed(packed)
     dpb, dvb = np.abs(pb - want_p).max(), np.abs(vb - want_v).max()
     print(f"flagship bf16 mode: max|dpolicy|={dpb:.3e} max|dvalue|={dvb:.3e} mean|dpolicy|={np.abs(pb - want_p).mean():.3e}")
-    assert dpb <= 5e-3 and dvb <= 3e-2 and np.abs(pb - want_p).mean() <= 1e-5
+    assert dpb <= 1e-2 and dvb <= 6e-2 and np.abs(pb - want_p).mean() <= 1e-5
     evb.close()

@@ -68,6 +68,7 @@ SIGNATURES = {
     "ug_eval_set_value_transform": (C.c_int, [C.c_void_p, C.c_int]),
     "ug_eval_info": (C.c_int, [C.c_void_p, C.POINTER(NetInfo)]),
     "ug_eval_set_conv_ctas": (C.c_int, [C.c_void_p, C.c_int]),
+    "ug_eval_set_conv_impl": (C.c_int, [C.c_void_p, C.c_int]),
     "ug_eval_set_residual_split": (C.c_int, [C.c_void_p, C.c_int]),
     "ug_eval_run_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ug_eval_run_planes_hwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -83,6 +84,9 @@ SIGNATURES = {
     "ug_eval_bench": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(BenchResult)]),
     "ug_k_conv3x3_bf16": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ug_k_conv3x3_v2": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(C.c_float), C.c_void_p]),
     "ug_queue_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "ug_queue_destroy": (None, [C.c_void_p]),
     "ug_queue_submit": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1,0 +1,42 @@
+// Launch interface of the second-generation tcgen05 3x3 convolution (conv3x3_v2.cu): input tile resident in
+// shared memory, filter taps as shifted descriptors + lane masks, TMA-staged epilogue.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ug {
+
+struct ConvV2Args {
+  const float* bias;      // [cout] folded batch-norm offset (fp32)
+  int M;                  // n * 361 output pixels
+  int cin;                // input channels as stored (multiple of ck)
+  int cout;               // <= 256, multiple of 32
+  int relu;
+  int f16;                // operands/outputs are fp16 (else bf16)
+  int has_res, has_res_lo, has_out_lo;
+  int desc_mode;          // bring-up knobs: bit 0 set the descriptor's matrix-base-offset field for shifted A tiles;
+                          // bit 1 unmasked MMA form and bit 2 no tap shift (both give wrong results: timing probes)
+  int num_tiles;          // filled by the launcher
+  long long* prof;        // optional [clusters][16] cycle counters (bring-up instrumentation), else null
+};
+
+// Tensor maps (see tmap.h): a = halo tile over the input [rows][cin] (box {ck, 168}); w = packed weights
+// (box {ck, cout/2}); res_* = residual [rows][cout] (box {32, 128}, SWIZZLE_64B); out_* = outputs (box {32, 32}).
+// res_* / out_lo may be null when the matching has_* flag is 0.
+struct ConvV2Maps {
+  const CUtensorMap* a;
+  const CUtensorMap* w;
+  const CUtensorMap* res_hi;
+  const CUtensorMap* res_lo;
+  const CUtensorMap* out_hi;
+  const CUtensorMap* out_lo;
+};
+
+cudaError_t conv3x3_v2_launch(const ConvV2Maps& maps, ConvV2Args a, int ck, int device, int sms,
+                              cudaStream_t stream);
+int conv3x3_v2_smem_bytes(int ck);
+// uploads the lane-mask table for `device` (cudaMalloc + copy): call once outside any stream capture
+bool conv3x3_v2_prepare(int device);
+
+}  // namespace ug

@@ -12,6 +12,7 @@
 #include <cuda_fp16.h>
 
 #include "conv3x3_tc.h"
+#include "conv3x3_v2.h"
 #include "tmap.h"
 
 namespace ug {
@@ -258,6 +259,20 @@ bool ug_eval::ensure_workspace(int C) {
   for (int i = 0; i < 2; ++i)
     if (!make_tmap_act_im2col(&tm_s[i], d_s_hi[i].p, max_batch, C, 64, &err)) { last_error = err; return false; }
   if (!make_tmap_act_im2col(&tm_t, d_t.p, max_batch, C, 64, &err)) { last_error = err; return false; }
+  {
+    const long rows = (long)max_batch * UG_NUM_POINTS;
+    bool ok2 = make_tmap_rows(&v2_a_in, d_in.p, rows, kCinPad, 32, 168, &err) &&
+               make_tmap_rows(&v2_a_t, d_t.p, rows, C, 64, 168, &err) &&
+               make_tmap_rows(&v2_out_t, d_t.p, rows, C, 32, 32, &err);
+    for (int i = 0; i < 2 && ok2; ++i)
+      ok2 = make_tmap_rows(&v2_a_s[i], d_s_hi[i].p, rows, C, 64, 168, &err) &&
+            make_tmap_rows(&v2_res_hi[i], d_s_hi[i].p, rows, C, 32, 128, &err) &&
+            make_tmap_rows(&v2_res_lo[i], d_s_lo[i].p, rows, C, 32, 128, &err) &&
+            make_tmap_rows(&v2_out_hi[i], d_s_hi[i].p, rows, C, 32, 32, &err) &&
+            make_tmap_rows(&v2_out_lo[i], d_s_lo[i].p, rows, C, 32, 32, &err);
+    if (!ok2) { last_error = err; return false; }
+    if (!conv3x3_v2_prepare(device)) { last_error = "cannot upload the conv lane-mask table"; return false; }
+  }
   if (!h_pinned) {
     h_pinned_bytes = nb * (sizeof(ug_packed_pos) + UG_MASK_WORDS * 4 + UG_NUM_PLANES * UG_NUM_POINTS +
                            (UG_NUM_MOVES + 1) * 4) + 256;
@@ -305,6 +320,7 @@ int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act, const 
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   }
+  if (conv_impl == 2 && C % 64 == 0) return enqueue_tower_v2(n, s, final_act, final_lo);
   const int ctas = conv_ctas;
   ConvArgs a{};
   a.M = n * UG_NUM_POINTS;
@@ -350,6 +366,51 @@ int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act, const 
   return 0;
 }
 
+int ug_eval::enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, const void** final_lo) {
+  const Weights& W = *weights;
+  const int C = W.C;
+  const bool split = resid_split;
+  ConvV2Args a{};
+  a.M = n * UG_NUM_POINTS;
+  a.relu = 1;
+  a.f16 = precision == UG_PREC_FP16;
+  a.cout = C;
+  // stem: writes S[0] (hi [+ lo])
+  a.cin = kCinPad;
+  a.bias = W.convs[0].bias.as<float>();
+  a.has_out_lo = split;
+  ConvV2Maps m{&v2_a_in, &W.convs[0].tm_w[1], nullptr, nullptr, &v2_out_hi[0], split ? &v2_out_lo[0] : nullptr};
+  cudaError_t e = conv3x3_v2_launch(m, a, 32, device, sms, s);
+  if (e != cudaSuccess) return fail(-1, std::string("stem conv launch: ") + cudaGetErrorString(e));
+  a.cin = C;
+  *final_act = d_s_hi[0].p;
+  *final_lo = split ? d_s_lo[0].p : nullptr;
+  for (int b = 0; b < W.blocks && debug_stop != 0; ++b) {
+    const int x = b & 1, y = x ^ 1;
+    const ConvLayer& c1 = W.convs[1 + 2 * b];
+    const ConvLayer& c2 = W.convs[2 + 2 * b];
+    a.bias = c1.bias.as<float>();
+    a.has_res = a.has_res_lo = a.has_out_lo = 0;
+    m = ConvV2Maps{&v2_a_s[x], &c1.tm_w[1], nullptr, nullptr, &v2_out_t, nullptr};
+    e = conv3x3_v2_launch(m, a, 64, device, sms, s);
+    if (e != cudaSuccess) return fail(-1, std::string("tower conv launch: ") + cudaGetErrorString(e));
+    *final_act = d_t.p;
+    *final_lo = nullptr;
+    if (debug_stop == 2 * b + 1) break;
+    a.bias = c2.bias.as<float>();
+    a.has_res = 1;
+    a.has_res_lo = a.has_out_lo = split;
+    m = ConvV2Maps{&v2_a_t, &c2.tm_w[1], &v2_res_hi[x], split ? &v2_res_lo[x] : nullptr, &v2_out_hi[y],
+                   split ? &v2_out_lo[y] : nullptr};
+    e = conv3x3_v2_launch(m, a, 64, device, sms, s);
+    if (e != cudaSuccess) return fail(-1, std::string("tower conv launch: ") + cudaGetErrorString(e));
+    *final_act = d_s_hi[y].p;
+    *final_lo = split ? d_s_lo[y].p : nullptr;
+    if (debug_stop == 2 * b + 2) break;
+  }
+  return 0;
+}
+
 int ug_eval::enqueue_heads(const void* act, const void* act_lo, int n, const uint32_t* d_leg, int vt, float* d_pol,
                            float* d_val, cudaStream_t s) {
   const HeadWeights hw = weights->head();
@@ -376,7 +437,7 @@ int ug_eval::enqueue(Src kind, const void* d_src, int n, const uint32_t* d_leg, 
   if (n <= 0 || n > max_batch) return fail(-1, "batch size " + std::to_string(n) + " outside [1, max_batch]");
   if (!use_graphs) return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
   const GraphKey key((int)kind, n, d_src, (const void*)d_leg, (const void*)d_pol, (const void*)d_val, vt,
-                     conv_ctas * 4 + precision + (resid_split ? 8192 : 0) + (debug_stop + 1) * 16);
+                     conv_ctas * 4 + precision + (resid_split ? 8192 : 0) + conv_impl * 16384 + (debug_stop + 1) * 16);
   auto it = graphs.find(key);
   if (it == graphs.end()) {
     if (graphs.size() > 256) drop_graphs();
@@ -435,6 +496,8 @@ ug_eval* ug_eval_create(int device, int precision, int max_batch) {
   h->use_graphs = !(ng && ng[0] == '1');
   const char* cc = getenv("UGEVAL_CONV_CTAS");
   if (cc && (cc[0] == '1' || cc[0] == '2')) h->conv_ctas = cc[0] - '0';
+  const char* ci = getenv("UGEVAL_CONV_IMPL");
+  if (ci && (ci[0] == '1' || ci[0] == '2')) h->conv_impl = ci[0] - '0';
   const char* rs = getenv("UGEVAL_RESID_SPLIT");
   if (rs && (rs[0] == '0' || rs[0] == '1')) h->resid_split = rs[0] == '1';
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -528,6 +591,12 @@ int ug_eval_set_debug_stop(ug_eval* h, int layer) {
 int ug_eval_set_conv_ctas(ug_eval* h, int ctas) {
   if (!h || (ctas != 1 && ctas != 2)) return -1;
   h->conv_ctas = ctas;
+  return 0;
+}
+
+int ug_eval_set_conv_impl(ug_eval* h, int impl) {
+  if (!h || (impl != 1 && impl != 2)) return -1;
+  h->conv_impl = impl;
   return 0;
 }
 
@@ -752,6 +821,61 @@ int ug_k_conv3x3_bf16(int device, const void* d_in, const void* d_w, const float
   a.relu = relu;
   cudaError_t e = conv3x3_tc_launch(ta, tb, a, ck, ctas, prop.multiProcessorCount, 0);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return -4; }
+  return 0;
+}
+
+int ug_k_conv3x3_v2(int device, const void* d_in, const void* d_w, const float* d_bias, const void* d_res_hi,
+                    const void* d_res_lo, void* d_out_hi, void* d_out_lo, int n, int n_alloc, int cin, int cout,
+                    int relu, int f16, int desc_mode, int iters, float* ms_out, long long* d_prof) {
+  cudaSetDevice(device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+  std::string err;
+  const int ck = (cin % 64 == 0) ? 64 : 32;
+  const long rows = (long)n_alloc * UG_NUM_POINTS;
+  CUtensorMap ta, tw, trh, trl, toh, tol;
+  if (!make_tmap_rows(&ta, d_in, rows, cin, ck, 168, &err) ||
+      !make_tmap_weights(&tw, d_w, cout, 9 * cin, ck, cout / 2, &err) ||
+      !make_tmap_rows(&toh, d_out_hi, rows, cout, 32, 32, &err) ||
+      (d_out_lo && !make_tmap_rows(&tol, d_out_lo, rows, cout, 32, 32, &err)) ||
+      (d_res_hi && !make_tmap_rows(&trh, d_res_hi, rows, cout, 32, 128, &err)) ||
+      (d_res_lo && !make_tmap_rows(&trl, d_res_lo, rows, cout, 32, 128, &err))) {
+    g_create_error = err;
+    return -2;
+  }
+  ConvV2Maps m{&ta, &tw, d_res_hi ? &trh : nullptr, d_res_lo ? &trl : nullptr, &toh, d_out_lo ? &tol : nullptr};
+  ConvV2Args a{};
+  a.bias = d_bias;
+  a.M = n * UG_NUM_POINTS;
+  a.cin = cin;
+  a.cout = cout;
+  a.relu = relu;
+  a.f16 = f16;
+  a.has_res = d_res_hi != nullptr;
+  a.has_res_lo = d_res_lo != nullptr;
+  a.has_out_lo = d_out_lo != nullptr;
+  a.desc_mode = desc_mode;
+  a.prof = d_prof;
+  cudaStream_t s = nullptr;
+  cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaError_t e = conv3x3_v2_launch(m, a, ck, device, prop.multiProcessorCount, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess && iters > 0) {
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < iters && e == cudaSuccess; ++i) e = conv3x3_v2_launch(m, a, ck, device, prop.multiProcessorCount, s);
+    cudaEventRecord(e1, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms_out) *ms_out = ms / iters;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaStreamDestroy(s);
   if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return -4; }
   return 0;
 }

@@ -58,6 +58,7 @@ struct ug_eval {
   int max_batch = 0;
   int sms = 148;
   int conv_ctas = 2;
+  int conv_impl = 2;  // 1 = im2col kernel (conv3x3_tc.cu), 2 = resident-tile kernel (conv3x3_v2.cu)
   bool resid_split = true;  // carry the residual stream as hi + lo 16-bit pair (numerics)
   int value_transform = UG_TR_IDENTITY;
   bool use_graphs = true;
@@ -82,6 +83,8 @@ struct ug_eval {
   ug::DevBuf d_s_hi[2], d_s_lo[2], d_t;
   ug::DevBuf f_in, f_s[2], f_t;  // fp32 validation build
   CUtensorMap tm_in, tm_s[2], tm_t;
+  // conv v2 maps over the same buffers: halo-tile loads, residual loads (hi/lo), staged stores (hi/lo)
+  CUtensorMap v2_a_in, v2_a_s[2], v2_a_t, v2_res_hi[2], v2_res_lo[2], v2_out_hi[2], v2_out_lo[2], v2_out_t;
   void* h_pinned = nullptr;  // staging for host-buffer entry points
   size_t h_pinned_bytes = 0;
 
@@ -102,6 +105,7 @@ struct ug_eval {
                   float* d_value, cudaStream_t s);
   int enqueue_encoder(Src kind, const void* d_src, int n, cudaStream_t s);
   int enqueue_tower(int n, cudaStream_t s, const void** final_act, const void** final_lo);
+  int enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, const void** final_lo);
   int enqueue_heads(const void* act, const void* act_lo, int n, const uint32_t* d_legal, int vt, float* d_policy, float* d_value,
                     cudaStream_t s);
 };

@@ -83,4 +83,26 @@ bool make_tmap_weights(CUtensorMap* out, const void* base, int cout, int ktot, i
   return true;
 }
 
+bool make_tmap_rows(CUtensorMap* out, const void* base, long rows, int cols, int box_cols, int box_rows,
+                    std::string* err) {
+  if (!resolve(err)) return false;
+  if (box_cols != 32 && box_cols != 64) {
+    if (err) *err = "make_tmap_rows: box_cols must be 32 or 64 (64 B / 128 B swizzle span)";
+    return false;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = (box_cols == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = g_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r);
+    return false;
+  }
+  return true;
+}
+
 }  // namespace ug

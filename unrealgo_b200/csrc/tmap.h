@@ -13,4 +13,10 @@ bool make_tmap_act_im2col(CUtensorMap* out, const void* base, int n, int c, int 
 bool make_tmap_weights(CUtensorMap* out, const void* base, int cout, int ktot, int ck, int box_rows,
                        std::string* err);
 
+// Generic 2-D tiled map over a row-major 16-bit matrix [rows][cols]; box = box_rows x box_cols; the swizzle
+// follows the box's inner extent (64 B -> SWIZZLE_64B, 128 B -> SWIZZLE_128B).  Out-of-range rows/columns
+// (including negative start coordinates) are zero-filled on load and clipped on store.
+bool make_tmap_rows(CUtensorMap* out, const void* base, long rows, int cols, int box_cols, int box_rows,
+                    std::string* err);
+
 }  // namespace ug

@@ -130,6 +130,10 @@ class DlTFNetworkEvaluator:
         if self._lib.ug_eval_set_conv_ctas(self._h, ctas) != 0:
             raise ValueError("ctas must be 1 or 2")
 
+    def set_conv_impl(self, impl):
+        if self._lib.ug_eval_set_conv_impl(self._h, impl) != 0:
+            raise ValueError("impl must be 1 or 2")
+
     def set_residual_split(self, on):
         self._lib.ug_eval_set_residual_split(self._h, 1 if on else 0)
 
