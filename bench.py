@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — positions/s of the batched network-evaluation path (BASELINE.json metric) on N B200s.
 
-A "step" is one pass of the hot path (GPU encoder -> 41 tcgen05 convs -> heads) over one batch of 256 synthetic
+A "step" is one pass of the hot path (GPU encoder -> 41 tcgen05 convs -> heads: 44 kernel launches) over one batch of 256 synthetic
 positions on the 20-block x 256-filter net (BASELINE.json configs[1]), weights from a seeded synthetic
 TF-format checkpoint (the bootstrap checkpoint is an un-fetched LFS object).  `value` = positions/s with inputs
 resident in HBM; `e2e` = the same through the reference-facing Evaluate() entry (ug_eval_run_planes) with host
@@ -292,6 +292,7 @@ def main():
                                    f"{info['blocks']}-block x {C}-filter dlcfg-19 net (BASELINE configs[1]), "
                                    "seeded synthetic TF-format checkpoint",
                        "batch": B, "blocks": info["blocks"], "filters": C, "conv_cta_group": info["conv_ctas"],
+                       "conv_impl": info.get("conv_impl"),
                        "arithmetic": f"{args.precision} operands (tcgen05 kind::f16), fp32 accumulation in TMEM, "
                                      "fp32 bias/residual epilogue, residual stream carried as hi+lo 16-bit pair",
                        "l2": "flushed between timed steps (256 MiB write outside the event bracket); 8 input batches rotated",
@@ -308,7 +309,8 @@ def main():
                          "frac": achieved / peak, "frac_of_burst": achieved / burst,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long loop)"
                                         if peaks else "fallback",
-                         "kernel": f"conv3x3_tc_kernel<64,{info['conv_ctas']}> (3x3 {C}->{C}, M={B * 361})",
+                         "kernel": (f"conv3x3_v2_kernel<64> cta_group::2 (3x3 {C}->{C}, M={B * 361})" if info.get("conv_impl") == 2
+                                    else f"conv3x3_tc_kernel<64,{info['conv_ctas']}> (3x3 {C}->{C}, M={B * 361})"),
                          "flops_per_launch": conv_flops, "ms_per_launch": conv_ms, "traffic": None},
         }
         if sp is not None:

@@ -60,6 +60,7 @@ typedef struct ug_net_info {
   double flops_per_position; /* algorithmic FLOPs (SURVEY 8(d) formula evaluated on this net) */
   int conv_ctas;        /* 1 or 2: cta_group of the tower kernel in use */
   int sm_count;
+  int conv_impl;        /* 1 = TMA-im2col tower kernel, 2 = resident-tile kernel (see ug_eval_set_conv_impl) */
 } ug_net_info;
 
 typedef struct ug_eval ug_eval;

@@ -171,3 +171,21 @@ def test_legal_mask_renormalisation(small_ckpt, positions):
         rest = np.setdiff1d(np.arange(362), idx)
         assert (pm[i, rest] == 0).all()
     ev.close()
+
+
+def test_both_tower_kernels_agree(wide_ckpt):
+    """conv_impl 1 (TMA-im2col operand staging) and 2 (resident tile + shifted-descriptor taps) are two stagings
+    of the same GEMM: per output element the same fp32 sums over the same 16-bit operands (only the order of the
+    taps differs), so whole-network outputs agree to fp32 accumulation-order noise."""
+    import oracle
+    from unrealgo_b200 import DlTFNetworkEvaluator
+    packed, _ = oracle.synthetic_positions(37, seed=4)
+    ev = DlTFNetworkEvaluator(wide_ckpt[0], max_batch=64)
+    assert ev.UpdateCheckPoint(wide_ckpt[1])
+    assert ev.info()["conv_impl"] == 2
+    p2, v2 = ev.evaluate_packed(packed)
+    ev.set_conv_impl(1)
+    assert ev.info()["conv_impl"] == 1
+    p1, v1 = ev.evaluate_packed(packed)
+    assert np.abs(p1 - p2).max() <= 2e-4 and np.abs(v1 - v2).max() <= 2e-3
+    ev.close()

@@ -33,7 +33,7 @@ class NetInfo(C.Structure):
     _fields_ = [
         ("blocks", C.c_int), ("filters", C.c_int), ("policy_channels", C.c_int), ("value_channels", C.c_int),
         ("value_hidden", C.c_int), ("input_planes", C.c_int), ("flops_per_position", C.c_double),
-        ("conv_ctas", C.c_int), ("sm_count", C.c_int),
+        ("conv_ctas", C.c_int), ("sm_count", C.c_int), ("conv_impl", C.c_int),
     ]
 
 

@@ -58,7 +58,10 @@ struct Load8<float> {
   }
 };
 
-// feat[point][h] = relu(sum_c act[point][c] * w[h][c] + b[h]);  HC = pc+vc <= 8, C % 8 == 0
+// feat[point][h] = relu(sum_c act[point][c] * w[h][c] + b[h]);  HC = pc+vc <= 8, C % 8 == 0.
+// One warp handles kPtsPerIter board points per iteration (all their 16-byte loads are issued before the
+// arithmetic, so 2*kPtsPerIter loads per lane are in flight); a point's C channels are spread over the lanes.
+constexpr int kPtsPerIter = 4;
 template <typename T, int HC>
 __global__ void __launch_bounds__(256) head_conv_kernel(const T* __restrict__ act, const T* __restrict__ act_lo,
                                                         const float* __restrict__ w,
@@ -71,39 +74,61 @@ __global__ void __launch_bounds__(256) head_conv_kernel(const T* __restrict__ ac
   const long warp_global = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long warp_stride = (long)gridDim.x * (blockDim.x >> 5);
   const int chunks = C >> 3;
-  for (long pt = warp_global; pt < total_points; pt += warp_stride) {
-    float acc[HC];
+  for (long pt0 = warp_global * kPtsPerIter; pt0 < total_points; pt0 += warp_stride * kPtsPerIter) {
+    float acc[kPtsPerIter][HC];
 #pragma unroll
-    for (int h = 0; h < HC; ++h) acc[h] = 0.f;
-    const T* row = act + pt * C;
+    for (int u = 0; u < kPtsPerIter; ++u)
+#pragma unroll
+      for (int h = 0; h < HC; ++h) acc[u][h] = 0.f;
     for (int ch = lane; ch < chunks; ch += 32) {
-      float x[8];
-      Load8<T>::load(row + ch * 8, x, f16);
-      if (act_lo != nullptr) {
-        float xl[8];
-        Load8<T>::load(act_lo + pt * C + ch * 8, xl, f16);
+      float x[kPtsPerIter][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] += xl[i];
+      for (int u = 0; u < kPtsPerIter; ++u) {
+        const long pt = min(pt0 + u, total_points - 1);  // clamped: the duplicate is not stored
+        Load8<T>::load(act + pt * C + ch * 8, x[u], f16);
+      }
+      if (act_lo != nullptr) {
+#pragma unroll
+        for (int u = 0; u < kPtsPerIter; ++u) {
+          const long pt = min(pt0 + u, total_points - 1);
+          float xl[8];
+          Load8<T>::load(act_lo + pt * C + ch * 8, xl, f16);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[u][i] += xl[i];
+        }
       }
 #pragma unroll
       for (int h = 0; h < HC; ++h) {
         const float4 w0 = *reinterpret_cast<const float4*>(sw + h * C + ch * 8);
         const float4 w1 = *reinterpret_cast<const float4*>(sw + h * C + ch * 8 + 4);
-        acc[h] += x[0] * w0.x + x[1] * w0.y + x[2] * w0.z + x[3] * w0.w + x[4] * w1.x + x[5] * w1.y +
-                  x[6] * w1.z + x[7] * w1.w;
+#pragma unroll
+        for (int u = 0; u < kPtsPerIter; ++u)
+          acc[u][h] += x[u][0] * w0.x + x[u][1] * w0.y + x[u][2] * w0.z + x[u][3] * w0.w + x[u][4] * w1.x +
+                       x[u][5] * w1.y + x[u][6] * w1.z + x[u][7] * w1.w;
       }
     }
 #pragma unroll
-    for (int h = 0; h < HC; ++h) acc[h] = warp_sum(acc[h]);
+    for (int u = 0; u < kPtsPerIter; ++u)
+#pragma unroll
+      for (int h = 0; h < HC; ++h) acc[u][h] = warp_sum(acc[u][h]);
     if (lane == 0) {
 #pragma unroll
-      for (int h = 0; h < HC; ++h) feat[pt * HC + h] = fmaxf(acc[h] + __ldg(b + h), 0.f);
+      for (int u = 0; u < kPtsPerIter; ++u) {
+        if (pt0 + u < total_points) {
+#pragma unroll
+          for (int h = 0; h < HC; ++h) feat[(pt0 + u) * HC + h] = fmaxf(acc[u][h] + __ldg(b + h), 0.f);
+        }
+      }
     }
   }
 }
 
 constexpr int kPosPerCta = 4;
-constexpr int kFcThreads = 384;
+constexpr int kPolThreads = 384;                 // policy FC: one output column per thread (362 used) ...
+constexpr int kPolSplit = 2;                     // ... and the K range split over 2 thread groups
+constexpr int kValThreads = 256;                 // value FC1: one hidden unit per thread (strided when H > 256)
+constexpr int kFcThreads = kPolSplit * kPolThreads + kValThreads;  // 1024
+constexpr int kFcUnroll = 16;                    // independent weight loads in flight per thread
 
 __device__ __forceinline__ float block_reduce(float v, bool is_max, float* scratch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -117,8 +142,31 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* scrat
   return r;
 }
 
+// acc[p] += sum_i f[p][i] * w[i*stride]  for kPosPerCta positions; weights stream from L2 (coalesced across the
+// threads of a warp: consecutive threads own consecutive columns), kFcUnroll loads issued before their FMAs
+__device__ __forceinline__ void fc_column(const float* __restrict__ wcol, int stride, const float* f, int fstride,
+                                          int len, float (&acc)[kPosPerCta]) {
+  int i = 0;
+  for (; i + kFcUnroll <= len; i += kFcUnroll) {
+    float wv[kFcUnroll];
+#pragma unroll
+    for (int u = 0; u < kFcUnroll; ++u) wv[u] = __ldg(wcol + (size_t)(i + u) * stride);
+#pragma unroll
+    for (int u = 0; u < kFcUnroll; ++u)
+#pragma unroll
+      for (int p = 0; p < kPosPerCta; ++p) acc[p] = fmaf(f[p * fstride + i + u], wv[u], acc[p]);
+  }
+  for (; i < len; ++i) {
+    const float wv = __ldg(wcol + (size_t)i * stride);
+#pragma unroll
+    for (int p = 0; p < kPosPerCta; ++p) acc[p] = fmaf(f[p * fstride + i], wv, acc[p]);
+  }
+}
+
 // feat layout per position: [361][pc+vc] (policy channels first).  Policy FC input index = point*pc + c,
 // value FC input index = point*vc + c (the NHWC flatten TensorFlow's Reshape produces).
+// Threads [0,768) own the policy columns (two groups, each half of the K range), threads [768,1024) the value
+// hidden units: both FCs run concurrently and every thread walks ~361 weight rows.
 __global__ void __launch_bounds__(kFcThreads) head_fc_kernel(const float* __restrict__ feat, HeadWeights hw,
                                                              const uint32_t* __restrict__ legal, int vt,
                                                              float* __restrict__ policy,
@@ -130,6 +178,7 @@ __global__ void __launch_bounds__(kFcThreads) head_fc_kernel(const float* __rest
   float* fv = fp + kPosPerCta * pin;       // [kPosPerCta][vin]
   float* hid = fv + kPosPerCta * vin;      // [kPosPerCta][H]
   float* scratch = hid + kPosPerCta * H;   // [32]
+  float* part = scratch + 32;              // [kPosPerCta][kPolThreads] partial logits of the second K half
   const int p0 = blockIdx.x * kPosPerCta;
   const int np = min(kPosPerCta, n - p0);
 
@@ -143,59 +192,63 @@ __global__ void __launch_bounds__(kFcThreads) head_fc_kernel(const float* __rest
   }
   __syncthreads();
 
-  // ---- policy: logits[j] = b[j] + sum_i f[i] * W[i][j]
-  const int j = threadIdx.x;
+  const int tid = threadIdx.x;
+  const int j = tid < kPolSplit * kPolThreads ? tid % kPolThreads : kMoves;  // policy column (>= 362: none)
+  const int khalf = tid / kPolThreads;                                       // 0/1 for policy threads
   float logit[kPosPerCta];
 #pragma unroll
   for (int p = 0; p < kPosPerCta; ++p) logit[p] = 0.f;
-  if (j < kMoves) {
-    const float* wcol = hw.pfc_w + j;
-#pragma unroll 4
-    for (int i = 0; i < pin; ++i) {
-      const float wv = __ldg(wcol + (size_t)i * kMoves);
+  if (tid < kPolSplit * kPolThreads) {
+    // ---- policy: logits[j] = b[j] + sum_i f[i] * W[i][j]; group 0 sums i in [0, pin/2), group 1 the rest
+    if (j < kMoves) {
+      const int k0 = khalf == 0 ? 0 : pin / 2;
+      const int k1 = khalf == 0 ? pin / 2 : pin;
+      fc_column(hw.pfc_w + (size_t)k0 * kMoves + j, kMoves, fp + k0, pin, k1 - k0, logit);
+      if (khalf == 1) {
 #pragma unroll
-      for (int p = 0; p < kPosPerCta; ++p) logit[p] = fmaf(fp[p * pin + i], wv, logit[p]);
+        for (int p = 0; p < kPosPerCta; ++p) part[p * kPolThreads + j] = logit[p];
+      }
     }
+  } else {
+    // ---- value: hidden = relu(W1^T f + b1)
+    for (int h = tid - kPolSplit * kPolThreads; h < H; h += kValThreads) {
+      float acc[kPosPerCta];
+#pragma unroll
+      for (int p = 0; p < kPosPerCta; ++p) acc[p] = 0.f;
+      fc_column(hw.v1_w + h, H, fv, vin, vin, acc);
+      const float b1 = __ldg(hw.v1_b + h);
+#pragma unroll
+      for (int p = 0; p < kPosPerCta; ++p) hid[p * H + h] = fmaxf(acc[p] + b1, 0.f);
+    }
+  }
+  __syncthreads();
+  const bool pol = tid < kPolThreads && j < kMoves;  // the threads that own a finished logit
+  if (pol) {
     const float bj = __ldg(hw.pfc_b + j);
 #pragma unroll
-    for (int p = 0; p < kPosPerCta; ++p) logit[p] += bj;
+    for (int p = 0; p < kPosPerCta; ++p) logit[p] += part[p * kPolThreads + j] + bj;
   }
 #pragma unroll
   for (int p = 0; p < kPosPerCta; ++p) {
     if (p >= np) break;  // np is block-uniform
-    const float mx = block_reduce(j < kMoves ? logit[p] : -CUDART_INF_F, true, scratch);
+    const float mx = block_reduce(pol ? logit[p] : -CUDART_INF_F, true, scratch);
     float prob = logit[p];
     if (hw.policy_softmax) {
-      const float e = (j < kMoves) ? expf(logit[p] - mx) : 0.f;
+      const float e = pol ? expf(logit[p] - mx) : 0.f;
       const float sum = block_reduce(e, false, scratch);
       prob = e / sum;
     }
     if (legal != nullptr) {
       // UpdatePrior: prior = p[idx] / sum over legal children of p[idx]; illegal moves get 0
       const uint32_t* lm = legal + (size_t)(p0 + p) * UG_MASK_WORDS;
-      const bool ok = (j < kMoves) && ((__ldg(lm + (j >> 5)) >> (j & 31)) & 1u);
+      const bool ok = pol && ((__ldg(lm + (j >> 5)) >> (j & 31)) & 1u);
       const float lsum = block_reduce(ok ? prob : 0.f, false, scratch);
       prob = ok ? prob / lsum : 0.f;
     }
-    if (j < kMoves) policy[(size_t)(p0 + p) * kMoves + j] = prob;
+    if (pol) policy[(size_t)(p0 + p) * kMoves + j] = prob;
   }
 
-  // ---- value: hidden = relu(W1^T f + b1); v = tanh(w2 . hidden + b2)
-  for (int h = threadIdx.x; h < H; h += blockDim.x) {
-    float acc[kPosPerCta];
-#pragma unroll
-    for (int p = 0; p < kPosPerCta; ++p) acc[p] = 0.f;
-    const float* wcol = hw.v1_w + h;
-#pragma unroll 4
-    for (int i = 0; i < vin; ++i) {
-      const float wv = __ldg(wcol + (size_t)i * H);
-#pragma unroll
-      for (int p = 0; p < kPosPerCta; ++p) acc[p] = fmaf(fv[p * vin + i], wv, acc[p]);
-    }
-    const float b1 = __ldg(hw.v1_b + h);
-#pragma unroll
-    for (int p = 0; p < kPosPerCta; ++p) hid[p * H + h] = fmaxf(acc[p] + b1, 0.f);
-  }
+  // ---- v = tanh(w2 . hidden + b2); hid was completed before the first block_reduce's barrier
   __syncthreads();
   for (int p = 0; p < np; ++p) {
     float part = 0.f;
@@ -216,7 +269,7 @@ void head_conv_dispatch(const T* act, const T* act_lo, int f16, const HeadWeight
                         cudaStream_t s) {
   const long total = (long)n * kPoints;
   const int hc = w.pc + w.vc;
-  int grid = (int)((total + 7) / 8);
+  int grid = (int)((total + 8 * kPtsPerIter - 1) / (8 * kPtsPerIter));
   if (grid > 148 * 8) grid = 148 * 8;
   const size_t smem = (size_t)hc * w.C * sizeof(float);
   switch (hc) {
@@ -245,7 +298,7 @@ void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* leg
                     float* value, int n, cudaStream_t s) {
   if (n <= 0) return;
   const size_t smem =
-      sizeof(float) * ((size_t)kPosPerCta * (kPoints * (w.pc + w.vc) + w.H) + 32);
+      sizeof(float) * ((size_t)kPosPerCta * (kPoints * (w.pc + w.vc) + w.H + kPolThreads) + 32);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaFuncSetAttribute(head_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

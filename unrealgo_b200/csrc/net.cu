@@ -620,6 +620,7 @@ int ug_eval_info(const ug_eval* h, ug_net_info* out) {
                             2.0 * (P * W.pc) * UG_NUM_MOVES + 2 * P * C * W.vc + 2.0 * (P * W.vc) * W.H + 2.0 * W.H;
   out->conv_ctas = h->conv_ctas;
   out->sm_count = h->sms;
+  out->conv_impl = (h->conv_impl == 2 && W.C % 64 == 0) ? 2 : 1;
   return 0;
 }
 
