@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
                     help="operand format of the tcgen05 tower (same MMA rate; fp16 meets the parity tolerance)")
     ap.add_argument("--no-selfplay", action="store_true")
-    ap.add_argument("--sp-games", type=int, default=512, help="concurrent self-play games per GPU")
+    ap.add_argument("--sp-games", type=int, default=768, help="concurrent self-play games per GPU")
     ap.add_argument("--sp-threads", type=int, default=0, help="search threads per GPU (0 = auto)")
     ap.add_argument("--sp-playouts", type=int, default=1600, help="playouts per move (BASELINE configs[2])")
     ap.add_argument("--sp-moves", type=int, default=2, help="moves per game in the bounded self-play sample")
@@ -169,7 +169,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
     meta, prefix = checkpoint(args.blocks, args.filters)
-    ev = DlTFNetworkEvaluator(meta, device=local, max_batch=B,
+    # 262 positions = 5 full waves of the tower kernel (ug_eval_efficient_batch): the self-play leg batches up to that
+    SP_BATCH = max(B, 262)
+    ev = DlTFNetworkEvaluator(meta, device=local, max_batch=SP_BATCH,
                               precision=PREC_FP16 if args.precision == "fp16" else PREC_BF16)
     assert ev.UpdateCheckPoint(prefix), ev._err()
     if args.ctas:
@@ -249,7 +251,7 @@ def main():
         if world > 1:
             dist.barrier()
         st, _ = selfplay(ev, games=args.sp_games, threads=threads, playouts_per_move=args.sp_playouts,
-                         max_moves=args.sp_moves, max_batch=B, timeout_us=300, reuse_tree=True,
+                         max_moves=args.sp_moves, max_batch=SP_BATCH, timeout_us=300, reuse_tree=True,
                          random_opening_moves=1, seed=1000 + rank)
         tsp = torch.tensor([float(st["playouts"]), float(st["evaluations"])], dtype=torch.float64, device="cuda")
         tsec = torch.tensor([st["seconds"]], dtype=torch.float64, device="cuda")
@@ -259,6 +261,7 @@ def main():
         sp = {"playouts_per_s": float(tsp[0].item()) / float(tsec.item()), "unit": "playouts/s",
               "evaluations_per_s": float(tsp[1].item()) / float(tsec.item()), "seconds": float(tsec.item()),
               "games_per_gpu": args.sp_games, "search_threads_per_gpu": threads, "host_cpus": os.cpu_count(),
+              "leaf_batch_cap": SP_BATCH,
               "playouts_per_move": args.sp_playouts, "moves_per_game_sampled": args.sp_moves,
               "mean_batch_rank0": st["mean_batch"], "flush_timeouts_rank0": st["flush_timeouts"],
               "mean_tree_nodes_rank0": st["mean_tree_nodes"], "reuse_searchtree": True,

@@ -95,6 +95,10 @@ int ug_eval_set_value_transform(ug_eval* h, int vt);
 int ug_eval_info(const ug_eval* h, ug_net_info* out);
 /* use cta_group::1 or ::2 tower kernels (default 2); testing/benchmark knob */
 int ug_eval_set_conv_ctas(ug_eval* h, int ctas);
+/* Largest batch size <= n that fills whole waves of the persistent tower kernel (a wave = 74 CTA pairs x 256 pixel
+ * rows = 52.47 positions on a 148-SM part): 213 positions cost 5 waves, exactly as much as 262; 209 cost 4.  The
+ * leaf queue uses it when it flushes a partial batch.  Returns n itself below one wave. */
+int ug_eval_efficient_batch(const ug_eval* h, int n);
 /* tower kernel generation: 1 = TMA-im2col operand staging (conv3x3_tc.cu), 2 = shared-memory-resident input tile
  * with shifted-descriptor taps and TMA-staged epilogue (conv3x3_v2.cu, default); testing/benchmark knob */
 int ug_eval_set_conv_impl(ug_eval* h, int impl);

@@ -105,4 +105,6 @@ if __name__ == "__main__":
         print("time conv1 n=256 256->256         :", run(256, 256, 256, ALL, dm, False, False, iters=20, prof=True), flush=True)
         print("time conv2 n=256 256->256 res+lo  :", run(256, 256, 256, ALL, dm, True, True, iters=20, prof=True), flush=True)
         print("time stem  n=256 32->256 lo       :", run(256, 32, 256, ALL, dm, False, True, iters=20, prof=True), flush=True)
+        print("time conv1 +PDL                   :", run(256, 256, 256, ALL, dm | 8, False, False, iters=20), flush=True)
+        print("time conv2 +PDL                   :", run(256, 256, 256, ALL, dm | 8, True, True, iters=20), flush=True)
         print("time conv2 bf16 n=256             :", run(256, 256, 256, ALL, dm, True, True, f16=False, iters=20), flush=True)

@@ -158,6 +158,11 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  // Programmatic dependent launch: this grid may have been scheduled while the previous layer was still
+  // draining.  Everything above (barriers, TMEM, bias) and the weight ring below do not depend on it; the two
+  // warps that read the previous layer's output (A chunks, residual) wait for it, and every later step of the
+  // tile pipeline is ordered behind their loads.
+  pdl_launch_dependents();
 
   // The three producer warps and the MMA warp run their loops with all 32 lanes on warp-uniform values and
   // predicate only the TMA / MMA instruction itself on one elected lane.  (Issuing from inside an `if (lane == 0)`
@@ -166,6 +171,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t elected = elect_one();
   if (warp == 0) {
     // ===================== A-chunk producer =====================
+    pdl_wait();
     int sa = 0;
     uint32_t pha = 0;
     for (int tile = cluster_id; tile < args.num_tiles; tile += num_clusters) {
@@ -268,6 +274,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 3) {
     // ===================== residual producer =====================
     if constexpr (has_res) {
+      pdl_wait();
       int rs = 0;
       uint32_t phr = 0;
       constexpr uint32_t bytes = has_res_lo ? kResSlot : kResHalf;
@@ -443,13 +450,15 @@ cudaError_t launch_v2(const ConvV2Maps& m, const ConvV2Args& a, int sms, cudaStr
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = a.pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kfn, *m.a, *m.w, *m.res_hi, *m.res_lo, *m.out_hi, *m.out_lo, a);
 }
 

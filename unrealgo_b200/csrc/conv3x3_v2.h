@@ -17,6 +17,8 @@ struct ConvV2Args {
   int has_res, has_res_lo, has_out_lo;
   int desc_mode;          // bring-up knobs: bit 0 set the descriptor's matrix-base-offset field for shifted A tiles;
                           // bit 1 unmasked MMA form and bit 2 no tap shift (both give wrong results: timing probes)
+  int pdl;                // launch with programmatic stream serialization (overlap the prologue and the weight
+                          // prefetch with the previous kernel's tail)
   int num_tiles;          // filled by the launcher
   long long* prof;        // optional [clusters][16] cycle counters (bring-up instrumentation), else null
 };

@@ -375,6 +375,7 @@ int ug_eval::enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, con
   a.relu = 1;
   a.f16 = precision == UG_PREC_FP16;
   a.cout = C;
+  a.pdl = use_pdl ? 1 : 0;
   // stem: writes S[0] (hi [+ lo])
   a.cin = kCinPad;
   a.bias = W.convs[0].bias.as<float>();
@@ -437,10 +438,10 @@ int ug_eval::enqueue(Src kind, const void* d_src, int n, const uint32_t* d_leg, 
   if (n <= 0 || n > max_batch) return fail(-1, "batch size " + std::to_string(n) + " outside [1, max_batch]");
   if (!use_graphs) return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
   const GraphKey key((int)kind, n, d_src, (const void*)d_leg, (const void*)d_pol, (const void*)d_val, vt,
-                     conv_ctas * 4 + precision + (resid_split ? 8192 : 0) + conv_impl * 16384 + (debug_stop + 1) * 16);
+                     conv_ctas * 4 + precision + (resid_split ? 8192 : 0) + conv_impl * 16384 + (use_pdl ? 65536 : 0) + (debug_stop + 1) * 16);
   auto it = graphs.find(key);
   if (it == graphs.end()) {
-    if (graphs.size() > 256) drop_graphs();
+    if (graphs.size() > 1024) drop_graphs();
     cudaGraph_t g = nullptr;
     if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
       return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
@@ -496,6 +497,8 @@ ug_eval* ug_eval_create(int device, int precision, int max_batch) {
   h->use_graphs = !(ng && ng[0] == '1');
   const char* cc = getenv("UGEVAL_CONV_CTAS");
   if (cc && (cc[0] == '1' || cc[0] == '2')) h->conv_ctas = cc[0] - '0';
+  const char* pd = getenv("UGEVAL_PDL");
+  if (pd && (pd[0] == '0' || pd[0] == '1')) h->use_pdl = pd[0] == '1';
   const char* ci = getenv("UGEVAL_CONV_IMPL");
   if (ci && (ci[0] == '1' || ci[0] == '2')) h->conv_impl = ci[0] - '0';
   const char* rs = getenv("UGEVAL_RESID_SPLIT");
@@ -592,6 +595,16 @@ int ug_eval_set_conv_ctas(ug_eval* h, int ctas) {
   if (!h || (ctas != 1 && ctas != 2)) return -1;
   h->conv_ctas = ctas;
   return 0;
+}
+
+int ug_eval_efficient_batch(const ug_eval* h, int n) {
+  if (!h || n <= 0) return n;
+  // one wave of the persistent tower kernel = (SMs / 2) CTA pairs x 256 pixel rows
+  const long wave_rows = (long)(h->sms / 2) * 256;
+  const long waves = ((long)n * UG_NUM_POINTS) / wave_rows;  // full waves this batch fills
+  if (waves == 0) return n;                                  // less than one wave costs one wave whatever n is
+  const long m = waves * wave_rows / UG_NUM_POINTS;
+  return (int)(m < n ? m : n);
 }
 
 int ug_eval_set_conv_impl(ug_eval* h, int impl) {
@@ -856,7 +869,8 @@ int ug_k_conv3x3_v2(int device, const void* d_in, const void* d_w, const float* 
   a.has_res = d_res_hi != nullptr;
   a.has_res_lo = d_res_lo != nullptr;
   a.has_out_lo = d_out_lo != nullptr;
-  a.desc_mode = desc_mode;
+  a.desc_mode = desc_mode & 7;
+  a.pdl = (desc_mode & 8) ? 1 : 0;  // timing probe: programmatic dependent launch between the repeated launches
   a.prof = d_prof;
   cudaStream_t s = nullptr;
   cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);

@@ -247,6 +247,13 @@ __device__ __forceinline__ void umma_f16_1sm_masked(uint32_t tmem_d, uint64_t ad
       : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// No-ops unless the kernel was launched with cudaLaunchAttributeProgrammaticStreamSerialization.
+// wait: returns once every prerequisite grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// lets the dependent grid be scheduled as soon as every CTA of this grid has issued it (or exited)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- descriptors
 // K-major operand tile in shared memory written by TMA with SWIZZLE_128B (rows of 128 B, 8-row atoms of
 // 1024 B) or SWIZZLE_64B (rows of 64 B, 8-row atoms of 512 B).  Field layout: start>>4 [0,14),

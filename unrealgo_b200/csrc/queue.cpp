@@ -134,7 +134,12 @@ void ug_queue::gather_loop() {
       if (std::chrono::duration_cast<std::chrono::microseconds>(dt).count() >= timeout_us) { timed_out = true; break; }
       cpu_relax();
     }
-    if (timed_out) n_timeouts.fetch_add(1, std::memory_order_relaxed);
+    if (timed_out) {
+      n_timeouts.fetch_add(1, std::memory_order_relaxed);
+      // a partial batch is cut back to whole waves of the tower kernel; the leaves beyond stay published in
+      // the ring and open the next batch
+      n = ug_eval_efficient_batch(eval, n);
+    }
     S.n = n;
     head += n;
     // H2D on the copy-in stream, tower on the evaluator stream, D2H on the copy-out stream
@@ -143,7 +148,12 @@ void ug_queue::gather_loop() {
       cudaMemcpyAsync(S.d_legal, S.h_legal, (size_t)n * UG_MASK_WORDS * 4, cudaMemcpyHostToDevice, s_in);
     cudaEventRecord(S.ev_in, s_in);
     cudaStreamWaitEvent(eval->stream, S.ev_in, 0);
-    const int rc = ug_eval_run_packed_device(eval, S.d_pos, n, S.any_legal ? S.d_legal : nullptr, S.d_policy,
+    // Launch on a batch size rounded up to a multiple of 8 (capped): the extra positions are stale staging rows
+    // whose outputs are never copied back, and the evaluator's CUDA-graph cache then sees 32 batch sizes per
+    // staging buffer instead of 256.
+    int n_run = (n + 7) & ~7;
+    if (n_run > max_batch) n_run = max_batch;
+    const int rc = ug_eval_run_packed_device(eval, S.d_pos, n_run, S.any_legal ? S.d_legal : nullptr, S.d_policy,
                                              S.d_value, eval->stream);
     if (rc != 0) error.store(rc);
     cudaEventRecord(S.ev_done, eval->stream);
