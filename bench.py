@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — positions/s of the batched network-evaluation path (BASELINE.json metric) on N B200s.
 
-A "step" is one pass of the hot path (GPU encoder -> 41 tcgen05 convs -> heads: 44 kernel launches) over one batch of 256 synthetic
+A "step" is one pass of the hot path (GPU encoder -> 41 tcgen05 convs, the last with the head 1x1 convs fused -> head FC kernel: 43 launches) over one batch of 256 synthetic
 positions on the 20-block x 256-filter net (BASELINE.json configs[1]), weights from a seeded synthetic
 TF-format checkpoint (the bootstrap checkpoint is an un-fetched LFS object).  `value` = positions/s with inputs
 resident in HBM; `e2e` = the same through the reference-facing Evaluate() entry (ug_eval_run_planes) with host
@@ -307,7 +307,7 @@ def main():
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": B * 17 * 361, "d2h_bytes_per_step": B * 363 * 4,
                     "api": "DlTFNetworkEvaluator::Evaluate (ug_eval_run_planes): host int8 planes -> host double policy/value"},
-            "gpu_launches": (3 + 1 + conv_launches) * args.steps,
+            "gpu_launches": br["launches_per_pass"] * args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "frac_of_burst": achieved / burst,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long loop)"

@@ -189,3 +189,23 @@ def test_both_tower_kernels_agree(wide_ckpt):
     p1, v1 = ev.evaluate_packed(packed)
     assert np.abs(p1 - p2).max() <= 2e-4 and np.abs(v1 - v2).max() <= 2e-3
     ev.close()
+
+
+def test_fused_head_convolutions_match_the_separate_kernel(wide_ckpt, monkeypatch):
+    """The last tower layer can carry the head 1x1 convolutions in its epilogue (fp32 activations straight from
+    the accumulator) instead of storing hi+lo and running head_conv_kernel: same result up to the 2^-22 relative
+    rounding of the hi+lo pair."""
+    import oracle
+    from unrealgo_b200 import DlTFNetworkEvaluator
+    packed, _ = oracle.synthetic_positions(29, seed=8)
+    monkeypatch.setenv("UGEVAL_FUSE_HEADS", "1")
+    ev = DlTFNetworkEvaluator(wide_ckpt[0], max_batch=32)
+    assert ev.UpdateCheckPoint(wide_ckpt[1])
+    pf, vf = ev.evaluate_packed(packed)
+    ev.close()
+    monkeypatch.setenv("UGEVAL_FUSE_HEADS", "0")
+    ev = DlTFNetworkEvaluator(wide_ckpt[0], max_batch=32)
+    assert ev.UpdateCheckPoint(wide_ckpt[1])
+    ps, vs = ev.evaluate_packed(packed)
+    ev.close()
+    assert np.abs(pf - ps).max() <= 1e-5 and np.abs(vf - vs).max() <= 1e-4

@@ -93,7 +93,9 @@ __device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, bool 
 }
 
 // RES: 0 = no residual, 1 = one 16-bit residual tensor, 2 = hi + lo pair.  OUT_LO: also write (result - hi).
-template <int CK, bool F16, int RES, bool OUT_LO>
+// HEADS > 0: last layer of the tower — instead of storing the activation, every thread feeds its row's fp32
+// results into the HEADS 1x1 head convolutions (policy channels first) and writes relu(head) to args.head_out.
+template <int CK, bool F16, int RES, bool OUT_LO, int HEADS>
 __global__ void __launch_bounds__(256, 1)
 conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmRhi, const __grid_constant__ CUtensorMap tmRlo,
@@ -312,6 +314,9 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       timed_wait(&acc_full[as], aphase, prof, &w_full);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kAccCols;
+      float hacc[HEADS > 0 ? HEADS : 1];
+#pragma unroll
+      for (int h = 0; h < (HEADS > 0 ? HEADS : 1); ++h) hacc[h] = 0.f;
       for (int c0 = 0; c0 < cout; c0 += kEpiCols) {
         uint32_t v[32];
         tmem_ld_32x32(t_row + c0, v);
@@ -337,12 +342,14 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
         }
         // staging slot must have been read by the TMA store issued kNO iterations ago
-        if (lane == 0) {
-          const long long t0 = prof ? clock64() : 0;
-          bulk_wait_group_read<kNO - 1>();
-          if (prof) w_st += clock64() - t0;
+        if constexpr (HEADS == 0) {
+          if (lane == 0) {
+            const long long t0 = prof ? clock64() : 0;
+            bulk_wait_group_read<kNO - 1>();
+            if (prof) w_st += clock64() - t0;
+          }
+          __syncwarp();
         }
-        __syncwarp();
         uint8_t* orow = my_out + os * kOutSlot + lane * 64;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -369,28 +376,50 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             f0 = fmaxf(f0, act_floor);
             f1 = fmaxf(f1, act_floor);
+            if constexpr (HEADS > 0) {
+              // head weights [HEADS][cout] fp32: the same address in every lane (one L1 wavefront per load)
+#pragma unroll
+              for (int h = 0; h < HEADS; ++h) {
+                const float2 hw = __ldg(reinterpret_cast<const float2*>(args.head_w + (size_t)h * cout + c0 + c));
+                hacc[h] = fmaf(f0, hw.x, fmaf(f1, hw.y, hacc[h]));
+              }
+              continue;
+            }
             packed[e] = pack2_sat<F16>(f0, f1);
             if constexpr (has_out_lo) {
               const float2 hi = unpack2_t<F16>(packed[e]);
               packed_lo[e] = pack2_sat<F16>(f0 - hi.x, f1 - hi.y);
             }
           }
-          *reinterpret_cast<uint4*>(orow + ((q ^ sw) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-          if constexpr (has_out_lo)
-            *reinterpret_cast<uint4*>(orow + kOutHalf + ((q ^ sw) << 4)) =
-                make_uint4(packed_lo[0], packed_lo[1], packed_lo[2], packed_lo[3]);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          const int row0 = mc + quarter * 32;
-          if (row0 < args.M) {  // rows past M inside the box are clipped by the tensor map (its height is M_alloc)
-            tma_store_2d(&tmOhi, my_out + os * kOutSlot, c0, row0);
-            if (has_out_lo) tma_store_2d(&tmOlo, my_out + os * kOutSlot + kOutHalf, c0, row0);
+          if constexpr (HEADS == 0) {
+            *reinterpret_cast<uint4*>(orow + ((q ^ sw) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            if constexpr (has_out_lo)
+              *reinterpret_cast<uint4*>(orow + kOutHalf + ((q ^ sw) << 4)) =
+                  make_uint4(packed_lo[0], packed_lo[1], packed_lo[2], packed_lo[3]);
           }
-          bulk_commit_group();
         }
-        if (++os == kNO) os = 0;
+        if constexpr (HEADS == 0) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int row0 = mc + quarter * 32;
+            if (row0 < args.M) {  // rows past M inside the box are clipped by the tensor map (its height is M_alloc)
+              tma_store_2d(&tmOhi, my_out + os * kOutSlot, c0, row0);
+              if (has_out_lo) tma_store_2d(&tmOlo, my_out + os * kOutSlot + kOutHalf, c0, row0);
+            }
+            bulk_commit_group();
+          }
+          if (++os == kNO) os = 0;
+        }
+      }
+      if constexpr (HEADS > 0) {
+        // feat[row][h] = relu(head conv + folded batch-norm offset): 4*HEADS bytes per row, rows consecutive
+        const long row = (long)mc + row_l;
+        if (row < args.M) {
+#pragma unroll
+          for (int h = 0; h < HEADS; ++h)
+            args.head_out[row * HEADS + h] = fmaxf(hacc[h] + __ldg(args.head_b + h), 0.f);
+        }
       }
     }
     if (lane == 0) bulk_wait_group_all();
@@ -433,9 +462,9 @@ bool upload_masks(int device) {
   return true;
 }
 
-template <int CK, bool F16, int RES, bool OUT_LO>
+template <int CK, bool F16, int RES, bool OUT_LO, int HEADS = 0>
 cudaError_t launch_v2(const ConvV2Maps& m, const ConvV2Args& a, int sms, cudaStream_t stream) {
-  auto kfn = conv3x3_v2_kernel<CK, F16, RES, OUT_LO>;
+  auto kfn = conv3x3_v2_kernel<CK, F16, RES, OUT_LO, HEADS>;
   constexpr int smem = Cfg<CK>::kSmem;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
@@ -466,6 +495,14 @@ template <int CK, bool F16>
 cudaError_t dispatch_v2(const ConvV2Maps& m, const ConvV2Args& a, int sms, cudaStream_t stream) {
   const int res = a.has_res ? (a.has_res_lo ? 2 : 1) : 0;
   const bool lo = a.has_out_lo != 0;
+  if (a.head_out != nullptr) {
+    // fused heads: only the shapes the tower's last layer takes (64-channel chunks, 3 head channels)
+    if constexpr (CK == 64) {
+      if (a.head_channels == 3 && res == 2 && lo) return launch_v2<CK, F16, 2, true, 3>(m, a, sms, stream);
+      if (a.head_channels == 3 && res == 1 && !lo) return launch_v2<CK, F16, 1, false, 3>(m, a, sms, stream);
+    }
+    return cudaErrorInvalidValue;
+  }
   if (res == 0 && !lo) return launch_v2<CK, F16, 0, false>(m, a, sms, stream);
   if (res == 0 && lo) return launch_v2<CK, F16, 0, true>(m, a, sms, stream);
   if (res == 1 && !lo) return launch_v2<CK, F16, 1, false>(m, a, sms, stream);
@@ -477,6 +514,11 @@ cudaError_t dispatch_v2(const ConvV2Maps& m, const ConvV2Args& a, int sms, cudaS
 }  // namespace
 
 bool conv3x3_v2_prepare(int device) { return upload_masks(device); }
+
+bool conv3x3_v2_can_fuse_heads(int ck, int has_res, int has_res_lo, int has_out_lo, int head_channels) {
+  if (ck != 64 || head_channels != 3 || !has_res) return false;
+  return (has_res_lo && has_out_lo) || (!has_res_lo && !has_out_lo);
+}
 
 int conv3x3_v2_smem_bytes(int ck) { return ck == 64 ? Cfg<64>::kSmem : Cfg<32>::kSmem; }
 

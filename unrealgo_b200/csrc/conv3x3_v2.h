@@ -9,6 +9,12 @@ namespace ug {
 
 struct ConvV2Args {
   const float* bias;      // [cout] folded batch-norm offset (fp32)
+  // fused head 1x1 convolutions (last tower layer only; see conv3x3_v2_can_fuse_heads): weights [head_channels][cout]
+  // and offsets [head_channels] in fp32, output [M][head_channels] fp32 = relu(conv + offset).  head_out == null: off.
+  const float* head_w;
+  const float* head_b;
+  float* head_out;
+  int head_channels;
   int M;                  // n * 361 output pixels
   int cin;                // input channels as stored (multiple of ck)
   int cout;               // <= 256, multiple of 32
@@ -38,6 +44,8 @@ struct ConvV2Maps {
 cudaError_t conv3x3_v2_launch(const ConvV2Maps& maps, ConvV2Args a, int ck, int device, int sms,
                               cudaStream_t stream);
 int conv3x3_v2_smem_bytes(int ck);
+// whether a launch with these flags and `head_channels` fused head outputs has a kernel instantiation
+bool conv3x3_v2_can_fuse_heads(int ck, int has_res, int has_res_lo, int has_out_lo, int head_channels);
 // uploads the lane-mask table for `device` (cudaMalloc + copy): call once outside any stream capture
 bool conv3x3_v2_prepare(int device);
 

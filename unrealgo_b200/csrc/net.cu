@@ -401,10 +401,25 @@ int ug_eval::enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, con
     a.bias = c2.bias.as<float>();
     a.has_res = 1;
     a.has_res_lo = a.has_out_lo = split;
+    // last layer: the head 1x1 convolutions ride in its epilogue and the activation itself is never stored
+    const bool fuse = fuse_heads && debug_stop < 0 && b == W.blocks - 1 &&
+                      conv3x3_v2_can_fuse_heads(64, 1, split, split, W.pc + W.vc);
+    if (fuse) {
+      a.head_w = W.head_conv_w.as<float>();
+      a.head_b = W.head_conv_b.as<float>();
+      a.head_out = d_feat.as<float>();
+      a.head_channels = W.pc + W.vc;
+    }
     m = ConvV2Maps{&v2_a_t, &c2.tm_w[1], &v2_res_hi[x], split ? &v2_res_lo[x] : nullptr, &v2_out_hi[y],
                    split ? &v2_out_lo[y] : nullptr};
     e = conv3x3_v2_launch(m, a, 64, device, sms, s);
     if (e != cudaSuccess) return fail(-1, std::string("tower conv launch: ") + cudaGetErrorString(e));
+    a.head_out = nullptr;
+    if (fuse) {  // d_feat already holds relu(head conv): enqueue_heads() skips its first stage
+      *final_act = nullptr;
+      *final_lo = nullptr;
+      break;
+    }
     *final_act = d_s_hi[y].p;
     *final_lo = split ? d_s_lo[y].p : nullptr;
     if (debug_stop == 2 * b + 2) break;
@@ -415,8 +430,9 @@ int ug_eval::enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, con
 int ug_eval::enqueue_heads(const void* act, const void* act_lo, int n, const uint32_t* d_leg, int vt, float* d_pol,
                            float* d_val, cudaStream_t s) {
   const HeadWeights hw = weights->head();
-  launch_head_conv(act, act_lo, precision == UG_PREC_FP32 ? 1 : (precision == UG_PREC_FP16 ? 2 : 0), hw,
-                   d_feat.as<float>(), n, s);
+  if (act != nullptr)  // null: the tower's last layer already produced d_feat (fused head convolutions)
+    launch_head_conv(act, act_lo, precision == UG_PREC_FP32 ? 1 : (precision == UG_PREC_FP16 ? 2 : 0), hw,
+                     d_feat.as<float>(), n, s);
   launch_head_fc(d_feat.as<float>(), hw, d_leg, vt, d_pol, d_val, n, s);
   return cudaGetLastError() == cudaSuccess ? 0 : fail(-1, "head kernel launch failed");
 }
@@ -438,7 +454,7 @@ int ug_eval::enqueue(Src kind, const void* d_src, int n, const uint32_t* d_leg, 
   if (n <= 0 || n > max_batch) return fail(-1, "batch size " + std::to_string(n) + " outside [1, max_batch]");
   if (!use_graphs) return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
   const GraphKey key((int)kind, n, d_src, (const void*)d_leg, (const void*)d_pol, (const void*)d_val, vt,
-                     conv_ctas * 4 + precision + (resid_split ? 8192 : 0) + conv_impl * 16384 + (use_pdl ? 65536 : 0) + (debug_stop + 1) * 16);
+                     conv_ctas * 4 + precision + (resid_split ? 8192 : 0) + conv_impl * 16384 + (use_pdl ? 65536 : 0) + (fuse_heads ? 131072 : 0) + (debug_stop + 1) * 16);
   auto it = graphs.find(key);
   if (it == graphs.end()) {
     if (graphs.size() > 1024) drop_graphs();
@@ -497,6 +513,8 @@ ug_eval* ug_eval_create(int device, int precision, int max_batch) {
   h->use_graphs = !(ng && ng[0] == '1');
   const char* cc = getenv("UGEVAL_CONV_CTAS");
   if (cc && (cc[0] == '1' || cc[0] == '2')) h->conv_ctas = cc[0] - '0';
+  const char* fh = getenv("UGEVAL_FUSE_HEADS");
+  if (fh && (fh[0] == '0' || fh[0] == '1')) h->fuse_heads = fh[0] == '1';
   const char* pd = getenv("UGEVAL_PDL");
   if (pd && (pd[0] == '0' || pd[0] == '1')) h->use_pdl = pd[0] == '1';
   const char* ci = getenv("UGEVAL_CONV_IMPL");
@@ -810,7 +828,7 @@ int ug_eval_bench(ug_eval* h, const ug_packed_pos* host_pos, int n, int iters, u
   if (!rc) rc = timed([&] { return h->enqueue_heads(act, act_lo, n, nullptr, h->value_transform, h->d_policy.as<float>(),
                                                     h->d_value.as<float>(), s); }, &out->ms_heads);
   out->ms_total = full * iters;
-  out->launches_per_pass = 1 + (h->precision == UG_PREC_FP32 ? 1 : 0) + 1 + 2 * h->weights->blocks + 2;
+  out->launches_per_pass = 1 + (h->precision == UG_PREC_FP32 ? 1 : 0) + 1 + 2 * h->weights->blocks + (act == nullptr ? 1 : 2);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return rc;

@@ -59,6 +59,7 @@ struct ug_eval {
   int sms = 148;
   int conv_ctas = 2;
   int conv_impl = 2;  // 1 = im2col kernel (conv3x3_tc.cu), 2 = resident-tile kernel (conv3x3_v2.cu)
+  bool fuse_heads = true;   // head 1x1 convolutions in the last tower layer's epilogue (UGEVAL_FUSE_HEADS=0 disables)
   bool use_pdl = true;      // programmatic dependent launch between tower layers (UGEVAL_PDL=0 disables)
   bool resid_split = true;  // carry the residual stream as hi + lo 16-bit pair (numerics)
   int value_transform = UG_TR_IDENTITY;
