@@ -97,6 +97,7 @@ def cpu_reference(args, seconds, batch):
     from oracle.net_oracle import GraphOracle
     from unrealgo_b200 import synth
     meta, prefix = checkpoint(args.blocks, args.filters)
+    torch.set_num_threads(os.cpu_count() or 1)
     orc = GraphOracle(meta, prefix)
     planes = synth.packed_to_planes(synth.synthetic_packed_positions(batch, seed=7))
     cores = torch.get_num_threads()
@@ -124,6 +125,7 @@ def main_reference(args):
     import torch
     from oracle.net_oracle import GraphOracle
     from unrealgo_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; this arm owns the host cores
     meta, prefix = checkpoint(args.blocks, args.filters)
     orc = GraphOracle(meta, prefix)
     planes = synth.packed_to_planes(synth.synthetic_packed_positions(batch, seed=7))
@@ -166,7 +168,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a rank that dies must not leave the others in a 10-minute collective timeout
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=240))
     B = args.batch
     meta, prefix = checkpoint(args.blocks, args.filters)
     # 262 positions = 5 full waves of the tower kernel (ug_eval_efficient_batch): the self-play leg batches up to that

@@ -6,15 +6,20 @@
 //   consumer: NetworkEvalThread spins, always evaluates all num_threads slots, and marks whichever slots
 //             are ready *after* the evaluation as evaluated (search/UctSearch.cpp:164-205) — a slot that
 //             became ready mid-evaluation gets a stale result, and the batch is capped at MAX_BATCHES=16.
-// Here: a bounded multi-producer ring with per-slot sequence numbers (claim = one fetch_add, no lock), a
-// gather thread that snapshots *published* leaves only (so every ticket gets exactly its own result), flushes
-// on max_batch or timeout, and double-buffered pinned staging: the H2D copy of batch k+1 and the D2H copy of
-// batch k-1 run on their own streams while batch k is in the tower.
+// Here: leaves live in a pool of slots.  A producer takes a free slot (lock-free bounded MPMC free list), fills
+// it and pushes its id on a lock-free bounded multi-producer submission queue; the gather thread pops ids in
+// arrival order (only *published* leaves, so every ticket gets exactly its own result), flushes on max_batch or
+// timeout, and runs double-buffered pinned staging: the H2D copy of batch k+1 and the D2H copy of batch k-1
+// run on their own streams while batch k is in the tower.  Results are written back into the slots; the
+// consumer frees the slot when it takes the result.  Because a slot is owned by one leaf from submit to
+// poll/wait — not by a position in a ring — a producer that is slow to collect a result can never block
+// another producer's submit (an earlier ring-of-slots version deadlocked when the ring lapped a parked result).
 #include <cuda_runtime.h>
 
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -25,14 +30,70 @@
 
 namespace {
 
+enum : uint32_t { SLOT_FREE = 0, SLOT_QUEUED = 1, SLOT_READY = 2 };
+
 struct Slot {
-  std::atomic<uint64_t> seq;   // == ticket: free for that ticket; ticket+1: published; ticket+2: result ready
+  std::atomic<uint32_t> state{SLOT_FREE};
+  std::atomic<uint64_t> ticket{0};  // (allocation count << 20) | slot id: stale tickets never match
+  uint64_t allocs = 0;              // touched by the owner only
   ug_packed_pos pos;
   uint32_t legal[UG_MASK_WORDS];
   uint32_t has_legal;
   float policy[UG_NUM_MOVES];
   float value;
 };
+
+// Bounded MPMC queue of slot ids (D. Vyukov's array queue): per-cell sequence numbers, one CAS per operation.
+struct IdQueue {
+  struct Cell { std::atomic<uint64_t> seq; uint32_t id; };
+  std::vector<Cell> cells;
+  uint64_t mask = 0;
+  alignas(64) std::atomic<uint64_t> enq{0};
+  alignas(64) std::atomic<uint64_t> deq{0};
+  void init(uint64_t cap) {
+    cells = std::vector<Cell>(cap);
+    mask = cap - 1;
+    for (uint64_t i = 0; i < cap; ++i) cells[i].seq.store(i, std::memory_order_relaxed);
+  }
+  bool push(uint32_t id) {
+    uint64_t pos = enq.load(std::memory_order_relaxed);
+    for (;;) {
+      Cell& c = cells[pos & mask];
+      const int64_t dif = (int64_t)c.seq.load(std::memory_order_acquire) - (int64_t)pos;
+      if (dif == 0) {
+        if (enq.compare_exchange_weak(pos, pos + 1, std::memory_order_relaxed)) {
+          c.id = id;
+          c.seq.store(pos + 1, std::memory_order_release);
+          return true;
+        }
+      } else if (dif < 0) {
+        return false;  // full
+      } else {
+        pos = enq.load(std::memory_order_relaxed);
+      }
+    }
+  }
+  bool pop(uint32_t* id) {
+    uint64_t pos = deq.load(std::memory_order_relaxed);
+    for (;;) {
+      Cell& c = cells[pos & mask];
+      const int64_t dif = (int64_t)c.seq.load(std::memory_order_acquire) - (int64_t)(pos + 1);
+      if (dif == 0) {
+        if (deq.compare_exchange_weak(pos, pos + 1, std::memory_order_relaxed)) {
+          *id = c.id;
+          c.seq.store(pos + mask + 1, std::memory_order_release);
+          return true;
+        }
+      } else if (dif < 0) {
+        return false;  // empty (or the next cell is claimed but not yet published)
+      } else {
+        pos = deq.load(std::memory_order_relaxed);
+      }
+    }
+  }
+};
+
+constexpr int kIdBits = 20;
 
 struct Staging {
   ug_packed_pos* h_pos = nullptr;   // pinned
@@ -43,7 +104,7 @@ struct Staging {
   float* d_policy = nullptr;
   float* d_value = nullptr;
   cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
-  uint64_t first_ticket = 0;
+  std::vector<uint32_t> ids;         // slot id of every leaf in the batch
   int n = 0;
   bool any_legal = false;
   bool busy = false;
@@ -61,10 +122,10 @@ struct ug_queue {
   ug_eval* eval = nullptr;
   int max_batch = 0;
   int timeout_us = 0;
-  uint64_t capacity = 0, mask = 0;
+  uint64_t capacity = 0;
   std::vector<Slot> slots;
-  std::atomic<uint64_t> tail{0};   // next ticket to hand out
-  uint64_t head = 0;               // next ticket to gather (gather thread only)
+  IdQueue free_ids, submitted;
+  std::vector<uint32_t> carry;     // gathered but cut from the last batch (gather thread only)
   Staging st[2];
   cudaStream_t s_in = nullptr, s_out = nullptr;
   std::thread gather_thread, complete_thread;
@@ -96,15 +157,17 @@ void ug_queue::gather_loop() {
       }
     }
     // wait for the first published leaf
-    Slot& first = slots[head & mask];
-    if (first.seq.load(std::memory_order_acquire) != head + 1) {
-      for (int i = 0; i < 64; ++i) cpu_relax();
-      if (first.seq.load(std::memory_order_acquire) != head + 1) {
+    if (carry.empty()) {
+      uint32_t id;
+      bool got = submitted.pop(&id);
+      for (int i = 0; i < 64 && !got; ++i) { cpu_relax(); got = submitted.pop(&id); }
+      if (!got) {
         std::this_thread::sleep_for(std::chrono::microseconds(5));
         continue;
       }
+      carry.push_back(id);
     }
-    // a staging buffer must be free before leaves are pulled out of the ring
+    // a staging buffer must be free before leaves are copied out of their slots
     Staging& S = st[which];
     {
       std::unique_lock<std::mutex> lk(mu);
@@ -116,32 +179,40 @@ void ug_queue::gather_loop() {
     int n = 0;
     bool timed_out = false;
     S.any_legal = false;
-    S.first_ticket = head;
+    S.ids.clear();
+    size_t from_carry = 0;
     while (n < max_batch) {
-      Slot& sl = slots[(head + n) & mask];
-      if (sl.seq.load(std::memory_order_acquire) == head + n + 1) {
-        memcpy(&S.h_pos[n], &sl.pos, sizeof(ug_packed_pos));
-        if (sl.has_legal) {
-          memcpy(&S.h_legal[(size_t)n * UG_MASK_WORDS], sl.legal, sizeof(sl.legal));
-          S.any_legal = true;
-        } else {
-          memset(&S.h_legal[(size_t)n * UG_MASK_WORDS], 0xff, sizeof(sl.legal));
-        }
-        ++n;
+      uint32_t id;
+      if (from_carry < carry.size()) id = carry[from_carry++];
+      else if (!submitted.pop(&id)) {
+        const auto dt = std::chrono::steady_clock::now() - t0;
+        if (std::chrono::duration_cast<std::chrono::microseconds>(dt).count() >= timeout_us) { timed_out = true; break; }
+        cpu_relax();
         continue;
       }
-      const auto dt = std::chrono::steady_clock::now() - t0;
-      if (std::chrono::duration_cast<std::chrono::microseconds>(dt).count() >= timeout_us) { timed_out = true; break; }
-      cpu_relax();
+      S.ids.push_back(id);
+      ++n;
     }
+    carry.erase(carry.begin(), carry.begin() + (long)from_carry);
     if (timed_out) {
       n_timeouts.fetch_add(1, std::memory_order_relaxed);
-      // a partial batch is cut back to whole waves of the tower kernel; the leaves beyond stay published in
-      // the ring and open the next batch
-      n = ug_eval_efficient_batch(eval, n);
+      // a partial batch is cut back to whole waves of the tower kernel; the leaves beyond open the next batch
+      const int keep = ug_eval_efficient_batch(eval, n);
+      carry.insert(carry.begin(), S.ids.begin() + keep, S.ids.end());
+      S.ids.resize((size_t)keep);
+      n = keep;
+    }
+    for (int i = 0; i < n; ++i) {
+      const Slot& sl = slots[S.ids[(size_t)i]];
+      memcpy(&S.h_pos[i], &sl.pos, sizeof(ug_packed_pos));
+      if (sl.has_legal) {
+        memcpy(&S.h_legal[(size_t)i * UG_MASK_WORDS], sl.legal, sizeof(sl.legal));
+        S.any_legal = true;
+      } else {
+        memset(&S.h_legal[(size_t)i * UG_MASK_WORDS], 0xff, sizeof(sl.legal));
+      }
     }
     S.n = n;
-    head += n;
     // H2D on the copy-in stream, tower on the evaluator stream, D2H on the copy-out stream
     cudaMemcpyAsync(S.d_pos, S.h_pos, (size_t)n * sizeof(ug_packed_pos), cudaMemcpyHostToDevice, s_in);
     if (S.any_legal)
@@ -155,7 +226,8 @@ void ug_queue::gather_loop() {
     if (n_run > max_batch) n_run = max_batch;
     const int rc = ug_eval_run_packed_device(eval, S.d_pos, n_run, S.any_legal ? S.d_legal : nullptr, S.d_policy,
                                              S.d_value, eval->stream);
-    if (rc != 0) error.store(rc);
+    if (rc != 0 && error.exchange(rc) == 0)
+      fprintf(stderr, "ugeval queue: evaluator failure %d on a batch of %d: %s\n", rc, n_run, ug_last_error(eval));
     cudaEventRecord(S.ev_done, eval->stream);
     cudaStreamWaitEvent(s_out, S.ev_done, 0);
     cudaMemcpyAsync(S.h_out, S.d_policy, (size_t)n * UG_NUM_MOVES * 4, cudaMemcpyDeviceToHost, s_out);
@@ -183,13 +255,14 @@ void ug_queue::complete_loop() {
       which = inflight.front();
     }
     Staging& S = st[which];
-    if (cudaEventSynchronize(S.ev_out) != cudaSuccess) error.store(-1);
+    const cudaError_t ce = cudaEventSynchronize(S.ev_out);
+    if (ce != cudaSuccess && error.exchange(-1) == 0)
+      fprintf(stderr, "ugeval queue: CUDA error while waiting for a batch: %s\n", cudaGetErrorString(ce));
     for (int i = 0; i < S.n; ++i) {
-      const uint64_t ticket = S.first_ticket + (uint64_t)i;
-      Slot& sl = slots[ticket & mask];
+      Slot& sl = slots[S.ids[(size_t)i]];
       memcpy(sl.policy, S.h_out + (size_t)i * UG_NUM_MOVES, sizeof(sl.policy));
       sl.value = S.h_out[(size_t)S.n * UG_NUM_MOVES + i];
-      sl.seq.store(ticket + 2, std::memory_order_release);
+      sl.state.store(SLOT_READY, std::memory_order_release);
     }
     {
       std::lock_guard<std::mutex> lk(mu);
@@ -213,15 +286,18 @@ ug_queue* ug_queue_create(ug_eval* h, int max_batch, int timeout_us, int capacit
   q->eval = h;
   q->max_batch = max_batch;
   q->timeout_us = timeout_us < 0 ? 0 : timeout_us;
+  if (cap > (1ull << kIdBits)) cap = 1ull << kIdBits;
   q->capacity = cap;
-  q->mask = cap - 1;
   q->slots = std::vector<Slot>(cap);
-  for (uint64_t i = 0; i < cap; ++i) q->slots[i].seq.store(i, std::memory_order_relaxed);
+  q->free_ids.init(cap);
+  q->submitted.init(cap);
+  for (uint64_t i = 0; i < cap; ++i) q->free_ids.push((uint32_t)i);
   bool ok = cudaStreamCreateWithFlags(&q->s_in, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&q->s_out, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < 2 && ok; ++i) {
     Staging& S = q->st[i];
     const size_t nb = (size_t)max_batch;
+    S.ids.reserve(nb);
     ok = cudaMallocHost((void**)&S.h_pos, nb * sizeof(ug_packed_pos)) == cudaSuccess &&
          cudaMallocHost((void**)&S.h_legal, nb * UG_MASK_WORDS * 4) == cudaSuccess &&
          cudaMallocHost((void**)&S.h_out, nb * (UG_NUM_MOVES + 1) * 4) == cudaSuccess &&
@@ -277,46 +353,64 @@ void ug_queue_destroy(ug_queue* q) {
 
 int64_t ug_queue_submit(ug_queue* q, const ug_packed_pos* pos, const uint32_t* legal) {
   if (!q || !pos) return -1;
-  const uint64_t ticket = q->tail.fetch_add(1, std::memory_order_acq_rel);
-  Slot& sl = q->slots[ticket & q->mask];
-  // the slot is ours once the previous lap's owner has consumed its result
+  uint32_t id;
   int spins = 0;
-  while (sl.seq.load(std::memory_order_acquire) != ticket) {
-    if (q->quit.load(std::memory_order_acquire)) return -1;
+  // a free slot: there is always one unless more leaves are outstanding than the pool holds
+  while (!q->free_ids.pop(&id)) {
+    if (q->quit.load(std::memory_order_acquire) || q->error.load(std::memory_order_relaxed)) return -1;
     if (++spins < 256) cpu_relax(); else std::this_thread::yield();
   }
+  Slot& sl = q->slots[id];
   memcpy(&sl.pos, pos, sizeof(ug_packed_pos));
   sl.has_legal = legal ? 1u : 0u;
   if (legal) memcpy(sl.legal, legal, sizeof(sl.legal));
-  sl.seq.store(ticket + 1, std::memory_order_release);
+  const uint64_t ticket = (++sl.allocs << kIdBits) | id;
+  sl.ticket.store(ticket, std::memory_order_relaxed);
+  sl.state.store(SLOT_QUEUED, std::memory_order_release);
+  q->submitted.push(id);  // cannot be full: at most `capacity` ids exist
   return (int64_t)ticket;
+}
+
+static inline Slot* slot_of(ug_queue* q, int64_t ticket) {
+  const uint64_t id = (uint64_t)ticket & ((1ull << kIdBits) - 1);
+  return id < q->capacity ? &q->slots[id] : nullptr;
+}
+
+// result ready for exactly this ticket?  (a consumed or foreign ticket never matches)
+static inline bool ready(const Slot& sl, int64_t ticket) {
+  return sl.state.load(std::memory_order_acquire) == SLOT_READY &&
+         sl.ticket.load(std::memory_order_relaxed) == (uint64_t)ticket;
+}
+
+static inline void take(ug_queue* q, Slot& sl, int64_t ticket, float* policy, float* value) {
+  if (policy) memcpy(policy, sl.policy, sizeof(sl.policy));
+  if (value) *value = sl.value;
+  sl.state.store(SLOT_FREE, std::memory_order_release);
+  q->free_ids.push((uint32_t)((uint64_t)ticket & ((1ull << kIdBits) - 1)));
 }
 
 int ug_queue_wait(ug_queue* q, int64_t ticket, float* policy, float* value) {
   if (!q || ticket < 0) return -1;
-  const uint64_t t = (uint64_t)ticket;
-  Slot& sl = q->slots[t & q->mask];
+  Slot* sl = slot_of(q, ticket);
+  if (!sl) return -1;
   int spins = 0;
-  while (sl.seq.load(std::memory_order_acquire) != t + 2) {
+  while (!ready(*sl, ticket)) {
     if (q->quit.load(std::memory_order_acquire)) return -1;
+    if (sl->ticket.load(std::memory_order_relaxed) != (uint64_t)ticket) return -1;  // not an outstanding ticket
     if (++spins < 2000) { cpu_relax(); continue; }
     std::unique_lock<std::mutex> lk(q->mu);
     q->cv_results.wait_for(lk, std::chrono::microseconds(200));
   }
-  if (policy) memcpy(policy, sl.policy, sizeof(sl.policy));
-  if (value) *value = sl.value;
-  sl.seq.store(t + q->capacity, std::memory_order_release);  // free for the next lap
+  take(q, *sl, ticket, policy, value);
   return q->error.load() ? -1 : 0;
 }
 
 int ug_queue_poll(ug_queue* q, int64_t ticket, float* policy, float* value) {
   if (!q || ticket < 0) return -1;
-  const uint64_t t = (uint64_t)ticket;
-  Slot& sl = q->slots[t & q->mask];
-  if (sl.seq.load(std::memory_order_acquire) != t + 2) return q->quit.load(std::memory_order_acquire) ? -1 : 0;
-  if (policy) memcpy(policy, sl.policy, sizeof(sl.policy));
-  if (value) *value = sl.value;
-  sl.seq.store(t + q->capacity, std::memory_order_release);
+  Slot* sl = slot_of(q, ticket);
+  if (!sl) return -1;
+  if (!ready(*sl, ticket)) return q->quit.load(std::memory_order_acquire) ? -1 : 0;
+  take(q, *sl, ticket, policy, value);
   return q->error.load() ? -1 : 1;
 }
 

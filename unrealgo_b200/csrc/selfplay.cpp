@@ -14,6 +14,8 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <random>
@@ -138,6 +140,7 @@ bool start_playout(Game& g, Shared& sh) {
   g.work.pack(&pos);
   g.leaf = node;
   g.ticket = ug_queue_submit(sh.q, &pos, legal);
+  if (g.ticket < 0) sh.stop.store(true);  // queue closed or evaluator failed: every worker winds down
   return g.ticket >= 0;
 }
 
@@ -264,7 +267,30 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
     if (lo >= hi) break;
     threads.emplace_back([&games, lo, hi, &sh] { worker(games, lo, hi, sh); });
   }
+  // optional progress log (UGEVAL_SP_LOG=<seconds>): playouts and queue counters while the games run
+  std::atomic<bool> done{false};
+  std::thread monitor;
+  if (const char* lg = getenv("UGEVAL_SP_LOG")) {
+    const double every = atof(lg) > 0 ? atof(lg) : 2.0;
+    monitor = std::thread([&sh, &done, every, t0] {
+      auto next = std::chrono::steady_clock::now();
+      while (!done.load(std::memory_order_acquire)) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(50));
+        if (std::chrono::steady_clock::now() < next) continue;
+        next += std::chrono::microseconds((long long)(every * 1e6));
+        uint64_t b = 0, l = 0, to = 0;
+        ug_queue_stats(sh.q, &b, &l, &to);
+        fprintf(stderr, "[selfplay %.1fs] playouts=%llu moves=%llu games_done=%llu batches=%llu leaves=%llu timeouts=%llu\n",
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(),
+                (unsigned long long)sh.playouts.load(), (unsigned long long)sh.moves.load(),
+                (unsigned long long)sh.games_done.load(), (unsigned long long)b, (unsigned long long)l,
+                (unsigned long long)to);
+      }
+    });
+  }
   for (std::thread& t : threads) t.join();
+  done.store(true, std::memory_order_release);
+  if (monitor.joinable()) monitor.join();
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   uint64_t batches = 0, leaves = 0, timeouts = 0;
   ug_queue_stats(sh.q, &batches, &leaves, &timeouts);
