@@ -288,6 +288,11 @@ def main():
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     burst = peaks.get("bf16_tflops", 1590.0)
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    traffic = None
+    try:  # DRAM bytes per launch from the committed ncu capture (mean of the two tower-conv variants)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["tower_conv_mean"]
+    except Exception:
+        pass
     if rank == 0:
         value = world * B * args.steps / (dev_ms * 1e-3)
         e2e_v = world * B * e2e_steps / e2e_s
@@ -318,7 +323,9 @@ def main():
                                         if peaks else "fallback",
                          "kernel": (f"conv3x3_v2_kernel<64> cta_group::2 (3x3 {C}->{C}, M={B * 361})" if info.get("conv_impl") == 2
                                     else f"conv3x3_tc_kernel<64,{info['conv_ctas']}> (3x3 {C}->{C}, M={B * 361})"),
-                         "flops_per_launch": conv_flops, "ms_per_launch": conv_ms, "traffic": None},
+                         "flops_per_launch": conv_flops, "ms_per_launch": conv_ms, "traffic": traffic,
+                         "traffic_note": "DRAM read+write bytes per launch, mean of the two tower-conv variants, from "
+                                         "profiles/r01_traffic.json (ncu --set full, cold L2); tensor-bound kernel"},
         }
         if sp is not None:
             out["selfplay"] = sp
