@@ -161,7 +161,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from unrealgo_b200 import PREC_BF16, PREC_FP16, DlTFNetworkEvaluator, selfplay, synth
+    from unrealgo_b200 import PREC_BF16, PREC_FP16, DlTFNetworkEvaluator, selfplay, shard, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -227,6 +227,8 @@ def main():
     planes = [synth.packed_to_planes(p) for p in host_packed[:2]]
     pol = np.empty((B, 362), np.float64)
     val = np.empty(B, np.float64)
+    # the reference's EvalBuffer is one fixed allocation: page-lock the caller arrays once, as its shim does
+    registered = ev.register_host(planes[0], planes[1], pol, val)
     for i in range(3):
         assert ev.Evaluate(planes[i % 2], pol, val, B)
     if world > 1:
@@ -257,13 +259,11 @@ def main():
         st, _ = selfplay(ev, games=args.sp_games, threads=threads, playouts_per_move=args.sp_playouts,
                          max_moves=args.sp_moves, max_batch=SP_BATCH, timeout_us=300, reuse_tree=True,
                          random_opening_moves=1, seed=1000 + rank)
-        tsp = torch.tensor([float(st["playouts"]), float(st["evaluations"])], dtype=torch.float64, device="cuda")
-        tsec = torch.tensor([st["seconds"]], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tsp, op=dist.ReduceOp.SUM)
-            dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
-        sp = {"playouts_per_s": float(tsp[0].item()) / float(tsec.item()), "unit": "playouts/s",
-              "evaluations_per_s": float(tsp[1].item()) / float(tsec.item()), "seconds": float(tsec.item()),
+        # whole-job rate = playouts of all ranks / slowest rank's time (shard.reduce_throughput: SUM, MAX)
+        playouts, sp_secs = shard.reduce_throughput(st["playouts"], st["seconds"], device="cuda")
+        evals, _ = shard.reduce_throughput(st["evaluations"], st["seconds"], device="cuda")
+        sp = {"playouts_per_s": playouts / sp_secs, "unit": "playouts/s",
+              "evaluations_per_s": evals / sp_secs, "seconds": sp_secs,
               "games_per_gpu": args.sp_games, "search_threads_per_gpu": threads, "host_cpus": os.cpu_count(),
               "leaf_batch_cap": SP_BATCH,
               "playouts_per_move": args.sp_playouts, "moves_per_game_sampled": args.sp_moves,
@@ -314,8 +314,9 @@ def main():
                        "kernel_group_ms": {"encoder": br["ms_encoder"], "tower": br["ms_tower"], "heads": br["ms_heads"],
                                            "stem": br_stem["ms_tower"]}},
             "clocks": sampler.summary(),
-            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": B * 17 * 361, "d2h_bytes_per_step": B * 363 * 4,
-                    "api": "DlTFNetworkEvaluator::Evaluate (ug_eval_run_planes): host int8 planes -> host double policy/value"},
+            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": B * 17 * 361, "d2h_bytes_per_step": B * 363 * (8 if registered == 4 else 4),
+                    "api": "DlTFNetworkEvaluator::Evaluate (ug_eval_run_planes): host int8 planes -> host double policy/value",
+                    "host_buffers": f"{registered}/4 caller arrays page-locked once with ug_eval_register_host"},
             "gpu_launches": br["launches_per_pass"] * args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "frac_of_burst": achieved / burst,

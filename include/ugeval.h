@@ -111,6 +111,13 @@ int ug_eval_run_planes(ug_eval* h, const int8_t* chw, int n, double* policy, dou
 /* Evaluate(char feature[][19][19][17], ...) overload, .cc:321-352. */
 int ug_eval_run_planes_hwc(ug_eval* h, const int8_t* hwc, int n, double* policy, double* value);
 
+/* Optional: page-lock a caller buffer that run_planes calls will use (feature, policy or value array — the reference's
+ * EvalBuffer is one fixed allocation, search/UctSearch.h:126-130) so the evaluator copies straight from/to it instead
+ * of going through its own pinned staging; outputs are then widened to double on the GPU.  0 ok, >0 refused
+ * (the call still works through staging).  Unregister before freeing the memory; destroy unregisters the rest. */
+int ug_eval_register_host(ug_eval* h, void* p, size_t bytes);
+int ug_eval_unregister_host(ug_eval* h, void* p);
+
 /* Native fast path: packed leaves in, fp32 out, HOST buffers, synchronous (H2D + kernels + D2H).
  * legal (optional, n x 12 words, bit i = move index i legal, 361 = pass): priors are renormalised over the
  * legal set as UctSearch::UpdatePrior does (search/UctSearch.cpp:1257-1270), illegal entries are 0. */

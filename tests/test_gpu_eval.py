@@ -209,3 +209,27 @@ def test_fused_head_convolutions_match_the_separate_kernel(wide_ckpt, monkeypatc
     ps, vs = ev.evaluate_packed(packed)
     ev.close()
     assert np.abs(pf - ps).max() <= 1e-5 and np.abs(vf - vs).max() <= 1e-4
+
+
+def test_registered_host_buffers_give_identical_results(small_ckpt):
+    """Evaluate() through page-locked caller arrays (direct DMA, outputs widened on the GPU) must return exactly
+    what the staged path returns, including value_transform, and must leave foreign arrays on the staged path."""
+    import oracle
+    from unrealgo_b200 import TR_FLIP_PROB, DlTFNetworkEvaluator
+    _, planes = oracle.synthetic_positions(19, seed=31)
+    ev = DlTFNetworkEvaluator(small_ckpt[0], max_batch=32)
+    assert ev.UpdateCheckPoint(small_ckpt[1])
+    ev.set_value_transform(TR_FLIP_PROB)
+    p0, v0 = np.zeros((19, 362)), np.zeros(19)
+    assert ev.Evaluate(planes, p0, v0, 19)
+    planes_r = planes.copy()
+    p1, v1 = np.full((19, 362), -7.0), np.full(19, -7.0)
+    assert ev.register_host(planes_r, p1, v1) == 3
+    assert ev.Evaluate(planes_r, p1, v1, 19)
+    assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
+    # mixed: registered input, unregistered outputs
+    p2, v2 = np.zeros((19, 362)), np.zeros(19)
+    assert ev.Evaluate(planes_r, p2, v2, 19)
+    assert np.array_equal(p0, p2) and np.array_equal(v0, v2)
+    ev.unregister_host(planes_r, p1, v1)
+    ev.close()

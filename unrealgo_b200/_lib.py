@@ -73,6 +73,8 @@ SIGNATURES = {
     "ug_eval_set_residual_split": (C.c_int, [C.c_void_p, C.c_int]),
     "ug_eval_run_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ug_eval_run_planes_hwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ug_eval_register_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ug_eval_unregister_host": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ug_eval_run_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ug_eval_run_packed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p]),

@@ -141,6 +141,19 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
   if (i < count) out[i] = unpack1(reinterpret_cast<const uint16_t*>(in)[i], f16);
 }
 
+__global__ void widen_outputs_kernel(const float* __restrict__ policy, const float* __restrict__ value,
+                                     double* __restrict__ policy64, double* __restrict__ value64, int n, int vt) {
+  const size_t total = (size_t)n * UG_NUM_MOVES;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) policy64[i] = (double)policy[i];
+  if (i < (size_t)n) {
+    double d = (double)value[i];
+    if (vt == UG_TR_FLIP_SIGN) d = -d;
+    else if (vt == UG_TR_FLIP_PROB) d = 1 - d;
+    value64[i] = d;
+  }
+}
+
 inline int pos_grid(int n) { return n < 148 * 16 ? n : 148 * 16; }
 
 }  // namespace
@@ -166,6 +179,12 @@ void launch_nhwc_to_f32(const __nv_bfloat16* in, float* out, int n, int f16, cud
   if (n <= 0) return;
   const size_t total = (size_t)n * kPoints * UG_NUM_PLANES;
   nhwc_to_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, out, total, f16);
+}
+void launch_widen_outputs(const float* policy, const float* value, double* policy64, double* value64, int n, int vt,
+                          cudaStream_t s) {
+  if (n <= 0) return;
+  const size_t total = (size_t)n * UG_NUM_MOVES;
+  widen_outputs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(policy, value, policy64, value64, n, vt);
 }
 void launch_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t count, int f16, cudaStream_t s) {
   if (count == 0) return;

@@ -48,6 +48,10 @@ void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* leg
 void launch_conv3x3_f32(const float* in, const float* w_hwio, const float* bias, const float* res, float* out,
                         int n, int cin, int cout, int relu, cudaStream_t s);
 // bf16 <-> fp32 images for debug readback
+// out64[i] = (double)in[i] for the policy; value: widened, then value_transform applied in double exactly as the
+// reference does on the host (DlTensorUtil::GetValue + DlTFNetworkEvaluator.cc:300-310)
+void launch_widen_outputs(const float* policy, const float* value, double* policy64, double* value64, int n, int vt,
+                          cudaStream_t s);
 void launch_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t count, int f16, cudaStream_t s);
 
 }  // namespace ug

@@ -221,8 +221,16 @@ bool ends_with(const std::string& s, const char* suf) {
 using namespace ug;
 
 // ------------------------------------------------------------------------------------------ ug_eval members
+bool ug_eval::is_registered(const void* p, size_t bytes) const {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  for (const auto& r : host_regs)
+    if (a >= r.first && a + bytes <= r.first + r.second) return true;
+  return false;
+}
+
 ug_eval::~ug_eval() {
   if (stream) cudaStreamSynchronize(stream);
+  for (const auto& r : host_regs) cudaHostUnregister(reinterpret_cast<void*>(r.first));
   drop_graphs();
   delete weights;
   if (h_pinned) cudaFreeHost(h_pinned);
@@ -242,7 +250,8 @@ bool ug_eval::ensure_workspace(int C) {
   bool ok = d_pos.alloc(nb * sizeof(ug_packed_pos)) && d_legal.alloc(nb * UG_MASK_WORDS * 4) &&
             d_planes.alloc(nb * UG_NUM_PLANES * UG_NUM_POINTS) && d_bytes.alloc(nb * UG_NUM_PLANES * UG_NUM_POINTS) &&
             d_in.alloc(nb * UG_NUM_POINTS * kCinPad * 2) && d_feat.alloc(nb * UG_NUM_POINTS * 8 * 4) &&
-            d_policy.alloc(nb * UG_NUM_MOVES * 4) && d_value.alloc(nb * 4);
+            d_policy.alloc(nb * UG_NUM_MOVES * 4) && d_value.alloc(nb * 4) &&
+            d_policy64.alloc(nb * UG_NUM_MOVES * 8) && d_value64.alloc(nb * 8);
   for (int i = 0; i < 2 && ok; ++i) ok = d_s_hi[i].alloc(act_elems * 2) && d_s_lo[i].alloc(act_elems * 2);
   ok = ok && d_t.alloc(act_elems * 2);
   if (ok && precision == UG_PREC_FP32) {
@@ -668,21 +677,40 @@ static int run_planes_common(ug_eval* h, const int8_t* planes, int hwc, int n, d
   if (n <= 0 || n > h->max_batch) return h->fail(-1, "Running model failed: bad batch size");
   cudaSetDevice(h->device);
   const size_t in_bytes = (size_t)n * UG_NUM_PLANES * UG_NUM_POINTS;
+  const size_t pol_count = (size_t)n * UG_NUM_MOVES;
   uint8_t* stage = static_cast<uint8_t*>(h->h_pinned);
   float* out_stage = reinterpret_cast<float*>(stage + (((size_t)h->max_batch * UG_NUM_PLANES * UG_NUM_POINTS + 255) & ~size_t(255)));
-  memcpy(stage, planes, in_bytes);
   cudaStream_t s = h->stream;
-  cudaMemcpyAsync(h->d_planes.p, stage, in_bytes, cudaMemcpyHostToDevice, s);
-  // value_transform is applied below in double, exactly as the reference does after widening (.cc:298-310)
+  // caller buffers registered with ug_eval_register_host are DMA sources/targets themselves (the reference's
+  // EvalBuffer is one fixed allocation, search/UctSearch.h:126-130); anything else goes through pinned staging
+  if (h->is_registered(planes, in_bytes)) {
+    cudaMemcpyAsync(h->d_planes.p, planes, in_bytes, cudaMemcpyHostToDevice, s);
+  } else {
+    memcpy(stage, planes, in_bytes);
+    cudaMemcpyAsync(h->d_planes.p, stage, in_bytes, cudaMemcpyHostToDevice, s);
+  }
+  // value_transform is applied in double after widening, exactly as the reference does (.cc:298-310)
   int rc = h->enqueue(hwc ? ug_eval::SRC_HWC : ug_eval::SRC_CHW, h->d_planes.p, n, nullptr, UG_TR_IDENTITY,
                       h->d_policy.as<float>(), h->d_value.as<float>(), s);
   if (rc) return rc;
-  cudaMemcpyAsync(out_stage, h->d_policy.p, (size_t)n * UG_NUM_MOVES * 4, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(out_stage + (size_t)n * UG_NUM_MOVES, h->d_value.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s);
+  const bool direct_out = h->is_registered(policy, pol_count * 8) && h->is_registered(value, (size_t)n * 8);
+  if (direct_out) {
+    // Outputs must stay untouched on failure (.cc:315-317): a faulting kernel poisons the stream, so the copies
+    // queued behind it never run.
+    launch_widen_outputs(h->d_policy.as<float>(), h->d_value.as<float>(), h->d_policy64.as<double>(),
+                         h->d_value64.as<double>(), n, h->value_transform, s);
+    cudaMemcpyAsync(policy, h->d_policy64.p, pol_count * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(value, h->d_value64.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s);
+    const cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return h->fail(-1, std::string("Running model failed: ") + cudaGetErrorString(e));
+    return 0;
+  }
+  cudaMemcpyAsync(out_stage, h->d_policy.p, pol_count * 4, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(out_stage + pol_count, h->d_value.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s);
   const cudaError_t e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return h->fail(-1, std::string("Running model failed: ") + cudaGetErrorString(e));
-  for (size_t i = 0; i < (size_t)n * UG_NUM_MOVES; ++i) policy[i] = (double)out_stage[i];  // DlTensorUtil::GetValue
-  const float* v = out_stage + (size_t)n * UG_NUM_MOVES;
+  for (size_t i = 0; i < pol_count; ++i) policy[i] = (double)out_stage[i];  // DlTensorUtil::GetValue
+  const float* v = out_stage + pol_count;
   for (int i = 0; i < n; ++i) {
     double d = (double)v[i];
     if (h->value_transform == UG_TR_FLIP_SIGN) d = -d;
@@ -690,6 +718,33 @@ static int run_planes_common(ug_eval* h, const int8_t* planes, int hwc, int n, d
     value[i] = d;
   }
   return 0;
+}
+
+int ug_eval_register_host(ug_eval* h, void* p, size_t bytes) {
+  if (!h || !p || bytes == 0) return -1;
+  if (h->is_registered(p, bytes)) return 0;
+  if (h->host_regs.size() >= 64) return h->fail(1, "too many registered host buffers");
+  cudaSetDevice(h->device);
+  const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return h->fail(1, std::string("cudaHostRegister failed: ") + cudaGetErrorString(e));
+  }
+  h->host_regs.emplace_back(reinterpret_cast<uintptr_t>(p), bytes);
+  return 0;
+}
+
+int ug_eval_unregister_host(ug_eval* h, void* p) {
+  if (!h || !p) return -1;
+  for (size_t i = 0; i < h->host_regs.size(); ++i)
+    if (h->host_regs[i].first == reinterpret_cast<uintptr_t>(p)) {
+      cudaSetDevice(h->device);
+      cudaStreamSynchronize(h->stream);
+      cudaHostUnregister(p);
+      h->host_regs.erase(h->host_regs.begin() + (long)i);
+      return 0;
+    }
+  return 1;
 }
 
 int ug_eval_run_planes(ug_eval* h, const int8_t* chw, int n, double* policy, double* value) {

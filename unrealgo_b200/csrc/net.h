@@ -81,6 +81,8 @@ struct ug_eval {
   // workspace (allocated once the architecture is known)
   int ws_C = 0;
   ug::DevBuf d_pos, d_legal, d_planes, d_in, d_feat, d_policy, d_value, d_bytes;
+  ug::DevBuf d_policy64, d_value64;  // double images of the outputs for registered (pinned) caller buffers
+  std::vector<std::pair<uintptr_t, size_t>> host_regs;  // caller buffers registered with ug_eval_register_host
   // residual stream ping-pong S[0]/S[1] as bf16 hi + bf16 lo (skip = hi + lo), block-internal tensor T (bf16)
   ug::DevBuf d_s_hi[2], d_s_lo[2], d_t;
   ug::DevBuf f_in, f_s[2], f_t;  // fp32 validation build
@@ -97,6 +99,7 @@ struct ug_eval {
   ~ug_eval();
   int fail(int code, const std::string& msg) const { last_error = msg; return code; }
   bool ensure_workspace(int C);
+  bool is_registered(const void* p, size_t bytes) const;
   void drop_graphs();
   // source kinds for enqueue()
   enum Src { SRC_PACKED = 0, SRC_CHW = 1, SRC_HWC = 2 };

@@ -130,6 +130,19 @@ class DlTFNetworkEvaluator:
         if self._lib.ug_eval_set_conv_ctas(self._h, ctas) != 0:
             raise ValueError("ctas must be 1 or 2")
 
+    def register_host(self, *arrays):
+        """page-lock caller arrays that Evaluate() will be called with (see ug_eval_register_host); returns the
+        number accepted.  The arrays must outlive the evaluator or be passed to unregister_host() first."""
+        ok = 0
+        for a in arrays:
+            if self._lib.ug_eval_register_host(self._h, a.ctypes.data, a.nbytes) == 0:
+                ok += 1
+        return ok
+
+    def unregister_host(self, *arrays):
+        for a in arrays:
+            self._lib.ug_eval_unregister_host(self._h, a.ctypes.data)
+
     def set_conv_impl(self, impl):
         if self._lib.ug_eval_set_conv_impl(self._h, impl) != 0:
             raise ValueError("impl must be 1 or 2")
