@@ -219,6 +219,22 @@ void ug_board_pack(void* b, ug_packed_pos* out);
 int ug_board_generate(void* b, uint16_t* moves, uint32_t* legal);
 int ug_board_to_play(void* b);
 
+/* ------------------------------------------------------------------ self-play records (DlTFRecordWriter) */
+/* DlTFRecordWriter(filename), funcapproximator/DlTFRecordWriter.cc:18-22: TFRecord file of tf.train.Example
+ * messages, uncompressed.  NULL if the file cannot be created. */
+typedef struct ug_tfrecord ug_tfrecord;
+ug_tfrecord* ug_tfrecord_open(const char* path);
+/* WriteExample(feature17, f_len, policy, p_size, reward), .cc:59-76: keys "feature" (bytes), "policy" (floats),
+ * "reward" (1 float). */
+int ug_tfrecord_write_example(ug_tfrecord* w, const void* feature17, size_t f_len, const float* policy,
+                              size_t p_size, float reward);
+/* WriteExample with caller-chosen keys, .cc:78-100 */
+int ug_tfrecord_write_example_named(ug_tfrecord* w, const char* feature_name, const void* feature, size_t f_len,
+                                    const char* policy_name, const float* policy, size_t p_size,
+                                    const char* reward_name, float reward);
+int ug_tfrecord_flush(ug_tfrecord* w);      /* Flush(), .cc:34-37 */
+int64_t ug_tfrecord_close(ug_tfrecord* w);  /* ~DlTFRecordWriter, .cc:24-32; returns the number of records written */
+
 /* ------------------------------------------------------------------ dlcfg (DlConfig) */
 /* DlConfig(filename) + parse(), funcapproximator/DlConfig.cc:20-41. A missing file yields an empty map. */
 ug_dlcfg* ug_dlcfg_open(const char* path);

@@ -55,3 +55,61 @@ def test_flagship_batch256_parity_and_properties(flagship):
     print(f"flagship bf16 mode: max|dpolicy|={dpb:.3e} max|dvalue|={dvb:.3e} mean|dpolicy|={np.abs(pb - want_p).mean():.3e}")
     assert dpb <= 1e-2 and dvb <= 6e-2 and np.abs(pb - want_p).mean() <= 1e-5
     evb.close()
+
+
+@pytest.fixture(scope="module")
+def agz40(tmp_path_factory):
+    """BASELINE.json configs[4]: 40 blocks x 256 filters, random-init weights"""
+    from unrealgo_b200 import tfformat
+    return tfformat.write_synthetic_checkpoint(str(tmp_path_factory.mktemp("agz40")), 40, 256, seed=40)
+
+
+def test_config5_40x256_batch512(agz40):
+    """40x256 at batch 512 (two full 256-position groups, 10 waves of the tower kernel): size-independent
+    properties on the whole batch, oracle parity on a subset the CPU restatement finishes in seconds."""
+    import oracle
+    from oracle.net_oracle import GraphOracle
+    from unrealgo_b200 import DlTFNetworkEvaluator
+    packed, planes = oracle.synthetic_positions(512, seed=512)
+    ev = DlTFNetworkEvaluator(agz40[0], max_batch=512)
+    assert ev.UpdateCheckPoint(agz40[1])
+    info = ev.info()
+    assert (info["blocks"], info["filters"]) == (40, 256)
+    assert info["flops_per_position"] == 34097776104.0  # SURVEY.md 8(d)
+    p, v = ev.evaluate_packed(packed)
+    assert p.shape == (512, 362) and np.isfinite(p).all() and np.isfinite(v).all()
+    assert np.abs(p.sum(axis=1) - 1).max() <= 1e-5 and (p >= 0).all() and np.abs(v).max() <= 1.0
+    # a position's result does not depend on the batch it rode in (512 vs 37 vs 1, tail tiles included)
+    for lo, hi in [(0, 37), (300, 301), (475, 512)]:
+        ps, vs = ev.evaluate_packed(packed[lo:hi])
+        assert np.array_equal(ps, p[lo:hi]) and np.array_equal(vs, v[lo:hi])
+    # the reference-facing entry agrees with the packed entry on the same positions
+    pol = np.zeros((512, 362))
+    val = np.zeros(512)
+    assert ev.Evaluate(planes, pol, val, 512)
+    assert np.array_equal(pol.astype(np.float32), p) and np.array_equal(val.astype(np.float32), v)
+    sub = np.arange(0, 512, 16)  # 32 positions through the fp32 oracle
+    want_p, want_v = GraphOracle(*agz40).evaluate_reference(planes[sub])
+    dp, dv = np.abs(p[sub] - want_p).max(), np.abs(v[sub] - want_v).max()
+    print(f"40x256 batch 512 (fp16): max|dpolicy|={dp:.3e} max|dvalue|={dv:.3e}")
+    assert dp <= 2e-3 and dv <= 1e-2  # twice the 20-block budget: twice the depth
+    ev.close()
+
+
+def test_every_gpu_gives_the_single_gpu_result(flagship):
+    """weights are replicated per GPU and games never interact, so any device must return
+    bit-identical results for the same positions."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import oracle
+    from unrealgo_b200 import DlTFNetworkEvaluator
+    packed, _ = oracle.synthetic_positions(64, seed=77)
+    outs = []
+    for dev in range(min(torch.cuda.device_count(), 8)):
+        ev = DlTFNetworkEvaluator(flagship[0], device=dev, max_batch=64)
+        assert ev.UpdateCheckPoint(flagship[1])
+        outs.append(ev.evaluate_packed(packed))
+        ev.close()
+    for p, v in outs[1:]:
+        assert np.array_equal(p, outs[0][0]) and np.array_equal(v, outs[0][1])

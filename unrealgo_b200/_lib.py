@@ -105,6 +105,12 @@ SIGNATURES = {
     "ug_board_to_play": (C.c_int, [C.c_void_p]),
     "ug_queue_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ug_queue_swap_checkpoint": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "ug_tfrecord_open": (C.c_void_p, [C.c_char_p]),
+    "ug_tfrecord_write_example": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_float]),
+    "ug_tfrecord_write_example_named": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_void_p,
+                                                  C.c_size_t, C.c_char_p, C.c_float]),
+    "ug_tfrecord_flush": (C.c_int, [C.c_void_p]),
+    "ug_tfrecord_close": (C.c_int64, [C.c_void_p]),
     "ug_dlcfg_open": (C.c_void_p, [C.c_char_p]),
     "ug_dlcfg_close": (None, [C.c_void_p]),
     "ug_dlcfg_get": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),

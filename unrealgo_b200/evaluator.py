@@ -236,6 +236,44 @@ class DlTFNetworkEvaluator:
         return {f: getattr(res, f) for f, _ in _lib.BenchResult._fields_}
 
 
+class DlTFRecordWriter:
+    """tensorflow::io::DlTFRecordWriter (funcapproximator/DlTFRecordWriter.cc): self-play examples as a TFRecord file
+    of tf.train.Example messages, written by libugeval without TensorFlow."""
+
+    def __init__(self, filename):
+        self._lib = _lib.load()
+        self._w = self._lib.ug_tfrecord_open(filename.encode())
+        if not self._w:
+            raise OSError(f"cannot create {filename}")
+
+    def WriteExample(self, feature17, policy, reward, names=None):
+        """feature17: int8/uint8 array (6137 plane bytes in the reference); policy: float32 array; reward: float"""
+        f = np.ascontiguousarray(feature17).view(np.uint8).reshape(-1)
+        p = np.ascontiguousarray(policy, np.float32).reshape(-1)
+        if names is None:
+            rc = self._lib.ug_tfrecord_write_example(self._w, f.ctypes.data, f.size, p.ctypes.data, p.size, float(reward))
+        else:
+            fn, pn, rn = (n.encode() for n in names)
+            rc = self._lib.ug_tfrecord_write_example_named(self._w, fn, f.ctypes.data, f.size, pn, p.ctypes.data, p.size,
+                                                           rn, float(reward))
+        if rc != 0:
+            raise OSError("TFRecord write failed")
+        return 0
+
+    def Flush(self):
+        self._lib.ug_tfrecord_flush(self._w)
+
+    def close(self):
+        """returns the number of records written"""
+        n = -1
+        if getattr(self, "_w", None):
+            n = self._lib.ug_tfrecord_close(self._w)
+            self._w = None
+        return n
+
+    __del__ = close
+
+
 class UctBoardEvaluator:
     """search/UctBoardEvaluator.cpp:6-33 — config -> evaluator wiring + forwarding."""
 
