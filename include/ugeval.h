@@ -201,6 +201,14 @@ typedef struct ug_selfplay_config {
   int random_opening_moves;/* harness option: first k moves uniformly random (0 = reference behaviour) */
   float puct;              /* 0 = 2.5 (search/UctSearch.cpp:370) */
   uint64_t seed;
+  /* UctDeepPlayer::WriteTFRecord (search/UctDeepPlayer.cpp:362-388): when record_dir is non-NULL every finished game
+   * is written to <record_dir>/selfplay_<game_index_base + game>.tfrecord — walking back from the last non-pass
+   * move: the 6137 plane bytes of the position after the move, the root visit counts of the search that chose it
+   * (UctSearch::DeepUCTSelectBestChild, search/UctSearch.cpp:782-801: raw counts), and +-1 from the point of view of
+   * the player who made the move, by Tromp-Taylor score (GoBoardUtil::TrompTaylorScore, go/GoBoardUtil.h:626-680). */
+  const char* record_dir;
+  float komi;              /* 0 = 7.5 (DEFAULT_KOMI, go/GoRules.h:9) */
+  int game_index_base;     /* global index of this evaluator's first game (rank * games when sharded) */
 } ug_selfplay_config;
 typedef struct ug_selfplay_stats {
   uint64_t playouts, evaluations, batches, flush_timeouts, moves, games_finished, terminal_leaves;
@@ -218,6 +226,8 @@ void ug_board_play(void* b, int idx);
 void ug_board_pack(void* b, ug_packed_pos* out);
 int ug_board_generate(void* b, uint16_t* moves, uint32_t* legal);
 int ug_board_to_play(void* b);
+float ug_board_score(void* b, float komi);     /* Tromp-Taylor score used for the recorded reward (go/GoBoardUtil.h:626-680) */
+void ug_board_planes(void* b, int8_t* chw_out); /* host CollectFeatures of the current position: char[17][19][19] */
 
 /* ------------------------------------------------------------------ self-play records (DlTFRecordWriter) */
 /* DlTFRecordWriter(filename), funcapproximator/DlTFRecordWriter.cc:18-22: TFRecord file of tf.train.Example

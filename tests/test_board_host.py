@@ -61,3 +61,42 @@ def test_two_passes_end_move_generation():
     assert len(pb.generate()[0]) == 362 - 0  # empty board: every point + pass
     pb.play(361)
     assert len(pb.generate()[0]) == 0
+
+
+def _tromp_taylor(colors, komi):
+    """independent restatement of GoBoardUtil::TrompTaylorScore (go/GoBoardUtil.h:626-680) on a 19x19 colour array"""
+    c = colors.reshape(19, 19)
+    score = -komi + float((c == 0).sum()) - float((c == 1).sum())
+    seen = np.zeros((19, 19), bool)
+    for y in range(19):
+        for x in range(19):
+            if c[y, x] != 2 or seen[y, x]:
+                continue
+            stack, size, adj = [(y, x)], 0, set()
+            seen[y, x] = True
+            while stack:
+                yy, xx = stack.pop()
+                size += 1
+                for ny, nx in ((yy - 1, xx), (yy + 1, xx), (yy, xx - 1), (yy, xx + 1)):
+                    if 0 <= ny < 19 and 0 <= nx < 19:
+                        if c[ny, nx] == 2:
+                            if not seen[ny, nx]:
+                                seen[ny, nx] = True
+                                stack.append((ny, nx))
+                        else:
+                            adj.add(int(c[ny, nx]))
+            if adj == {0}:
+                score += size
+            elif adj == {1}:
+                score -= size
+    return score
+
+
+def test_score_and_host_planes_match_the_oracle():
+    assert ProductBoard().score(7.5) == -7.5  # empty board: one region touching neither colour
+    for seed, length, pp in [(21, 30, 0.0), (22, 250, 0.02), (23, 500, 0.01), (24, 5, 0.4)]:
+        ob, pb = _random_game(seed, length, pp)
+        assert pb.score(7.5) == _tromp_taylor(ob.colors(), 7.5)
+        assert pb.score(0.5) == _tromp_taylor(ob.colors(), 0.5)
+        # the planes written to self-play records == CollectFeatures' undo/replay walk
+        assert np.array_equal(pb.planes(), ob.collect_features())

@@ -128,3 +128,50 @@ def test_selfplay_moves_are_legal_and_follow_visit_counts(small_ckpt):
             assert b.is_legal(mv), (g, mv)   # legality judged by the oracle's board, not the driver's
             b.play(mv)
     ev.close()
+
+
+def test_selfplay_records_follow_write_tfrecord(small_ckpt, tmp_path):
+    """Recorded games (UctDeepPlayer::WriteTFRecord, search/UctDeepPlayer.cpp:362-388): one example per move up to
+    the last non-pass move, newest first; planes = CollectFeatures of the position after the move (oracle board),
+    policy = root visit counts of the search that chose it, reward = +-1 alternating, sign from Tromp-Taylor."""
+    import oracle
+    from tests.test_board_host import _tromp_taylor
+    from tests.test_tfrecord import _example_class, read_records
+    from unrealgo_b200 import selfplay
+    Example = _example_class()
+    ev = _ev(small_ckpt, max_batch=64)
+    playouts = 20
+    st, games = selfplay(ev, games=5, threads=2, playouts_per_move=playouts, max_moves=17, random_opening_moves=2,
+                         seed=11, record_moves=True, max_batch=64, reuse_tree=False, record_dir=str(tmp_path),
+                         game_index_base=40)
+    ev.close()
+    assert st["games_finished"] == 5
+    for gi, moves in enumerate(games):
+        recs = read_records(str(tmp_path / f"selfplay_{40 + gi}.tfrecord"))
+        last = len(moves) - 1
+        while last >= 0 and moves[last] == 361:
+            last -= 1
+        assert len(recs) == last + 1
+        b = oracle.Board()
+        planes_after, colors_after = [], None
+        for mv in moves[:last + 1]:
+            b.play(mv)
+            planes_after.append(b.collect_features())
+        colors_after = b.colors()
+        score = _tromp_taylor(colors_after, 7.5)
+        mover_is_black = last % 2 == 0
+        reward = 1.0 if (score > 0) == mover_is_black else -1.0
+        for k, data in enumerate(recs):           # record k describes move index last - k
+            i = last - k
+            ex = Example()
+            ex.ParseFromString(data)
+            f = ex.features.feature
+            got = np.frombuffer(f["feature"].bytes_list.value[0], np.int8).reshape(17, 19, 19)
+            assert np.array_equal(got, planes_after[i]), (gi, i)
+            pol = np.array(f["policy"].float_list.value, np.float32)
+            assert pol.shape == (362,) and (pol >= 0).all() and np.all(pol == np.round(pol))   # raw visit counts
+            # without tree reuse the root children share exactly playouts - 1 visits (the first playout expands the root)
+            assert pol.sum() == playouts - 1
+            if i >= 2:  # after the random opening the move played is the most visited child (first wins ties)
+                assert pol[moves[i]] == pol.max()
+            assert list(f["reward"].float_list.value) == [reward if k % 2 == 0 else -reward]

@@ -40,7 +40,8 @@ class NetInfo(C.Structure):
 class SelfplayConfig(C.Structure):
     _fields_ = [("games", C.c_int), ("threads", C.c_int), ("playouts_per_move", C.c_int), ("max_moves", C.c_int),
                 ("max_batch", C.c_int), ("timeout_us", C.c_int), ("reuse_tree", C.c_int),
-                ("random_opening_moves", C.c_int), ("puct", C.c_float), ("seed", C.c_uint64)]
+                ("random_opening_moves", C.c_int), ("puct", C.c_float), ("seed", C.c_uint64),
+                ("record_dir", C.c_char_p), ("komi", C.c_float), ("game_index_base", C.c_int)]
 
 
 class SelfplayStats(C.Structure):
@@ -103,6 +104,8 @@ SIGNATURES = {
     "ug_board_pack": (None, [C.c_void_p, C.c_void_p]),
     "ug_board_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ug_board_to_play": (C.c_int, [C.c_void_p]),
+    "ug_board_score": (C.c_float, [C.c_void_p, C.c_float]),
+    "ug_board_planes": (None, [C.c_void_p, C.c_void_p]),
     "ug_queue_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ug_queue_swap_checkpoint": (C.c_int, [C.c_void_p, C.c_char_p]),
     "ug_tfrecord_open": (C.c_void_p, [C.c_char_p]),

@@ -207,6 +207,37 @@ struct Board {
     out->reserved[0] = out->reserved[1] = out->reserved[2] = 0;
   }
 
+  // GoBoardUtil::TrompTaylorScore(bd, komi), go/GoBoardUtil.h:626-680: stones plus empty regions that touch one
+  // colour only, minus komi; positive = Black ahead.
+  float tromp_taylor(float komi) const {
+    float score = -komi;
+    bool mark[NB] = {false};
+    int stack[NB];
+    for (int b = 0; b < NB; ++b) {
+      if (mark[b] || color[b] == BORDER) continue;
+      if (color[b] == BLACK) { score += 1.f; continue; }
+      if (color[b] == WHITE) { score -= 1.f; continue; }
+      int sp = 0, size = 0;
+      bool adj[2] = {false, false};
+      stack[sp++] = b;
+      mark[b] = true;
+      while (sp > 0) {
+        const int p = stack[--sp];
+        ++size;
+        int nb[4];
+        nbrs(p, nb);
+        for (int i = 0; i < 4; ++i) {
+          const uint8_t c = color[nb[i]];
+          if (c == BLACK || c == WHITE) adj[c] = true;
+          else if (c == EMPTY && !mark[nb[i]]) { mark[nb[i]] = true; stack[sp++] = nb[i]; }
+        }
+      }
+      if (adj[BLACK] && !adj[WHITE]) score += (float)size;
+      else if (!adj[BLACK] && adj[WHITE]) score -= (float)size;
+    }
+    return score;
+  }
+
   // GenerateLegalMoves: returns the count; moves[] are policy indices (PASS last); legal_mask gets one bit per move.
   // No moves at all after two consecutive passes (gouct/GoUctGlobalSearch.h:311-314).
   int generate_moves(uint16_t* moves, uint32_t* legal_mask) const {

@@ -46,6 +46,8 @@ struct Game {
   int playouts_this_move = 0;
   bool finished = false;
   std::vector<int16_t> moves;
+  std::vector<float> visit_policy;  // [moves][362] root visit counts per move (only when records are written)
+  int index = 0;                    // game number on this evaluator
   std::mt19937_64 rng;
   float policy[UG_NUM_MOVES];
 };
@@ -54,8 +56,54 @@ struct Shared {
   ug_queue* q;
   ug_selfplay_config cfg;
   std::atomic<uint64_t> playouts{0}, moves{0}, games_done{0}, nodes{0}, terminal_leaves{0};
+  std::atomic<uint64_t> record_errors{0};
   std::atomic<bool> stop{false};
 };
+
+// CollectFeatures (gouct/GoUctGlobalSearch.h:160-206) from a packed position: plane 2k / 2k+1 = stones of the
+// side to move / the opponent k moves ago, plane 16 = 1 - to_play
+void planes_from_packed(const ug_packed_pos& p, int8_t* out) {
+  const uint32_t tp = p.to_play & 1u;
+  for (int k = 0; k < UG_HISTORY; ++k) {
+    const uint32_t* mine = tp == 0 ? p.black[k] : p.white[k];
+    const uint32_t* theirs = tp == 0 ? p.white[k] : p.black[k];
+    for (int i = 0; i < UG_NUM_POINTS; ++i) {
+      out[(2 * k) * UG_NUM_POINTS + i] = (int8_t)((mine[i >> 5] >> (i & 31)) & 1u);
+      out[(2 * k + 1) * UG_NUM_POINTS + i] = (int8_t)((theirs[i >> 5] >> (i & 31)) & 1u);
+    }
+  }
+  memset(out + 16 * UG_NUM_POINTS, tp == 0 ? 1 : 0, UG_NUM_POINTS);
+}
+
+// UctDeepPlayer::WriteTFRecord, search/UctDeepPlayer.cpp:362-388 (see ug_selfplay_config.record_dir)
+bool write_game_record(const Game& g, const ug_selfplay_config& cfg) {
+  const int n = (int)g.moves.size();
+  int last = n - 1;
+  while (last >= 0 && g.moves[(size_t)last] == ugo::PASS) --last;  // trailing passes are taken back first (:371-374)
+  char path[4096];
+  snprintf(path, sizeof(path), "%s/selfplay_%d.tfrecord", cfg.record_dir, cfg.game_index_base + g.index);
+  ug_tfrecord* w = ug_tfrecord_open(path);
+  if (!w) return false;
+  std::vector<ug_packed_pos> after((size_t)(last + 1));
+  ugo::Board b;
+  for (int i = 0; i <= last; ++i) {
+    b.play(g.moves[(size_t)i]);
+    b.pack(&after[(size_t)i]);
+  }
+  const float score = b.tromp_taylor(cfg.komi > 0 ? cfg.komi : 7.5f);
+  const int colour = (last % 2 == 0) ? ugo::BLACK : ugo::WHITE;  // Black moves first
+  const bool win = (score > 0 && colour == ugo::BLACK) || (score < 0 && colour == ugo::WHITE);
+  float reward = win ? 1.f : -1.f;
+  int8_t planes[UG_NUM_PLANES * UG_NUM_POINTS];
+  bool ok = true;
+  for (int i = last; i >= 0 && ok; --i) {
+    planes_from_packed(after[(size_t)i], planes);
+    ok = ug_tfrecord_write_example(w, planes, sizeof(planes), &g.visit_policy[(size_t)i * UG_NUM_MOVES],
+                                   UG_NUM_MOVES, reward) == 0;
+    reward = -reward;
+  }
+  return ug_tfrecord_close(w) >= 0 && ok;
+}
 
 inline float mean_value(const Node& n) { return n.visits ? n.w / (float)n.visits : 0.f; }
 
@@ -183,6 +231,15 @@ void make_move(Game& g, Shared& sh) {
     }
     move = g.tree[chosen].move;
   }
+  if (sh.cfg.record_dir) {
+    // the policy block of the move: zero, then the visit count of every root child (search/UctSearch.cpp:782-801)
+    const size_t at = g.visit_policy.size();
+    g.visit_policy.resize(at + UG_NUM_MOVES, 0.f);
+    for (uint32_t i = 0; i < r.n_children; ++i) {
+      const Node& c = g.tree[r.first_child + i];
+      g.visit_policy[at + c.move] = (float)c.visits;
+    }
+  }
   g.root_board.play(move);
   g.moves.push_back((int16_t)move);
   sh.moves.fetch_add(1, std::memory_order_relaxed);
@@ -194,6 +251,7 @@ void make_move(Game& g, Shared& sh) {
   if (g.root_board.passes >= 2 || g.root_board.move_number >= limit) {
     g.finished = true;
     sh.games_done.fetch_add(1, std::memory_order_relaxed);
+    if (sh.cfg.record_dir && !write_game_record(g, sh.cfg)) sh.record_errors.fetch_add(1, std::memory_order_relaxed);
   }
 }
 
@@ -255,6 +313,7 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
   std::vector<Game> games((size_t)cfg.games);
   for (int i = 0; i < cfg.games; ++i) {
     games[i].rng.seed(cfg.seed * 1000003ull + (uint64_t)i);
+    games[i].index = i;
     new_root(games[i]);
   }
   const auto t0 = std::chrono::steady_clock::now();
@@ -314,6 +373,7 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
       memcpy(moves_out + (size_t)i * cap, games[i].moves.data(), (size_t)n * sizeof(int16_t));
     }
   }
+  if (sh.record_errors.load()) return -4;  // a record file could not be written
   return sh.stop.load() ? -3 : 0;
 }
 
@@ -331,4 +391,10 @@ int ug_board_generate(void* b, uint16_t* moves, uint32_t* legal) {
   return static_cast<ugo::Board*>(b)->generate_moves(moves, legal);
 }
 int ug_board_to_play(void* b) { return static_cast<ugo::Board*>(b)->to_play; }
+float ug_board_score(void* b, float komi) { return static_cast<ugo::Board*>(b)->tromp_taylor(komi); }
+void ug_board_planes(void* b, int8_t* chw_out) {
+  ug_packed_pos p;
+  static_cast<ugo::Board*>(b)->pack(&p);
+  planes_from_packed(p, chw_out);
+}
 }
