@@ -41,8 +41,7 @@ constexpr int kHalo = kBoard + 1;           // 20
 constexpr int kARows = kTileM + 2 * kHalo;  // 168
 constexpr int kAccCols = 256;
 constexpr int kNA = 3;   // A chunk slots
-constexpr int kNB = 6;   // B stages
-constexpr int kNR = 2;   // residual slots (32 columns each, hi + lo)
+constexpr int kNR = 2;   // residual slots (32 columns each, hi + lo), only in kernels that read a residual
 constexpr int kNO = 2;   // per-warp output staging slots
 constexpr int kEpiCols = 32;
 constexpr int kResHalf = kTileM * kEpiCols * 2;   // 8192: 128 rows x 64 B
@@ -50,19 +49,23 @@ constexpr int kResSlot = 2 * kResHalf;            // hi + lo
 constexpr int kOutHalf = 32 * kEpiCols * 2;       // 2048: 32 rows x 64 B (one warp)
 constexpr int kOutSlot = 2 * kOutHalf;            // hi + lo
 
-template <int CK>
+// Shared-memory plan.  Kernels without a residual input spend the residual ring's 32 KB on two more weight stages.
+template <int CK, bool HAS_RES>
 struct Cfg {
+  static constexpr int kNB = HAS_RES ? 6 : 8;       // B stages
+  static constexpr int kNRes = HAS_RES ? kNR : 0;   // residual slots
   static constexpr int kRowBytes = CK * 2;
   static constexpr int kASlot = kARows * kRowBytes;   // 21504 (CK=64) / 10752 (CK=32)
   static constexpr int kBStage = kTileM * kRowBytes;  // up to 128 weight rows per CTA
   static constexpr int kOffB = kNA * kASlot;
   static constexpr int kOffRes = kOffB + kNB * kBStage;
-  static constexpr int kOffOut = kOffRes + kNR * kResSlot;
+  static constexpr int kOffOut = kOffRes + kNRes * kResSlot;
   static constexpr int kOffBias = kOffOut + 4 * kNO * kOutSlot;
   static constexpr int kOffBars = kOffBias + 256 * 4;
-  static constexpr int kNumBars = 2 * kNA + 2 * kNB + 2 * kNR + 2 + 2;
+  static constexpr int kNumBars = 2 * kNA + 2 * kNB + 2 * kNR + 2 + 2;  // (residual barriers exist in every variant)
   static constexpr int kBytes = kOffBars + kNumBars * 8 + 16;
   static constexpr int kSmem = kBytes + 1024;  // alignment slack
+  static_assert(kSmem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
 };
 
 // Disable-output-lane words: c_edge_mask[tap][q] bit i is set when pixel (q + i) mod 361 of an image has no
@@ -101,7 +104,8 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const __grid_constant__ CUtensorMap tmRhi, const __grid_constant__ CUtensorMap tmRlo,
                   const __grid_constant__ CUtensorMap tmOhi, const __grid_constant__ CUtensorMap tmOlo,
                   const ConvV2Args args) {
-  using C = Cfg<CK>;
+  using C = Cfg<CK, (RES > 0)>;
+  constexpr int kNB = C::kNB;
   constexpr int kRowBytes = C::kRowBytes;
   constexpr int kMmaPerStep = CK / 16;
 
@@ -465,7 +469,7 @@ bool upload_masks(int device) {
 template <int CK, bool F16, int RES, bool OUT_LO, int HEADS = 0>
 cudaError_t launch_v2(const ConvV2Maps& m, const ConvV2Args& a, int sms, cudaStream_t stream) {
   auto kfn = conv3x3_v2_kernel<CK, F16, RES, OUT_LO, HEADS>;
-  constexpr int smem = Cfg<CK>::kSmem;
+  constexpr int smem = Cfg<CK, (RES > 0)>::kSmem;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -520,7 +524,7 @@ bool conv3x3_v2_can_fuse_heads(int ck, int has_res, int has_res_lo, int has_out_
   return (has_res_lo && has_out_lo) || (!has_res_lo && !has_out_lo);
 }
 
-int conv3x3_v2_smem_bytes(int ck) { return ck == 64 ? Cfg<64>::kSmem : Cfg<32>::kSmem; }
+int conv3x3_v2_smem_bytes(int ck) { return ck == 64 ? Cfg<64, true>::kSmem : Cfg<32, true>::kSmem; }
 
 cudaError_t conv3x3_v2_launch(const ConvV2Maps& maps, ConvV2Args a, int ck, int device, int sms,
                               cudaStream_t stream) {

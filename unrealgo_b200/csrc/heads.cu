@@ -143,7 +143,9 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* scrat
 }
 
 // acc[p] += sum_i f[p][i] * w[i*stride]  for kPosPerCta positions; weights stream from L2 (coalesced across the
-// threads of a warp: consecutive threads own consecutive columns), kFcUnroll loads issued before their FMAs
+// threads of a warp: consecutive threads own consecutive columns), kFcUnroll loads issued before their FMAs.
+// The features are read from shared memory four at a time (one 16-byte broadcast load per position and group):
+// f and fstride must be multiples of 4 floats.
 __device__ __forceinline__ void fc_column(const float* __restrict__ wcol, int stride, const float* f, int fstride,
                                           int len, float (&acc)[kPosPerCta]) {
   int i = 0;
@@ -152,9 +154,15 @@ __device__ __forceinline__ void fc_column(const float* __restrict__ wcol, int st
 #pragma unroll
     for (int u = 0; u < kFcUnroll; ++u) wv[u] = __ldg(wcol + (size_t)(i + u) * stride);
 #pragma unroll
-    for (int u = 0; u < kFcUnroll; ++u)
+    for (int g = 0; g < kFcUnroll / 4; ++g)
 #pragma unroll
-      for (int p = 0; p < kPosPerCta; ++p) acc[p] = fmaf(f[p * fstride + i + u], wv[u], acc[p]);
+      for (int p = 0; p < kPosPerCta; ++p) {
+        const float4 x = *reinterpret_cast<const float4*>(f + p * fstride + i + 4 * g);
+        acc[p] = fmaf(x.x, wv[4 * g], acc[p]);
+        acc[p] = fmaf(x.y, wv[4 * g + 1], acc[p]);
+        acc[p] = fmaf(x.z, wv[4 * g + 2], acc[p]);
+        acc[p] = fmaf(x.w, wv[4 * g + 3], acc[p]);
+      }
   }
   for (; i < len; ++i) {
     const float wv = __ldg(wcol + (size_t)i * stride);
@@ -174,9 +182,10 @@ __global__ void __launch_bounds__(kFcThreads) head_fc_kernel(const float* __rest
   extern __shared__ float sm[];
   const int pc = hw.pc, vc = hw.vc, hc = pc + vc, H = hw.H;
   const int pin = kPoints * pc, vin = kPoints * vc;
-  float* fp = sm;                          // [kPosPerCta][pin]
-  float* fv = fp + kPosPerCta * pin;       // [kPosPerCta][vin]
-  float* hid = fv + kPosPerCta * vin;      // [kPosPerCta][H]
+  const int pstr = (pin + 3) & ~3, vstr = (vin + 3) & ~3;  // row strides padded for 16-byte reads
+  float* fp = sm;                          // [kPosPerCta][pstr]
+  float* fv = fp + kPosPerCta * pstr;      // [kPosPerCta][vstr]
+  float* hid = fv + kPosPerCta * vstr;     // [kPosPerCta][H]
   float* scratch = hid + kPosPerCta * H;   // [32]
   float* part = scratch + 32;              // [kPosPerCta][kPolThreads] partial logits of the second K half
   const int p0 = blockIdx.x * kPosPerCta;
@@ -187,8 +196,8 @@ __global__ void __launch_bounds__(kFcThreads) head_fc_kernel(const float* __rest
     const int r = i - p * (kPoints * hc);
     const int point = r / hc, c = r - point * hc;
     const float v = (p < np) ? __ldg(feat + (size_t)(p0 + p) * kPoints * hc + r) : 0.f;
-    if (c < pc) fp[p * pin + point * pc + c] = v;
-    else fv[p * vin + point * vc + (c - pc)] = v;
+    if (c < pc) fp[p * pstr + point * pc + c] = v;
+    else fv[p * vstr + point * vc + (c - pc)] = v;
   }
   __syncthreads();
 
@@ -201,9 +210,10 @@ __global__ void __launch_bounds__(kFcThreads) head_fc_kernel(const float* __rest
   if (tid < kPolSplit * kPolThreads) {
     // ---- policy: logits[j] = b[j] + sum_i f[i] * W[i][j]; group 0 sums i in [0, pin/2), group 1 the rest
     if (j < kMoves) {
-      const int k0 = khalf == 0 ? 0 : pin / 2;
-      const int k1 = khalf == 0 ? pin / 2 : pin;
-      fc_column(hw.pfc_w + (size_t)k0 * kMoves + j, kMoves, fp + k0, pin, k1 - k0, logit);
+      const int mid = (pin / 2) & ~3;  // multiple of 4: both halves start 16-byte aligned
+      const int k0 = khalf == 0 ? 0 : mid;
+      const int k1 = khalf == 0 ? mid : pin;
+      fc_column(hw.pfc_w + (size_t)k0 * kMoves + j, kMoves, fp + k0, pstr, k1 - k0, logit);
       if (khalf == 1) {
 #pragma unroll
         for (int p = 0; p < kPosPerCta; ++p) part[p * kPolThreads + j] = logit[p];
@@ -215,7 +225,7 @@ __global__ void __launch_bounds__(kFcThreads) head_fc_kernel(const float* __rest
       float acc[kPosPerCta];
 #pragma unroll
       for (int p = 0; p < kPosPerCta; ++p) acc[p] = 0.f;
-      fc_column(hw.v1_w + h, H, fv, vin, vin, acc);
+      fc_column(hw.v1_w + h, H, fv, vstr, vin, acc);
       const float b1 = __ldg(hw.v1_b + h);
 #pragma unroll
       for (int p = 0; p < kPosPerCta; ++p) hid[p * H + h] = fmaxf(acc[p] + b1, 0.f);
@@ -298,7 +308,7 @@ void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* leg
                     float* value, int n, cudaStream_t s) {
   if (n <= 0) return;
   const size_t smem =
-      sizeof(float) * ((size_t)kPosPerCta * (kPoints * (w.pc + w.vc) + w.H + kPolThreads) + 32);
+      sizeof(float) * ((size_t)kPosPerCta * (((kPoints * w.pc + 3) & ~3) + ((kPoints * w.vc + 3) & ~3) + w.H + kPolThreads) + 32);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaFuncSetAttribute(head_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
