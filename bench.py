@@ -145,17 +145,36 @@ def main_reference(args):
     cb = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
           "sample": f"{done} positions, batch {batch}, {args.blocks}x{args.filters}, fp32 torch-CPU restatement "
                     f"(TensorFlow and the bootstrap checkpoint are unavailable offline)"}
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+    emit({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * el / args.steps,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                       "data": "synthetic",
                       "config": {"workload": f"{args.blocks}x{args.filters} dlcfg-19 net, batch {batch} on host cores"},
                       "cpu_baseline": cb,
-                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line of the contract, on the process's real stdout"""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # Libraries print on stdout behind our back (NCCL writes its version line there): park the real stdout and
+    # route everything else to stderr, so that stdout carries exactly the JSON line.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return main_reference(args)
     import numpy as np
@@ -336,7 +355,7 @@ def main():
             except Exception as e:  # the baseline is reported beside the result, never part of it
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                        "sample": f"failed: {e!r}"}
-        print(json.dumps(out))
+        emit(out)
     ev.close()
     if world > 1:
         dist.destroy_process_group()

@@ -21,6 +21,8 @@
 // half of the B tile, which halves per-SM weight traffic).
 #include <cuda_bf16.h>
 
+#include <atomic>
+
 #include "conv3x3_tc.h"
 #include "numfmt.cuh"
 #include "ptx.cuh"
@@ -264,11 +266,14 @@ static cudaError_t launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB
                                   cudaStream_t stream) {
   auto kfn = conv3x3_tc_kernel<CK, CTAS>;
   constexpr int smem = conv_smem_bytes<CK, CTAS>();
-  static bool attr_done = false;  // per variant
-  if (!attr_done) {
+  // function attributes are per device: remember which devices this instantiation has been prepared on
+  static std::atomic<uint64_t> attr_done{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
   int clusters = sms / CTAS;
   if (clusters > a.num_tiles) clusters = a.num_tiles;

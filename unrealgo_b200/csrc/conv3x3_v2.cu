@@ -23,6 +23,8 @@
 // 2 = TMEM allocator + MMA issuer (leader CTA, one lane), 3 = residual producer, 4-7 = epilogue.
 #include <cuda_bf16.h>
 
+#include <atomic>
+
 #include <mutex>
 #include <vector>
 
@@ -470,11 +472,14 @@ template <int CK, bool F16, int RES, bool OUT_LO, int HEADS = 0>
 cudaError_t launch_v2(const ConvV2Maps& m, const ConvV2Args& a, int sms, cudaStream_t stream) {
   auto kfn = conv3x3_v2_kernel<CK, F16, RES, OUT_LO, HEADS>;
   constexpr int smem = Cfg<CK, (RES > 0)>::kSmem;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  // function attributes are per device: remember which devices this instantiation has been prepared on
+  static std::atomic<uint64_t> attr_done{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
   int clusters = sms / 2;
   if (clusters > a.num_tiles) clusters = a.num_tiles;

@@ -309,10 +309,13 @@ void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* leg
   if (n <= 0) return;
   const size_t smem =
       sizeof(float) * ((size_t)kPosPerCta * (((kPoints * w.pc + 3) & ~3) + ((kPoints * w.vc + 3) & ~3) + w.H + kPolThreads) + 32);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  static size_t smem_set[64] = {};  // per device (function attributes are per device)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t& set = smem_set[dev & 63];
+  if (smem > 48 * 1024 && smem > set) {
     cudaFuncSetAttribute(head_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smem_set = smem;
+    set = smem;
   }
   const int grid = (n + kPosPerCta - 1) / kPosPerCta;
   head_fc_kernel<<<grid, kFcThreads, smem, s>>>(feat, w, legal, vt, policy, value, n);
