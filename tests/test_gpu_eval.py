@@ -233,3 +233,21 @@ def test_registered_host_buffers_give_identical_results(small_ckpt):
     assert np.array_equal(p0, p2) and np.array_equal(v0, v2)
     ev.unregister_host(planes_r, p1, v1)
     ev.close()
+
+
+def test_large_batch_is_many_small_batches(small_ckpt):
+    """n = 2048 (739 328 pixel rows, 2888 CTA-pair tiles, 40 waves): every position must get exactly what it gets
+    in a batch of 128 — exercises the tile scheduler, the periodic edge-mask table and 32-bit row arithmetic far
+    beyond the benchmark size."""
+    import oracle
+    from unrealgo_b200 import DlTFNetworkEvaluator
+    packed, _ = oracle.synthetic_positions(256, seed=99)
+    big = np.concatenate([packed] * 8)                       # 2048 positions
+    big = big[np.random.default_rng(0).permutation(len(big))]
+    ev = DlTFNetworkEvaluator(small_ckpt[0], max_batch=2048)
+    assert ev.UpdateCheckPoint(small_ckpt[1])
+    p, v = ev.evaluate_packed(big)
+    for lo in range(0, 2048, 128):
+        ps, vs = ev.evaluate_packed(big[lo:lo + 128])
+        assert np.array_equal(ps, p[lo:lo + 128]) and np.array_equal(vs, v[lo:lo + 128]), lo
+    ev.close()
