@@ -140,6 +140,9 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int chunks = args.cin / CK;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
+  // Which cluster gets the short tile list (num_tiles is rarely a multiple of the cluster count) rotates from
+  // layer to layer, so that with tile-granular dependencies every SM pair does the same work over a few layers.
+  const int tile0 = (cluster_id + args.tile_rot) % num_clusters;
   constexpr bool has_res = RES > 0;
   constexpr bool has_res_lo = RES > 1;
   constexpr bool has_out_lo = OUT_LO;
@@ -179,11 +182,25 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t elected = elect_one();
   if (warp == 0) {
     // ===================== A-chunk producer =====================
-    pdl_wait();
+    // What this layer reads was written by the previous kernel in the stream.  Either wait for that whole grid
+    // (griddepcontrol.wait), or — tile-granular mode — for the three 256-row tiles this tile's rows and halo come
+    // from: the previous layer's epilogue counts its finished tiles in args.flags_in, so the tail of one layer and
+    // the head of the next overlap instead of draining the GPU at every layer boundary.
+    const bool tile_deps = args.flags_in != nullptr;
+    if (!tile_deps) pdl_wait();
     int sa = 0;
     uint32_t pha = 0;
-    for (int tile = cluster_id; tile < args.num_tiles; tile += num_clusters) {
+    for (int tile = tile0; tile < args.num_tiles; tile += num_clusters) {
       const int mc = tile * (2 * kTileM) + (int)cta_rank * kTileM;
+      if (tile_deps) {
+        if (elected) {
+          const int t_lo = tile > 0 ? tile - 1 : 0;
+          const int t_hi = tile + 1 < args.num_tiles ? tile + 1 : args.num_tiles - 1;
+          for (int t = t_lo; t <= t_hi; ++t) wait_flag_ge(args.flags_in + t, args.target_in);
+          fence_proxy_async_all();  // the TMA loads below must observe what the flags published
+        }
+        __syncwarp();
+      }
       for (int j = 0; j < chunks; ++j) {
         mbar_wait(&a_empty[sa], pha ^ 1);
         if (elected) {
@@ -198,7 +215,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ===================== B (weights) producer =====================
     int sb = 0;
     uint32_t phb = 0;
-    for (int tile = cluster_id; tile < args.num_tiles; tile += num_clusters) {
+    for (int tile = tile0; tile < args.num_tiles; tile += num_clusters) {
       for (int j = 0; j < chunks; ++j) {
 #pragma unroll 1
         for (int t = 0; t < 9; ++t) {
@@ -224,7 +241,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool prof = args.prof != nullptr;
       long long w_acc = 0, w_a = 0, w_b = 0;
       const long long t_begin = clock64();
-      for (int tile = cluster_id; tile < args.num_tiles; tile += num_clusters, ++it) {
+      for (int tile = tile0; tile < args.num_tiles; tile += num_clusters, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         timed_wait(&acc_empty[as], aphase ^ 1, prof, &w_acc);
@@ -282,12 +299,20 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 3) {
     // ===================== residual producer =====================
     if constexpr (has_res) {
-      pdl_wait();
+      const bool tile_deps = args.flags_res != nullptr;
+      if (!tile_deps) pdl_wait();
       int rs = 0;
       uint32_t phr = 0;
       constexpr uint32_t bytes = has_res_lo ? kResSlot : kResHalf;
-      for (int tile = cluster_id; tile < args.num_tiles; tile += num_clusters) {
+      for (int tile = tile0; tile < args.num_tiles; tile += num_clusters) {
         const int mc = tile * (2 * kTileM) + (int)cta_rank * kTileM;
+        if (tile_deps) {  // the residual tile was written two layers back: its own counter
+          if (elected) {
+            wait_flag_ge(args.flags_res + tile, args.target_res);
+            fence_proxy_async_all();
+          }
+          __syncwarp();
+        }
         for (int c0 = 0; c0 < cout; c0 += kEpiCols) {
           mbar_wait(&res_empty[rs], phr ^ 1);
           if (elected) {
@@ -313,7 +338,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool prof = args.prof != nullptr && leader && warp == 4;
     long long w_full = 0, w_res = 0, w_st = 0;
     const long long t_begin = clock64();
-    for (int tile = cluster_id; tile < args.num_tiles; tile += num_clusters, ++it) {
+    for (int tile = tile0; tile < args.num_tiles; tile += num_clusters, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int mc = tile * (2 * kTileM) + (int)cta_rank * kTileM;
@@ -416,6 +441,14 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             bulk_commit_group();
           }
           if (++os == kNO) os = 0;
+        }
+      }
+      if constexpr (HEADS == 0) {
+        // tile-granular mode: publish "this warp's 32 rows of the tile are in memory" (8 counts complete a tile)
+        if (args.flags_out != nullptr && lane == 0) {
+          bulk_wait_group_all();     // the TMA stores of this tile have completed, not merely been read
+          fence_proxy_async_all();   // async-proxy writes before the generic-proxy release below
+          red_release_gpu_add(args.flags_out + tile, 1u);
         }
       }
       if constexpr (HEADS > 0) {

@@ -251,7 +251,8 @@ bool ug_eval::ensure_workspace(int C) {
             d_planes.alloc(nb * UG_NUM_PLANES * UG_NUM_POINTS) && d_bytes.alloc(nb * UG_NUM_PLANES * UG_NUM_POINTS) &&
             d_in.alloc(nb * UG_NUM_POINTS * kCinPad * 2) && d_feat.alloc(nb * UG_NUM_POINTS * 8 * 4) &&
             d_policy.alloc(nb * UG_NUM_MOVES * 4) && d_value.alloc(nb * 4) &&
-            d_policy64.alloc(nb * UG_NUM_MOVES * 8) && d_value64.alloc(nb * 8);
+            d_policy64.alloc(nb * UG_NUM_MOVES * 8) && d_value64.alloc(nb * 8) &&
+            d_flags.alloc(2 * ((nb * UG_NUM_POINTS + 255) / 256) * sizeof(uint32_t));
   for (int i = 0; i < 2 && ok; ++i) ok = d_s_hi[i].alloc(act_elems * 2) && d_s_lo[i].alloc(act_elems * 2);
   ok = ok && d_t.alloc(act_elems * 2);
   if (ok && precision == UG_PREC_FP32) {
@@ -385,11 +386,27 @@ int ug_eval::enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, con
   a.f16 = precision == UG_PREC_FP16;
   a.cout = C;
   a.pdl = use_pdl ? 1 : 0;
+  // Tile-granular dependencies need the overlap that programmatic launch provides; counters restart every pass.
+  const bool deps = tile_deps && use_pdl;
+  const size_t tiles_alloc = ((size_t)max_batch * UG_NUM_POINTS + 255) / 256;
+  uint32_t* F[2] = {d_flags.as<uint32_t>(), d_flags.as<uint32_t>() + tiles_alloc};
+  if (deps) cudaMemsetAsync(d_flags.p, 0, d_flags.bytes, s);
+  int layer = 0;  // 0 = stem, then the tower convolutions in order
+  auto set_deps = [&](bool has_res) {
+    if (!deps) return;
+    a.tile_rot = (layer * 9) % 74;  // 361 tiles on 74 pairs leave 9 pairs one tile short: shift that group each layer
+    a.flags_out = F[layer & 1];
+    a.flags_in = layer > 0 ? F[(layer - 1) & 1] : nullptr;
+    a.target_in = layer > 0 ? 8u * (uint32_t)((layer - 1) / 2 + 1) : 0u;
+    a.flags_res = has_res ? F[layer & 1] : nullptr;   // written two layers back, same parity
+    a.target_res = has_res ? 8u * (uint32_t)(layer / 2) : 0u;
+  };
   // stem: writes S[0] (hi [+ lo])
   a.cin = kCinPad;
   a.bias = W.convs[0].bias.as<float>();
   a.has_out_lo = split;
   ConvV2Maps m{&v2_a_in, &W.convs[0].tm_w[1], nullptr, nullptr, &v2_out_hi[0], split ? &v2_out_lo[0] : nullptr};
+  set_deps(false);
   cudaError_t e = conv3x3_v2_launch(m, a, 32, device, sms, s);
   if (e != cudaSuccess) return fail(-1, std::string("stem conv launch: ") + cudaGetErrorString(e));
   a.cin = C;
@@ -402,6 +419,8 @@ int ug_eval::enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, con
     a.bias = c1.bias.as<float>();
     a.has_res = a.has_res_lo = a.has_out_lo = 0;
     m = ConvV2Maps{&v2_a_s[x], &c1.tm_w[1], nullptr, nullptr, &v2_out_t, nullptr};
+    layer = 2 * b + 1;
+    set_deps(false);
     e = conv3x3_v2_launch(m, a, 64, device, sms, s);
     if (e != cudaSuccess) return fail(-1, std::string("tower conv launch: ") + cudaGetErrorString(e));
     *final_act = d_t.p;
@@ -421,6 +440,8 @@ int ug_eval::enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, con
     }
     m = ConvV2Maps{&v2_a_t, &c2.tm_w[1], &v2_res_hi[x], split ? &v2_res_lo[x] : nullptr, &v2_out_hi[y],
                    split ? &v2_out_lo[y] : nullptr};
+    layer = 2 * b + 2;
+    set_deps(true);
     e = conv3x3_v2_launch(m, a, 64, device, sms, s);
     if (e != cudaSuccess) return fail(-1, std::string("tower conv launch: ") + cudaGetErrorString(e));
     a.head_out = nullptr;
@@ -463,7 +484,7 @@ int ug_eval::enqueue(Src kind, const void* d_src, int n, const uint32_t* d_leg, 
   if (n <= 0 || n > max_batch) return fail(-1, "batch size " + std::to_string(n) + " outside [1, max_batch]");
   if (!use_graphs) return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
   const GraphKey key((int)kind, n, d_src, (const void*)d_leg, (const void*)d_pol, (const void*)d_val, vt,
-                     conv_ctas * 4 + precision + (resid_split ? 8192 : 0) + conv_impl * 16384 + (use_pdl ? 65536 : 0) + (fuse_heads ? 131072 : 0) + (debug_stop + 1) * 16);
+                     conv_ctas * 4 + precision + (resid_split ? 8192 : 0) + conv_impl * 16384 + (use_pdl ? 65536 : 0) + (fuse_heads ? 131072 : 0) + (tile_deps ? 262144 : 0) + (debug_stop + 1) * 16);
   auto it = graphs.find(key);
   if (it == graphs.end()) {
     if (graphs.size() > 1024) drop_graphs();
@@ -524,6 +545,8 @@ ug_eval* ug_eval_create(int device, int precision, int max_batch) {
   if (cc && (cc[0] == '1' || cc[0] == '2')) h->conv_ctas = cc[0] - '0';
   const char* fh = getenv("UGEVAL_FUSE_HEADS");
   if (fh && (fh[0] == '0' || fh[0] == '1')) h->fuse_heads = fh[0] == '1';
+  const char* td = getenv("UGEVAL_TILE_DEPS");
+  if (td && (td[0] == '0' || td[0] == '1')) h->tile_deps = td[0] == '1';
   const char* pd = getenv("UGEVAL_PDL");
   if (pd && (pd[0] == '0' || pd[0] == '1')) h->use_pdl = pd[0] == '1';
   const char* ci = getenv("UGEVAL_CONV_IMPL");

@@ -60,6 +60,10 @@ struct ug_eval {
   int conv_ctas = 2;
   int conv_impl = 2;  // 1 = im2col kernel (conv3x3_tc.cu), 2 = resident-tile kernel (conv3x3_v2.cu)
   bool fuse_heads = true;   // head 1x1 convolutions in the last tower layer's epilogue (UGEVAL_FUSE_HEADS=0 disables)
+  // Layers depend on each other tile by tile (per-tile completion counters) instead of grid by grid.  Measured
+  // +0..1 % at batch 256 (the tail it can recover is the 2.4 % of 361 tiles on 74 CTA pairs), so it stays opt-in:
+  // UGEVAL_TILE_DEPS=1.
+  bool tile_deps = false;
   bool use_pdl = true;      // programmatic dependent launch between tower layers (UGEVAL_PDL=0 disables)
   bool resid_split = true;  // carry the residual stream as hi + lo 16-bit pair (numerics)
   int value_transform = UG_TR_IDENTITY;
@@ -81,6 +85,7 @@ struct ug_eval {
   // workspace (allocated once the architecture is known)
   int ws_C = 0;
   ug::DevBuf d_pos, d_legal, d_planes, d_in, d_feat, d_policy, d_value, d_bytes;
+  ug::DevBuf d_flags;  // [2][tiles] per-tile completion counters of the tower layers (tile-granular dependencies)
   ug::DevBuf d_policy64, d_value64;  // double images of the outputs for registered (pinned) caller buffers
   std::vector<std::pair<uintptr_t, size_t>> host_regs;  // caller buffers registered with ug_eval_register_host
   // residual stream ping-pong S[0]/S[1] as bf16 hi + bf16 lo (skip = hi + lo), block-internal tensor T (bf16)

@@ -254,6 +254,32 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // lets the dependent grid be scheduled as soon as every CTA of this grid has issued it (or exited)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---------------------------------------------------------------- inter-kernel tile flags
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// orders generic-proxy accesses (flag loads/stores) against async-proxy ones (TMA loads/stores), all state spaces
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Spin until *flag >= target.  Bounded like mbar_wait: a protocol bug traps instead of hanging the box.
+__device__ __forceinline__ void wait_flag_ge(const uint32_t* flag, uint32_t target) {
+  if (ld_acquire_gpu(flag) >= target) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(flag) < target) {
+    __nanosleep(100);
+    if ((++spins & 0xff) == 0 && clock64() - t0 > UG_MBAR_TIMEOUT_CYCLES) {
+      printf("ugeval: tile-flag timeout block %d thread %d flag %p target %u\n", (int)blockIdx.x, (int)threadIdx.x,
+             (const void*)flag, target);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- descriptors
 // K-major operand tile in shared memory written by TMA with SWIZZLE_128B (rows of 128 B, 8-row atoms of
 // 1024 B) or SWIZZLE_64B (rows of 64 B, 8-row atoms of 512 B).  Field layout: start>>4 [0,14),
