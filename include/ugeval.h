@@ -164,7 +164,7 @@ int ug_k_conv3x3_bf16(int device, const void* d_in, const void* d_w, const float
 /* Raw entry of the second-generation conv kernel (shared-memory-resident input tile, shifted-descriptor taps,
  * TMA-staged epilogue): 16-bit NHWC in/out on device buffers of n_alloc*361 rows, optional hi/lo residual and
  * lo output; runs once, then `iters` more times between CUDA events (ms_out = average launch time).
- * d_prof (optional, device, [74][16] int64): per-cluster stall-cycle counters of the last launch. */
+ * d_prof (optional, device, [74][64] int64): per-cluster stall-cycle counters of the last launch. */
 int ug_k_conv3x3_v2(int device, const void* d_in, const void* d_w, const float* d_bias, const void* d_res_hi,
                     const void* d_res_lo, void* d_out_hi, void* d_out_lo, int n, int n_alloc, int cin, int cout,
                     int relu, int f16, int desc_mode, int iters, float* ms_out, long long* d_prof);

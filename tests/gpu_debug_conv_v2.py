@@ -39,7 +39,7 @@ def run(n, cin, cout, taps, desc_mode, residual, out_lo, f16=True, relu=True, se
     doh = torch.full((n_alloc, 19, 19, cout), float("nan"), dtype=dt, device="cuda")
     dol = torch.full((n_alloc, 19, 19, cout), float("nan"), dtype=dt, device="cuda") if out_lo else None
     ms = C.c_float(0)
-    dprof = torch.zeros(74, 16, dtype=torch.int64, device="cuda") if prof else None
+    dprof = torch.zeros(74, 64, dtype=torch.int64, device="cuda") if prof else None
     rc = lib.ug_k_conv3x3_v2(0, dx.data_ptr(), dw.data_ptr(), db.data_ptr(), drh.data_ptr() if residual else None,
                              drl.data_ptr() if drl is not None else None, doh.data_ptr(), dol.data_ptr() if out_lo else None,
                              n, n_alloc, cin, cout, 1 if relu else 0, 1 if f16 else 0, desc_mode, iters, C.byref(ms),
@@ -74,6 +74,10 @@ def run(n, cin, cout, taps, desc_mode, residual, out_lo, f16=True, relu=True, se
                  "w_res", "w_store"]
         msg += "\n    prof(mean cycles/cluster): " + " ".join(f"{nm}={p[:, i].mean().item():.0f}" for i, nm in enumerate(names) if nm)
         msg += f"\n    prof(max mma_total)={p[:, 0].max().item():.0f} min={p[:, 0].min().item():.0f}"
+        # the raw entry runs 1 + iters launches on the same counters: bins accumulate over all of them
+        bins = p[:, 16:52].mean(0).reshape(4, 9)
+        msg += "\n    B-wait by (chunk j, tap step t), mean cycles over launches: " + " | ".join(
+            " ".join(f"{x:.0f}" for x in row) for row in bins.tolist()) + f"  first-tile total {p[:, 60].mean().item():.0f}"
     if iters:
         fl = 2.0 * n * 361 * 9 * cin * cout
         msg += f" | {ms.value * 1e3:.1f} us/launch {fl / ms.value / 1e9:.0f} TFLOP/s"

@@ -265,7 +265,19 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (q >= kPix) q -= kPix;  // q0 < 361 and 32*w <= 224, so one subtraction suffices
               m[w] = c_edge_mask[tap][q];
             }
-            timed_wait(&b_full[sb], phb, prof, &w_b);
+            if (prof) {  // B-stage stalls by position in the tile (chunk j, tap step t), and for the first tile apart
+              const long long tb = clock64();
+              mbar_wait(&b_full[sb], phb);
+              const long long d = clock64() - tb;
+              w_b += d;
+              if (lane == 0) {
+                long long* o = args.prof + (size_t)cluster_id * 64 + 16 + (j & 3) * 9 + t;
+                *o += d;
+                if (it == 0) args.prof[(size_t)cluster_id * 64 + 60] += d;
+              }
+            } else {
+              mbar_wait(&b_full[sb], phb);
+            }
             tc_fence_after();
             const uint32_t a_addr = a_slot + (uint32_t)shift * kRowBytes;
             uint64_t adesc = make_kmajor_desc<kRowBytes>(a_addr);
@@ -292,7 +304,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
       }
       if (prof && lane == 0) {
-        long long* o = args.prof + (size_t)cluster_id * 16;
+        long long* o = args.prof + (size_t)cluster_id * 64;
         o[0] = clock64() - t_begin; o[1] = w_acc; o[2] = 0; o[3] = w_a; o[4] = w_b; o[5] = it;
       }
     }
@@ -463,7 +475,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     if (lane == 0) bulk_wait_group_all();
     if (prof && lane == 0) {
-      long long* o = args.prof + (size_t)cluster_id * 16;
+      long long* o = args.prof + (size_t)cluster_id * 64;
       o[8] = clock64() - t_begin; o[9] = w_full; o[10] = w_res; o[11] = w_st;
     }
   }

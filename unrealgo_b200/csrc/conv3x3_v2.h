@@ -34,7 +34,7 @@ struct ConvV2Args {
   int pdl;                // launch with programmatic stream serialization (overlap the prologue and the weight
                           // prefetch with the previous kernel's tail)
   int num_tiles;          // filled by the launcher
-  long long* prof;        // optional [clusters][16] cycle counters (bring-up instrumentation), else null
+  long long* prof;        // optional [clusters][64] cycle counters, zeroed by the caller (bring-up instrumentation), else null
 };
 
 // Tensor maps (see tmap.h): a = halo tile over the input [rows][cin] (box {ck, 168}); w = packed weights
