@@ -242,6 +242,21 @@ def main():
     dev_ms = float(t.item())
     assert torch.isfinite(d_pol).all() and torch.isfinite(d_val).all()
 
+    # sustained rate: the same step back to back for ~3 s (no L2 flush, no idle gaps) — the part then sits at its
+    # power cap; this is the rate the self-play leg can at best reach
+    t0 = time.perf_counter()
+    sus_steps = 0
+    while time.perf_counter() - t0 < 3.0:
+        for i in range(32):
+            step(sus_steps + i)
+        torch.cuda.synchronize()
+        sus_steps += 32
+    sustained = world * B * sus_steps / (time.perf_counter() - t0)
+    ts = torch.tensor([sustained], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MIN)  # every rank reports world * its own rate: keep the slowest
+    sustained = float(ts.item())
+
     # end to end through the reference-facing entry: host int8 planes in, host double policy/value out
     planes = [synth.packed_to_planes(p) for p in host_packed[:2]]
     pol = np.empty((B, 362), np.float64)
@@ -330,6 +345,7 @@ def main():
                        "flops_per_position": info["flops_per_position"],
                        "tensor_frac_of_burst_peak_whole_step": value / world * info["flops_per_position"] / (burst * 1e12),
                        "e2e_packed_positions_per_s": world * B * e2e_steps / e2e_packed_s,
+                       "sustained_3s_positions_per_s": sustained,
                        "kernel_group_ms": {"encoder": br["ms_encoder"], "tower": br["ms_tower"], "heads": br["ms_heads"],
                                            "stem": br_stem["ms_tower"]}},
             "clocks": sampler.summary(),
