@@ -242,21 +242,6 @@ def main():
     dev_ms = float(t.item())
     assert torch.isfinite(d_pol).all() and torch.isfinite(d_val).all()
 
-    # sustained rate: the same step back to back for ~3 s (no L2 flush, no idle gaps) — the part then sits at its
-    # power cap; this is the rate the self-play leg can at best reach
-    t0 = time.perf_counter()
-    sus_steps = 0
-    while time.perf_counter() - t0 < 3.0:
-        for i in range(32):
-            step(sus_steps + i)
-        torch.cuda.synchronize()
-        sus_steps += 32
-    sustained = world * B * sus_steps / (time.perf_counter() - t0)
-    ts = torch.tensor([sustained], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ts, op=dist.ReduceOp.MIN)  # every rank reports world * its own rate: keep the slowest
-    sustained = float(ts.item())
-
     # end to end through the reference-facing entry: host int8 planes in, host double policy/value out
     planes = [synth.packed_to_planes(p) for p in host_packed[:2]]
     pol = np.empty((B, 362), np.float64)
@@ -283,6 +268,22 @@ def main():
     e2e_s, e2e_packed_s = (float(x) for x in te.tolist())
     sampler.stop_flag = True
     sampler.join(timeout=2)
+
+    # sustained rate: the same step back to back for ~3 s (no L2 flush, no idle gaps) — the part then sits at its
+    # power cap; this is the rate the self-play leg can at best reach
+    t0 = time.perf_counter()
+    sus_steps = 0
+    while time.perf_counter() - t0 < 3.0:
+        for i in range(32):
+            step(sus_steps + i)
+        torch.cuda.synchronize()
+        sus_steps += 32
+    sustained = world * B * sus_steps / (time.perf_counter() - t0)
+    ts = torch.tensor([sustained], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MIN)  # every rank reports world * its own rate: keep the slowest
+    sustained = float(ts.item())
+
 
     # self-play playouts/s (BASELINE configs[2]/[3]): games sharded per GPU, no collective on the data path
     sp = None
