@@ -307,7 +307,8 @@ ug_queue* ug_queue_create(ug_eval* h, int max_batch, int timeout_us, int capacit
          cudaMalloc((void**)&S.d_value, nb * 4) == cudaSuccess &&
          cudaEventCreateWithFlags(&S.ev_in, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&S.ev_out, cudaEventDisableTiming) == cudaSuccess;
+         // the completion thread sleeps on this one instead of spinning a core away (4 CPUs per GPU on 8-GPU boxes)
+         cudaEventCreateWithFlags(&S.ev_out, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
   }
   if (!ok) {
     h->fail(-1, "queue: cannot allocate staging buffers");

@@ -27,20 +27,44 @@
 
 namespace {
 
-struct Node {
-  float prior;
-  float w;            // sum of backed-up values (perspective of the player who made `move`)
-  uint32_t visits;
-  uint32_t first_child;
-  uint32_t parent;
-  uint16_t n_children;
-  uint16_t move;      // policy index, 361 = pass
+// Search tree, structure-of-arrays: one descent reads prior/w/visits of every child of every node on the path
+// (up to 362 children per level), so the three hot fields live in their own arrays (12 bytes per child instead of
+// a 24-byte record) and the scan in select_child() is a plain loop over contiguous floats.
+struct Tree {
+  std::vector<float> prior;          // network prior of the move leading here
+  std::vector<float> w;              // sum of backed-up values (perspective of the player who made `move`)
+  std::vector<uint32_t> visits;
+  std::vector<uint32_t> first_child; // children of a node are contiguous
+  std::vector<uint32_t> parent;
+  std::vector<uint16_t> n_children;
+  std::vector<uint16_t> move;        // policy index, 361 = pass
+  size_t size() const { return visits.size(); }
+  void clear() {
+    prior.clear(); w.clear(); visits.clear(); first_child.clear(); parent.clear(); n_children.clear(); move.clear();
+  }
+  void reserve(size_t n) {
+    prior.reserve(n); w.reserve(n); visits.reserve(n); first_child.reserve(n); parent.reserve(n); n_children.reserve(n);
+    move.reserve(n);
+  }
+  void resize(size_t n) {
+    prior.resize(n, 0.f); w.resize(n, 0.f); visits.resize(n, 0u); first_child.resize(n, 0u); parent.resize(n, 0u);
+    n_children.resize(n, 0); move.resize(n, 0);
+  }
+  void swap(Tree& o) {
+    prior.swap(o.prior); w.swap(o.w); visits.swap(o.visits); first_child.swap(o.first_child); parent.swap(o.parent);
+    n_children.swap(o.n_children); move.swap(o.move);
+  }
+  void copy_node(size_t dst, const Tree& src, size_t s) {
+    prior[dst] = src.prior[s]; w[dst] = src.w[s]; visits[dst] = src.visits[s]; first_child[dst] = src.first_child[s];
+    parent[dst] = src.parent[s]; n_children[dst] = src.n_children[s]; move[dst] = src.move[s];
+  }
 };
 
 struct Game {
   ugo::Board root_board;
   ugo::Board work;              // board at the pending leaf
-  std::vector<Node> tree, scratch;
+  Tree tree, scratch;
+  std::vector<uint32_t> map_src;  // scratch of reuse_subtree
   uint32_t leaf = 0;
   int64_t ticket = -1;          // >= 0: a leaf is waiting for its evaluation
   int playouts_this_move = 0;
@@ -105,55 +129,97 @@ bool write_game_record(const Game& g, const ug_selfplay_config& cfg) {
   return ug_tfrecord_close(w) >= 0 && ok;
 }
 
-inline float mean_value(const Node& n) { return n.visits ? n.w / (float)n.visits : 0.f; }
-
-// UctSearch::Select, search/UctSearch.cpp:1062-1098 (num_threads == 1: no virtual loss)
-uint32_t select_child(const std::vector<Node>& t, uint32_t parent, float c_puct) {
-  const Node& p = t[parent];
-  double total = 0;
-  for (uint32_t i = 0; i < p.n_children; ++i) total += t[p.first_child + i].visits;
-  const float spc = (float)std::max(std::sqrt(total), 1.0);
-  const double default_mean = -(double)mean_value(p);
-  double best_v = std::numeric_limits<double>::min();  // sic: the reference initialises with min(), not lowest()
-  int64_t best = -1;
-  for (uint32_t i = 0; i < p.n_children; ++i) {
-    const Node& c = t[p.first_child + i];
-    if (c.move == ugo::PASS) continue;  // PASS is only taken when it is the only child (:1082, :1093-1096)
-    const double q = c.visits ? (double)mean_value(c) : default_mean;
-    const double v = q + (double)c_puct * c.prior * spc / (1.0 + c.visits);
-    if (best < 0 || v > best_v) { best = p.first_child + i; best_v = v; }
+// value_i = Q_i + c_puct * prior_i * spc / (1 + visits_i), first maximum wins; Q of an unvisited child is
+// default_mean.  Two passes so that the arithmetic pass is branch-free and vectorises (the children's prior / w /
+// visits are contiguous arrays); the operation order per element is the reference's (search/UctSearch.cpp:1084).
+#if defined(__GNUC__) && defined(__x86_64__)
+__attribute__((optimize("O3"), target("avx2,fma")))
+static uint32_t argmax_puct_avx2(const float* __restrict__ pr, const float* __restrict__ ww,
+                                 const uint32_t* __restrict__ vv, uint32_t n, double default_mean, double cp, float spc) {
+  double val[UG_NUM_MOVES];
+  const double dspc = (double)spc;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t vis = vv[i];
+    const float qf = ww[i] / (float)(vis ? vis : 1u);
+    const double q = vis ? (double)qf : default_mean;
+    val[i] = q + cp * (double)pr[i] * dspc / (1.0 + (double)vis);
   }
-  return best < 0 ? p.first_child : (uint32_t)best;
+  uint32_t best = 0;
+  double best_v = val[0];
+  for (uint32_t i = 1; i < n; ++i)
+    if (val[i] > best_v) { best_v = val[i]; best = i; }
+  return best;
+}
+#endif
+static uint32_t argmax_puct_scalar(const float* __restrict__ pr, const float* __restrict__ ww,
+                                   const uint32_t* __restrict__ vv, uint32_t n, double default_mean, double cp, float spc) {
+  double best_v = 0;
+  uint32_t best = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t vis = vv[i];
+    const double q = vis ? (double)(ww[i] / (float)vis) : default_mean;
+    const double v = q + cp * (double)pr[i] * (double)spc / (1.0 + (double)vis);
+    if (i == 0 || v > best_v) { best = i; best_v = v; }
+  }
+  return best;
+}
+static uint32_t argmax_puct(const float* pr, const float* ww, const uint32_t* vv, uint32_t n, double default_mean,
+                            double cp, float spc) {
+#if defined(__GNUC__) && defined(__x86_64__)
+  static const bool have_avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
+  if (have_avx2) return argmax_puct_avx2(pr, ww, vv, n, default_mean, cp, spc);
+#endif
+  return argmax_puct_scalar(pr, ww, vv, n, default_mean, cp, spc);
+}
+
+// UctSearch::Select, search/UctSearch.cpp:1062-1098 (num_threads == 1: no virtual loss).
+// The reference sums the children's visit counts; every backup through a node passes through exactly one child
+// except the one that expanded it, so that sum is visits(parent) - 1 and the first pass over the children is saved.
+uint32_t select_child(const Tree& t, uint32_t parent, float c_puct) {
+  const uint32_t base = t.first_child[parent];
+  uint32_t n = t.n_children[parent];
+  const uint32_t pv = t.visits[parent];
+  const double total = pv > 0 ? (double)(pv - 1) : 0.0;
+  const float spc = (float)std::max(std::sqrt(total), 1.0);  // float, as in the reference (:1075)
+  const double default_mean = pv ? -(double)(t.w[parent] / (float)pv) : 0.0;
+  // PASS is generated last and only taken when it is the only child (:1082, :1093-1096)
+  if (n > 1 && t.move[base + n - 1] == ugo::PASS) --n;
+  else if (n == 1) return base;
+  const uint32_t best = argmax_puct(t.prior.data() + base, t.w.data() + base, t.visits.data() + base, n, default_mean,
+                                    (double)c_puct, spc);
+  return base + best;
 }
 
 void new_root(Game& g) {
   g.tree.clear();
-  Node r{};
-  r.parent = 0;
-  r.move = ugo::PASS;
-  g.tree.push_back(r);
+  g.tree.resize(1);
+  g.tree.move[0] = ugo::PASS;
 }
 
 // keep the subtree below `child` as the new tree (UctSearchTree::CopySubtree, search/UctSearchTree.cpp:159-225)
 void reuse_subtree(Game& g, uint32_t child) {
-  std::vector<Node>& src = g.tree;
-  std::vector<Node>& dst = g.scratch;
+  Tree& src = g.tree;
+  Tree& dst = g.scratch;
   dst.clear();
-  dst.push_back(src[child]);
-  dst[0].parent = 0;
+  dst.resize(1);
+  dst.copy_node(0, src, child);
+  dst.parent[0] = 0;
   // breadth-first copy keeps every node's children contiguous
-  std::vector<uint32_t> map_src;  // dst index -> src index
+  std::vector<uint32_t>& map_src = g.map_src;  // dst index -> src index
+  map_src.clear();
   map_src.push_back(child);
   for (size_t di = 0; di < dst.size(); ++di) {
-    const Node s = src[map_src[di]];
-    if (s.n_children == 0) continue;
+    const uint32_t si = map_src[di];
+    const uint32_t nc = src.n_children[si];
+    if (nc == 0) continue;
     const uint32_t base = (uint32_t)dst.size();
-    dst[di].first_child = base;
-    for (uint32_t i = 0; i < s.n_children; ++i) {
-      Node c = src[s.first_child + i];
-      c.parent = (uint32_t)di;
-      dst.push_back(c);
-      map_src.push_back(s.first_child + i);
+    const uint32_t sbase = src.first_child[si];
+    dst.first_child[di] = base;
+    dst.resize(base + nc);
+    for (uint32_t i = 0; i < nc; ++i) {
+      dst.copy_node(base + i, src, sbase + i);
+      dst.parent[base + i] = (uint32_t)di;
+      map_src.push_back(sbase + i);
     }
   }
   src.swap(dst);
@@ -164,9 +230,9 @@ void reuse_subtree(Game& g, uint32_t child) {
 bool start_playout(Game& g, Shared& sh) {
   g.work = g.root_board;
   uint32_t node = 0;
-  while (g.tree[node].n_children) {
+  while (g.tree.n_children[node]) {
     node = select_child(g.tree, node, sh.cfg.puct);
-    g.work.play(g.tree[node].move);
+    g.work.play(g.tree.move[node]);
   }
   uint16_t moves[UG_NUM_MOVES];
   uint32_t legal[UG_MASK_WORDS];
@@ -176,13 +242,12 @@ bool start_playout(Game& g, Shared& sh) {
     return false;
   }
   const uint32_t base = (uint32_t)g.tree.size();
-  g.tree[node].first_child = base;
-  g.tree[node].n_children = (uint16_t)n;
+  g.tree.first_child[node] = base;
+  g.tree.n_children[node] = (uint16_t)n;
+  g.tree.resize(base + (size_t)n);  // prior 0 until the evaluation arrives (UctSearchTree::Expand, :675-691)
   for (int i = 0; i < n; ++i) {
-    Node c{};
-    c.parent = node;
-    c.move = moves[i];
-    g.tree.push_back(c);  // prior 0 until the evaluation arrives (UctSearchTree::Expand, :675-691)
+    g.tree.parent[base + i] = node;
+    g.tree.move[base + i] = moves[i];
   }
   ug_packed_pos pos;
   g.work.pack(&pos);
@@ -193,58 +258,54 @@ bool start_playout(Game& g, Shared& sh) {
 }
 
 void finish_playout(Game& g, float value) {
-  Node& leaf = g.tree[g.leaf];
-  for (uint32_t i = 0; i < leaf.n_children; ++i) {
-    Node& c = g.tree[leaf.first_child + i];
-    c.prior = g.policy[c.move];  // already renormalised over the legal children on the GPU (UpdatePrior)
-  }
+  Tree& t = g.tree;
+  const uint32_t base = t.first_child[g.leaf], nc = t.n_children[g.leaf];
+  for (uint32_t i = 0; i < nc; ++i)
+    t.prior[base + i] = g.policy[t.move[base + i]];  // already renormalised over the legal children on the GPU
   uint32_t cur = g.leaf;
   float v = value;
   for (;;) {  // BackupTree, search/UctSearch.cpp:1282-1295
-    Node& n = g.tree[cur];
-    n.visits += 1;
-    n.w += v;
+    t.visits[cur] += 1;
+    t.w[cur] += v;
     v = -v;
     if (cur == 0) break;
-    cur = n.parent;
+    cur = t.parent[cur];
   }
 }
 
 // after playouts_per_move playouts: play the most visited child (first wins ties), keep or drop the tree
 void make_move(Game& g, Shared& sh) {
-  const Node& r = g.tree[0];
+  const Tree& t = g.tree;
+  const uint32_t rbase = t.first_child[0], rn = t.n_children[0];
   int move = ugo::PASS;
   uint32_t chosen = 0;
-  if (r.n_children) {
+  if (rn) {
     if (g.root_board.move_number < sh.cfg.random_opening_moves) {
       // harness option (not in the reference): diversify games with uniformly random legal opening moves
-      std::uniform_int_distribution<uint32_t> d(0, r.n_children > 1 ? r.n_children - 2 : 0);  // PASS is last
-      chosen = r.first_child + d(g.rng);
+      std::uniform_int_distribution<uint32_t> d(0, rn > 1 ? rn - 2 : 0);  // PASS is last
+      chosen = rbase + d(g.rng);
     } else {
       uint32_t best_visits = 0;
-      chosen = r.first_child;
+      chosen = rbase;
       bool first = true;
-      for (uint32_t i = 0; i < r.n_children; ++i) {
-        const Node& c = g.tree[r.first_child + i];
-        if (first || c.visits > best_visits) { best_visits = c.visits; chosen = r.first_child + i; first = false; }
+      for (uint32_t i = 0; i < rn; ++i) {
+        const uint32_t vis = t.visits[rbase + i];
+        if (first || vis > best_visits) { best_visits = vis; chosen = rbase + i; first = false; }
       }
     }
-    move = g.tree[chosen].move;
+    move = t.move[chosen];
   }
   if (sh.cfg.record_dir) {
     // the policy block of the move: zero, then the visit count of every root child (search/UctSearch.cpp:782-801)
     const size_t at = g.visit_policy.size();
     g.visit_policy.resize(at + UG_NUM_MOVES, 0.f);
-    for (uint32_t i = 0; i < r.n_children; ++i) {
-      const Node& c = g.tree[r.first_child + i];
-      g.visit_policy[at + c.move] = (float)c.visits;
-    }
+    for (uint32_t i = 0; i < rn; ++i) g.visit_policy[at + t.move[rbase + i]] = (float)t.visits[rbase + i];
   }
   g.root_board.play(move);
   g.moves.push_back((int16_t)move);
   sh.moves.fetch_add(1, std::memory_order_relaxed);
   sh.nodes.fetch_add(g.tree.size(), std::memory_order_relaxed);
-  if (sh.cfg.reuse_tree && r.n_children && g.tree[chosen].n_children) reuse_subtree(g, chosen);
+  if (sh.cfg.reuse_tree && rn && t.n_children[chosen]) reuse_subtree(g, chosen);
   else new_root(g);
   g.playouts_this_move = 0;
   const int limit = sh.cfg.max_moves > 0 ? sh.cfg.max_moves : 2 * 19 * 19;
@@ -314,6 +375,10 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
   for (int i = 0; i < cfg.games; ++i) {
     games[i].rng.seed(cfg.seed * 1000003ull + (uint64_t)i);
     games[i].index = i;
+    // one expansion per playout, up to 362 children each; with tree reuse about one move's worth survives
+    const size_t cap = (size_t)cfg.playouts_per_move * (UG_NUM_MOVES / 2) * (cfg.reuse_tree ? 3 : 2) / 2;
+    games[i].tree.reserve(cap);
+    if (cfg.reuse_tree) games[i].scratch.reserve(cap / 2);
     new_root(games[i]);
   }
   const auto t0 = std::chrono::steady_clock::now();
