@@ -44,6 +44,11 @@ def parse():
     return ap.parse_args()
 
 
+def workload(batch, blocks, filters):
+    return (f"batched evaluation of {batch} synthetic 19x19 positions per GPU, {blocks}-block x {filters}-filter "
+            "dlcfg-19 net (BASELINE configs[1]), seeded synthetic TF-format checkpoint")
+
+
 def checkpoint(blocks, filters):
     from unrealgo_b200 import tfformat
     d = f"/tmp/ugeval_bench_ckpt_{blocks}x{filters}_{os.getpid() if os.environ.get('RANK') else 'x'}"
@@ -149,7 +154,11 @@ def main_reference(args):
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * el / args.steps,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                       "data": "synthetic",
-                      "config": {"workload": f"{args.blocks}x{args.filters} dlcfg-19 net, batch {batch} on host cores"},
+                      "config": {"workload": workload(args.batch, args.blocks, args.filters), "batch": args.batch,
+                                 "blocks": args.blocks, "filters": args.filters,
+                                 "sample": f"each step evaluates positions of that workload {batch} at a time (MAX_BATCHES, "
+                                           "funcapproximator/DlTFNetworkEvaluator.h:15: the largest batch the reference's "
+                                           "evaluator accepts) for a bounded time on all host threads"},
                       "cpu_baseline": cb,
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
@@ -335,9 +344,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "bf16", "data": "synthetic",
-            "config": {"workload": f"batched evaluation of {B} synthetic 19x19 positions per GPU, "
-                                   f"{info['blocks']}-block x {C}-filter dlcfg-19 net (BASELINE configs[1]), "
-                                   "seeded synthetic TF-format checkpoint",
+            "config": {"workload": workload(B, info["blocks"], C),
                        "batch": B, "blocks": info["blocks"], "filters": C, "conv_cta_group": info["conv_ctas"],
                        "conv_impl": info.get("conv_impl"),
                        "arithmetic": f"{args.precision} operands (tcgen05 kind::f16), fp32 accumulation in TMEM, "
