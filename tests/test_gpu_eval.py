@@ -26,12 +26,19 @@ def _tol(precision):
     return (BF16_POL, BF16_VAL) if precision == PREC_BF16 else (TC_POL, TC_VAL)
 
 
-def _evaluator(ckpt, precision, max_batch=128, ctas=2):
+# tower kernel under test: "v2" = resident-tile kernel (default, CTA pairs); "v1-1" / "v1-2" = the TMA-im2col kernel
+# with cta_group 1 / 2
+KERNELS = ["v2", "v1-1", "v1-2"]
+
+
+def _evaluator(ckpt, precision, max_batch=128, ctas="v2"):
     from unrealgo_b200 import DlTFNetworkEvaluator
     ev = DlTFNetworkEvaluator(ckpt[0], precision=precision, max_batch=max_batch)
     assert ev.MetaGraphLoaded()
     assert ev.UpdateCheckPoint(ckpt[1])
-    ev.set_conv_ctas(ctas)
+    if ctas != "v2":
+        ev.set_conv_impl(1)
+        ev.set_conv_ctas(int(ctas[-1]))
     return ev
 
 
@@ -58,7 +65,7 @@ def test_fp32_validation_build_small(small_ckpt, positions, n):
 
 
 @pytest.mark.parametrize("precision", [2, 0], ids=["fp16", "bf16"])
-@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("ctas", KERNELS)
 @pytest.mark.parametrize("n", [1, 7, 16, 64])
 def test_tensor_core_build_small(small_ckpt, positions, n, ctas, precision):
     packed, planes = positions
@@ -75,7 +82,7 @@ def test_tensor_core_build_small(small_ckpt, positions, n, ctas, precision):
 
 
 @pytest.mark.parametrize("precision", [2, 0], ids=["fp16", "bf16"])
-@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("ctas", KERNELS)
 def test_wide_layers_and_outputs(wide_ckpt, positions, ctas, precision):
     """256 filters (the production tile shape) — every layer of the fp32 validation build against the oracle's
     graph interpreter, every layer of the bf16 tcgen05 build against the fp32 build, then end to end."""

@@ -41,10 +41,20 @@ def test_flagship_batch256_parity_and_properties(flagship):
     for lo, hi in [(0, 1), (5, 12), (100, 117)]:
         ps, vs = ev.evaluate_packed(packed[lo:hi])
         assert np.array_equal(ps, p2[lo:hi]) and np.array_equal(vs, v2[lo:hi])
-    for ctas in (1, 2):  # both tile shapes compute identical sums in identical order per output element
-        ev.set_conv_ctas(ctas)
-        pc, vc = ev.evaluate_packed(packed)
-        assert np.array_equal(pc, p2) and np.array_equal(vc, v2)
+    # the first-generation (TMA-im2col) kernel: its two tile shapes compute identical sums in identical order per
+    # output element; against the resident-tile kernel the tap order differs, so 16-bit roundings flip here and
+    # there in every layer — an independent realisation of the same rounding noise, held to the same tolerance
+    ev.set_conv_impl(1)
+    ev.set_conv_ctas(1)
+    p1, v1 = ev.evaluate_packed(packed)
+    ev.set_conv_ctas(2)
+    pc, vc = ev.evaluate_packed(packed)
+    assert np.array_equal(pc, p1) and np.array_equal(vc, v1)
+    d1p, d1v = np.abs(p1 - want_p).max(), np.abs(v1 - want_v).max()
+    print(f"flagship, im2col kernel: max|dpolicy|={d1p:.3e} max|dvalue|={d1v:.3e}; between kernels "
+          f"{np.abs(p1 - p2).max():.3e} / {np.abs(v1 - v2).max():.3e}")
+    assert d1p <= 1e-3 and d1v <= 5e-3
+    ev.set_conv_impl(2)
     ev.close()
     # bf16-operand mode on the same inputs: documented looser bound (8-bit mantissa through 41 convolutions)
     from unrealgo_b200 import PREC_BF16
