@@ -99,6 +99,8 @@ int ug_eval_set_conv_ctas(ug_eval* h, int ctas);
  * rows = 52.47 positions on a 148-SM part): 213 positions cost 5 waves, exactly as much as 262; 209 cost 4.  The
  * leaf queue uses it when it flushes a partial batch.  Returns n itself below one wave. */
 int ug_eval_efficient_batch(const ug_eval* h, int n);
+/* the same rule for a given SM count (host-only: no device needed) */
+int ug_efficient_batch_for_sms(int sm_count, int n);
 /* tower kernel generation: 1 = TMA-im2col operand staging (conv3x3_tc.cu), 2 = shared-memory-resident input tile
  * with shifted-descriptor taps and TMA-staged epilogue (conv3x3_v2.cu, default); testing/benchmark knob */
 int ug_eval_set_conv_impl(ug_eval* h, int impl);

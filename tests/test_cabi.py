@@ -56,3 +56,18 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "liboracle" not in src and "ugo_oracle" not in src, f
+
+
+def test_wave_aligned_batch_sizes():
+    """ug_eval_efficient_batch's rule (host arithmetic): a wave of the tower kernel on a 148-SM part is 74 CTA pairs x
+    256 pixel rows = 18944 rows = 52.47 positions; a partial batch is cut back to whole waves."""
+    from unrealgo_b200 import _lib
+    f = _lib.load().ug_efficient_batch_for_sms
+    assert [f(148, n) for n in (1, 30, 52)] == [1, 30, 52]          # below / at one wave: unchanged
+    assert f(148, 53) == 52 and f(148, 103) == 52 and f(148, 104) == 104 and f(148, 105) == 104
+    assert f(148, 209) == 209 and f(148, 213) == 209 and f(148, 256) == 209 and f(148, 261) == 209 and f(148, 262) == 262
+    bounds = [w * 18944 // 361 for w in range(1, 13)]               # 52, 104, 157, 209, 262, ...
+    for n in range(1, 600):
+        want = max([b for b in bounds if b <= n], default=n)
+        assert f(148, n) == want, n
+    assert f(0, 17) == 17 and f(148, 0) == 0

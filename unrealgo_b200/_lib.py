@@ -70,6 +70,7 @@ SIGNATURES = {
     "ug_eval_info": (C.c_int, [C.c_void_p, C.POINTER(NetInfo)]),
     "ug_eval_set_conv_ctas": (C.c_int, [C.c_void_p, C.c_int]),
     "ug_eval_efficient_batch": (C.c_int, [C.c_void_p, C.c_int]),
+    "ug_efficient_batch_for_sms": (C.c_int, [C.c_int, C.c_int]),
     "ug_eval_set_conv_impl": (C.c_int, [C.c_void_p, C.c_int]),
     "ug_eval_set_residual_split": (C.c_int, [C.c_void_p, C.c_int]),
     "ug_eval_run_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

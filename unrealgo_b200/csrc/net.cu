@@ -647,13 +647,16 @@ int ug_eval_set_conv_ctas(ug_eval* h, int ctas) {
   return 0;
 }
 
-int ug_eval_efficient_batch(const ug_eval* h, int n) {
-  if (!h || n <= 0) return n;
+int ug_eval_efficient_batch(const ug_eval* h, int n) { return h ? ug_efficient_batch_for_sms(h->sms, n) : n; }
+
+int ug_efficient_batch_for_sms(int sm_count, int n) {
+  if (sm_count < 2 || n <= 0) return n;
   // one wave of the persistent tower kernel = (SMs / 2) CTA pairs x 256 pixel rows
-  const long wave_rows = (long)(h->sms / 2) * 256;
-  const long waves = ((long)n * UG_NUM_POINTS) / wave_rows;  // full waves this batch fills
-  if (waves == 0) return n;                                  // less than one wave costs one wave whatever n is
-  const long m = waves * wave_rows / UG_NUM_POINTS;
+  const long wave_rows = (long)(sm_count / 2) * 256;
+  // the largest batch of w waves is floor(w * wave_rows / 361); take the largest w whose batch still fits in n
+  const long w = ((long)(n + 1) * UG_NUM_POINTS + wave_rows - 1) / wave_rows - 1;
+  if (w <= 0) return n;  // less than one wave costs one wave whatever n is
+  const long m = w * wave_rows / UG_NUM_POINTS;
   return (int)(m < n ? m : n);
 }
 
