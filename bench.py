@@ -59,40 +59,77 @@ def checkpoint(blocks, filters):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons during the timed region (B200_PROFILING.md recipe).  NVML through
+    pynvml when it is importable (a sample every ~2 ms, so even a 100 ms region gets dozens), else nvidia-smi."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.rows = []       # (sm_mhz, max_mhz, watts, set of reasons)
         self.stop_flag = False
+        self.source = "nvidia-smi"
 
-    def run(self):
+    def _nvml_loop(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        # CUDA_VISIBLE_DEVICES may renumber devices: ask torch for the UUID of the device in use
+        import torch
+        uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+        h = None
+        for i in range(nv.nvmlDeviceGetCount()):
+            hi = nv.nvmlDeviceGetHandleByIndex(i)
+            u = nv.nvmlDeviceGetUUID(hi)
+            u = u.decode() if isinstance(u, bytes) else u
+            if uuid in u:
+                h = hi
+        if h is None:
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        self.source = "nvml"
+        while not self.stop_flag:
+            mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            watts = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self.rows.append((mhz, mx, watts, {n for n, bit in names if mask & bit}))
+            time.sleep(0.002)
+
+    def _smi_loop(self):
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 parts = [p.strip() for p in out.strip().split(",")]
                 if len(parts) >= 7:
-                    self.rows.append(parts)
+                    reasons = {n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                  "sw_power_cap"), parts[3:7]) if v.lower().startswith("active")}
+                    self.rows.append((float(parts[0]), float(parts[1]), float(parts[2]), reasons))
             except Exception:
                 pass
             time.sleep(0.1)
 
+    def run(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            self.source = "nvidia-smi"
+            self._smi_loop()
+
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[0]) for r in self.rows)
+        sm = sorted(r[0] for r in self.rows)
         reasons = set()
         for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows),
-                "reasons": sorted(reasons)}
+            reasons |= r[3]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1],
+                "power_w_max": max(r[2] for r in self.rows), "samples": len(self.rows),
+                "reasons": sorted(reasons), "source": self.source}
 
 
 def cpu_reference(args, seconds, batch):
