@@ -19,8 +19,9 @@
 //      by TMA into shared memory (prefetched while the tile's MMAs run), results leave through per-warp
 //      swizzled staging and TMA stores — no uncoalesced per-thread global traffic.
 //
-// Warp roles (256 threads, persistent, CTA pair = cta_group::2): 0 = A-chunk + mask producer, 1 = B producer,
-// 2 = TMEM allocator + MMA issuer (leader CTA, one lane), 3 = residual producer, 4-7 = epilogue.
+// Warp roles (384 threads, persistent, CTA pair = cta_group::2): 0 = A-chunk + mask producer, 1 = B producer,
+// 2 = TMEM allocator + MMA issuer (leader CTA, one lane), 3 = residual producer, 4-11 = epilogue (two warps per
+// TMEM lane quarter).
 #include <cuda_bf16.h>
 
 #include <atomic>
@@ -44,7 +45,8 @@ constexpr int kARows = kTileM + 2 * kHalo;  // 168
 constexpr int kAccCols = 256;
 constexpr int kNA = 3;   // A chunk slots
 constexpr int kNR = 2;   // residual slots (32 columns each, hi + lo), only in kernels that read a residual
-constexpr int kNO = 2;   // per-warp output staging slots
+constexpr int kEpiWarps = 8;  // two per TMEM lane quarter
+constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kEpiCols = 32;
 constexpr int kResHalf = kTileM * kEpiCols * 2;   // 8192: 128 rows x 64 B
 constexpr int kResSlot = 2 * kResHalf;            // hi + lo
@@ -62,7 +64,7 @@ struct Cfg {
   static constexpr int kOffB = kNA * kASlot;
   static constexpr int kOffRes = kOffB + kNB * kBStage;
   static constexpr int kOffOut = kOffRes + kNRes * kResSlot;
-  static constexpr int kOffBias = kOffOut + 4 * kNO * kOutSlot;
+  static constexpr int kOffBias = kOffOut + kEpiWarps * kOutSlot;  // one staging slot (hi + lo) per epilogue warp
   static constexpr int kOffBars = kOffBias + 256 * 4;
   static constexpr int kNumBars = 2 * kNA + 2 * kNB + 2 * kNR + 2 + 2;  // (residual barriers exist in every variant)
   static constexpr int kBytes = kOffBars + kNumBars * 8 + 16;
@@ -101,7 +103,7 @@ __device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, bool 
 // HEADS > 0: last layer of the tower — instead of storing the activation, every thread feeds its row's fp32
 // results into the HEADS 1x1 head convolutions (policy channels first) and writes relu(head) to args.head_out.
 template <int CK, bool F16, int RES, bool OUT_LO, int HEADS>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmRhi, const __grid_constant__ CUtensorMap tmRlo,
                   const __grid_constant__ CUtensorMap tmOhi, const __grid_constant__ CUtensorMap tmOlo,
@@ -159,7 +161,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int s = 0; s < kNR; ++s) { mbar_init(&res_full[s], 1); mbar_init(&res_empty[s], 4); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 8);  // one elected lane per epilogue warp of both CTAs
+      mbar_init(&acc_empty[s], 2 * kEpiWarps);  // one elected lane per epilogue warp of both CTAs
     }
     fence_barrier_init();
   }
@@ -339,12 +341,16 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ===================== epilogue =====================
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32)
+    // Eight warps: a warp may only read the TMEM lane quarter (warp % 4), so two warps share each quarter and
+    // split the 32-column steps between them (group 0: steps 0, 2, 4, ...; group 1: steps 1, 3, 5, ...).  The
+    // epilogue of a layer's last tile is not hidden behind any MMA, so its length is paid once per launch.
+    const int quarter = warp & 3;          // TMEM lanes [32*quarter, +32)
+    const int grp = (warp - 4) >> 2;       // 0 or 1
     const float act_floor = args.relu ? 0.f : -3.0e38f;  // ReLU as a branch-free max
-    uint8_t* my_out = smOut + quarter * (kNO * kOutSlot);
+    uint8_t* my_out = smOut + (grp * 4 + quarter) * kOutSlot;  // one staging slot (hi + lo) per warp
     const int row_l = quarter * 32 + lane;   // row inside the CTA tile
     const int sw = (row_l >> 1) & 3;         // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
-    int rs = 0, os = 0;
+    const int rs = grp;                      // residual slot: step c uses slot c % kNR, and kNR == 2
     uint32_t phr = 0;
     int it = 0;
     const bool prof = args.prof != nullptr && leader && warp == 4;
@@ -360,7 +366,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float hacc[HEADS > 0 ? HEADS : 1];
 #pragma unroll
       for (int h = 0; h < (HEADS > 0 ? HEADS : 1); ++h) hacc[h] = 0.f;
-      for (int c0 = 0; c0 < cout; c0 += kEpiCols) {
+      for (int c0 = grp * kEpiCols; c0 < cout; c0 += 2 * kEpiCols) {
         uint32_t v[32];
         tmem_ld_32x32(t_row + c0, v);
         uint4 rh[4], rl[4];
@@ -375,25 +381,16 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&res_empty[rs]);
-          if (++rs == kNR) { rs = 0; phr ^= 1; }
+          phr ^= 1;
         }
         tmem_ld_wait();
-        if (c0 + kEpiCols >= cout) {
-          // accumulator fully read: hand the TMEM stage back before the arithmetic and the stores
+        if (c0 + 2 * kEpiCols >= cout) {
+          // this warp has read its share of the accumulator: hand the TMEM stage back before the arithmetic
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
         }
-        // staging slot must have been read by the TMA store issued kNO iterations ago
-        if constexpr (HEADS == 0) {
-          if (lane == 0) {
-            const long long t0 = prof ? clock64() : 0;
-            bulk_wait_group_read<kNO - 1>();
-            if (prof) w_st += clock64() - t0;
-          }
-          __syncwarp();
-        }
-        uint8_t* orow = my_out + os * kOutSlot + lane * 64;
+        uint4 oh[4], ol[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t packed[4], packed_lo[4];
@@ -434,29 +431,37 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               packed_lo[e] = pack2_sat<F16>(f0 - hi.x, f1 - hi.y);
             }
           }
-          if constexpr (HEADS == 0) {
-            *reinterpret_cast<uint4*>(orow + ((q ^ sw) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            if constexpr (has_out_lo)
-              *reinterpret_cast<uint4*>(orow + kOutHalf + ((q ^ sw) << 4)) =
-                  make_uint4(packed_lo[0], packed_lo[1], packed_lo[2], packed_lo[3]);
-          }
+          oh[q] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          if constexpr (has_out_lo) ol[q] = make_uint4(packed_lo[0], packed_lo[1], packed_lo[2], packed_lo[3]);
         }
         if constexpr (HEADS == 0) {
+          // the staging slot must have been read by this warp's previous TMA store (its arithmetic is already done)
+          if (lane == 0) {
+            const long long t0 = prof ? clock64() : 0;
+            bulk_wait_group_read<0>();
+            if (prof) w_st += clock64() - t0;
+          }
+          __syncwarp();
+          uint8_t* orow = my_out + lane * 64;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            *reinterpret_cast<uint4*>(orow + ((q ^ sw) << 4)) = oh[q];
+            if constexpr (has_out_lo) *reinterpret_cast<uint4*>(orow + kOutHalf + ((q ^ sw) << 4)) = ol[q];
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             const int row0 = mc + quarter * 32;
             if (row0 < args.M) {  // rows past M inside the box are clipped by the tensor map (its height is M_alloc)
-              tma_store_2d(&tmOhi, my_out + os * kOutSlot, c0, row0);
-              if (has_out_lo) tma_store_2d(&tmOlo, my_out + os * kOutSlot + kOutHalf, c0, row0);
+              tma_store_2d(&tmOhi, my_out, c0, row0);
+              if (has_out_lo) tma_store_2d(&tmOlo, my_out + kOutHalf, c0, row0);
             }
             bulk_commit_group();
           }
-          if (++os == kNO) os = 0;
         }
       }
       if constexpr (HEADS == 0) {
-        // tile-granular mode: publish "this warp's 32 rows of the tile are in memory" (8 counts complete a tile)
+        // tile-granular mode: publish "this warp's share of the tile is in memory" (16 counts complete a tile)
         if (args.flags_out != nullptr && lane == 0) {
           bulk_wait_group_all();     // the TMA stores of this tile have completed, not merely been read
           fence_proxy_async_all();   // async-proxy writes before the generic-proxy release below
@@ -464,12 +469,23 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       if constexpr (HEADS > 0) {
-        // feat[row][h] = relu(head conv + folded batch-norm offset): 4*HEADS bytes per row, rows consecutive
-        const long row = (long)mc + row_l;
-        if (row < args.M) {
+        // Each group holds the head dot products over its half of the channels.  Group 1 hands its partial sums to
+        // group 0 through shared memory (the unused output staging, double-buffered by tile parity; one named
+        // barrier per tile: group 1 cannot reach the buffer again before group 0 has passed the next barrier).
+        float* xch = reinterpret_cast<float*>(smOut) + (it & 1) * (kTileM * 4) + row_l * 4;
+        if (grp == 1) {
 #pragma unroll
-          for (int h = 0; h < HEADS; ++h)
-            args.head_out[row * HEADS + h] = fmaxf(hacc[h] + __ldg(args.head_b + h), 0.f);
+          for (int h = 0; h < HEADS; ++h) xch[h] = hacc[h];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (grp == 0) {
+          // feat[row][h] = relu(head conv + folded batch-norm offset): 4*HEADS bytes per row, rows consecutive
+          const long row = (long)mc + row_l;
+          if (row < args.M) {
+#pragma unroll
+            for (int h = 0; h < HEADS; ++h)
+              args.head_out[row * HEADS + h] = fmaxf(hacc[h] + xch[h] + __ldg(args.head_b + h), 0.f);
+          }
         }
       }
     }
@@ -530,7 +546,7 @@ cudaError_t launch_v2(const ConvV2Maps& m, const ConvV2Args& a, int sms, cudaStr
   if (clusters > a.num_tiles) clusters = a.num_tiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * 2);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];

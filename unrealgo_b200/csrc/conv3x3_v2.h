@@ -24,7 +24,7 @@ struct ConvV2Args {
   int desc_mode;          // bring-up knobs: bit 0 set the descriptor's matrix-base-offset field for shifted A tiles;
                           // bit 1 unmasked MMA form and bit 2 no tap shift (both give wrong results: timing probes)
   // Tile-granular dependencies between consecutive layers (all null/0: whole-grid dependency through
-  // griddepcontrol.wait).  Counters are per 256-row tile, +8 when a layer has stored the tile (one count per epilogue
+  // griddepcontrol.wait).  Counters are per 256-row tile, +16 when a layer has stored the tile (one count per epilogue
   // warp of the CTA pair), zeroed by the caller at the start of every pass through the tower.
   const uint32_t* flags_in;   // previous layer's counters: tile t may start once tiles t-1..t+1 reached target_in
   const uint32_t* flags_res;  // counters of the layer that wrote the residual tile (two layers back)

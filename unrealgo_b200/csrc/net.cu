@@ -397,9 +397,9 @@ int ug_eval::enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, con
     a.tile_rot = (layer * 9) % 74;  // 361 tiles on 74 pairs leave 9 pairs one tile short: shift that group each layer
     a.flags_out = F[layer & 1];
     a.flags_in = layer > 0 ? F[(layer - 1) & 1] : nullptr;
-    a.target_in = layer > 0 ? 8u * (uint32_t)((layer - 1) / 2 + 1) : 0u;
+    a.target_in = layer > 0 ? 16u * (uint32_t)((layer - 1) / 2 + 1) : 0u;  // 16 epilogue warps per CTA pair
     a.flags_res = has_res ? F[layer & 1] : nullptr;   // written two layers back, same parity
-    a.target_res = has_res ? 8u * (uint32_t)(layer / 2) : 0u;
+    a.target_res = has_res ? 16u * (uint32_t)(layer / 2) : 0u;
   };
   // stem: writes S[0] (hi [+ lo])
   a.cin = kCinPad;
