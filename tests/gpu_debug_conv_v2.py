@@ -101,6 +101,15 @@ if __name__ == "__main__":
         print("stem :", run(256, 32, 256, ALL, 0, False, True), flush=True)
         print("conv1:", run(256, 256, 256, ALL, 0, False, False), flush=True)
         print("conv2:", run(256, 256, 256, ALL, 0, True, True), flush=True)
+    if which == "power":
+        # sustained (power-capped) launch time of one tower conv, with and without the weight traffic
+        import subprocess
+        for dm, name in ((8, "normal"), (8 | 16, "no B reloads (wrong results, timing only)")):
+            for rep in range(3):
+                msg = run(256, 256, 256, ALL, dm, True, True, iters=12000 if rep == 2 else 3000)
+            smi = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader"],
+                                 capture_output=True, text=True).stdout.strip()
+            print(f"{name}: {msg.split('|')[-1].strip()}  (after the loop: {smi})", flush=True)
     if which == "probe":
         for dm in (0, 2, 4, 6):
             print(f"probe desc_mode={dm} conv1:", run(256, 256, 256, ALL, dm, False, False, iters=20, prof=True), flush=True)

@@ -968,7 +968,7 @@ int ug_k_conv3x3_v2(int device, const void* d_in, const void* d_w, const float* 
   a.has_res = d_res_hi != nullptr;
   a.has_res_lo = d_res_lo != nullptr;
   a.has_out_lo = d_out_lo != nullptr;
-  a.desc_mode = desc_mode & 7;
+  a.desc_mode = desc_mode & (7 | 16);
   a.pdl = (desc_mode & 8) ? 1 : 0;  // timing probe: programmatic dependent launch between the repeated launches
   a.prof = d_prof;
   cudaStream_t s = nullptr;
