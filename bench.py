@@ -214,8 +214,9 @@ def emit(obj):
 
 
 def main():
-    global _REAL_STDOUT
+    global _REAL_STDOUT, METRIC
     args = parse()
+    METRIC = f"nn_positions_per_s_batch{args.batch}_{args.blocks}block"  # the default is BASELINE.json's metric
     # Libraries print on stdout behind our back (NCCL writes its version line there): park the real stdout and
     # route everything else to stderr, so that stdout carries exactly the JSON line.
     sys.stdout.flush()
