@@ -7,9 +7,12 @@
 // Stage 1 (head_conv): both 1x1 convolutions (+ folded batch-norm + ReLU) in one pass over the final tower
 //   activation: one warp per board point, 16-byte loads, warp-shuffle reduction.  HBM-bound: reads
 //   361*C*2 bytes per position, writes 361*(pc+vc) floats.
-// Stage 2 (head_fc): per CTA kPosPerCta positions: policy FC -> softmax (optionally masked and
-//   renormalised), value FC -> ReLU -> FC -> tanh -> value_transform.  Weights stream once per CTA from L2.
+// Stage 2 (head_fc): policy FC -> softmax (optionally masked and renormalised), value FC -> ReLU -> FC -> tanh ->
+//   value_transform.  Default: head_fc_cluster_kernel (4-CTA cluster per 8 positions, reductions through distributed
+//   shared memory); head_fc_kernel (one CTA per 4 positions) is the single-CTA variant.
 #include <math_constants.h>
+
+#include <cstdlib>
 
 #include "kernels.h"
 #include "numfmt.cuh"
@@ -274,6 +277,258 @@ __global__ void __launch_bounds__(kFcThreads) head_fc_kernel(const float* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Clustered variant of stage 2: a cluster of 4 CTAs shares 8 positions.  Every CTA owns a quarter of the policy
+// columns and of the value hidden units (so the FC weights are read once per cluster, a quarter per CTA), the K
+// range of every column is split over several threads, and the softmax / legal-mask / value reductions run across
+// the cluster through distributed shared memory.  Same arithmetic as head_fc_kernel up to summation order.
+constexpr int kClu = 4;
+constexpr int kCluPos = 8;                     // positions per cluster
+constexpr int kCluThreads = 512;
+constexpr int kPolKSplit = 4, kValKSplit = 2;
+constexpr int kColsPerCta = (kMoves + kClu - 1) / kClu;  // 91
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store v at the same shared-memory offset in CTA `cta` of this cluster
+__device__ __forceinline__ void dsmem_store(float* local, uint32_t cta, float v) {
+  uint32_t la = static_cast<uint32_t>(__cvta_generic_to_shared(local)), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+
+// acc[p] += sum_{i<len} f[p*fstride + i] * w[i*stride], 8 positions.  Software-pipelined: the 16 weight loads of
+// the next step are in flight while the current 16 are consumed; features are 16-byte broadcast reads.
+__device__ __forceinline__ void fc_column8(const float* __restrict__ wcol, int stride, const float* f, int fstride,
+                                           int len, float (&acc)[kCluPos]) {
+  const int full = len & ~15;
+  float cur[16], nxt[16];
+  if (full > 0) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) cur[u] = __ldg(wcol + (size_t)u * stride);
+  }
+  for (int i = 0; i < full; i += 16) {
+    if (i + 16 < full) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) nxt[u] = __ldg(wcol + (size_t)(i + 16 + u) * stride);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int p = 0; p < kCluPos; ++p) {
+        const float4 x = *reinterpret_cast<const float4*>(f + p * fstride + i + 4 * g);
+        acc[p] = fmaf(x.x, cur[4 * g], acc[p]);
+        acc[p] = fmaf(x.y, cur[4 * g + 1], acc[p]);
+        acc[p] = fmaf(x.z, cur[4 * g + 2], acc[p]);
+        acc[p] = fmaf(x.w, cur[4 * g + 3], acc[p]);
+      }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) cur[u] = nxt[u];
+  }
+  for (int i = full; i < len; ++i) {
+    const float wv = __ldg(wcol + (size_t)i * stride);
+#pragma unroll
+    for (int p = 0; p < kCluPos; ++p) acc[p] = fmaf(f[p * fstride + i], wv, acc[p]);
+  }
+}
+
+__global__ void __cluster_dims__(kClu, 1, 1) __launch_bounds__(kCluThreads)
+head_fc_cluster_kernel(const float* __restrict__ feat, HeadWeights hw, const uint32_t* __restrict__ legal, int vt,
+                       float* __restrict__ policy, float* __restrict__ value, int n) {
+  extern __shared__ float sm[];
+  const int pc = hw.pc, vc = hw.vc, hc = pc + vc, H = hw.H;
+  const int pin = kPoints * pc, vin = kPoints * vc;
+  const int pstr = (pin + 3) & ~3, vstr = (vin + 3) & ~3;
+  const int hper = (H + kClu - 1) / kClu;       // hidden units of this CTA
+  float* fp = sm;                               // [8][pstr]
+  float* fv = fp + kCluPos * pstr;              // [8][vstr]
+  float* part = fv + kCluPos * vstr;            // [kPolKSplit][8][96] partial logits
+  float* vpart = part + kPolKSplit * kCluPos * 96;  // [kValKSplit][8][hper] partial hidden units
+  float* logit = vpart + kValKSplit * kCluPos * hper;  // [8][96]
+  float* hid = logit + kCluPos * 96;            // [8][hper]
+  float* xch = hid + kCluPos * hper;            // [4 kinds][kClu][8]: max, sum, legal sum, value partial (DSMEM targets)
+  const uint32_t rank = cluster_rank();
+  const int p0 = (blockIdx.x / kClu) * kCluPos;
+  const int np = min(kCluPos, n - p0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c0 = (int)rank * kColsPerCta;
+  const int ncol = max(0, min(kColsPerCta, kMoves - c0));
+  const int h0 = (int)rank * hper;
+  const int nh = max(0, min(hper, H - h0));
+
+  {  // features of the cluster's 8 positions -> shared memory, 4 independent loads in flight per thread
+    const int total = kCluPos * kPoints * hc;
+    for (int base = 0; base < total; base += 4 * (int)blockDim.x) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * (int)blockDim.x + tid;
+        const int p = i / (kPoints * hc);
+        v[u] = (i < total && p < np) ? __ldg(feat + (size_t)p0 * kPoints * hc + i) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * (int)blockDim.x + tid;
+        if (i < total) {
+          const int p = i / (kPoints * hc);
+          const int r = i - p * (kPoints * hc);
+          const int point = r / hc, c = r - point * hc;
+          if (c < pc) fp[p * pstr + point * pc + c] = v[u];
+          else fv[p * vstr + point * vc + (c - pc)] = v[u];
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- partial dot products, both FCs at once: policy threads [0, 4*91) (K split in 4), value threads
+  //      [384, 384 + 2*hper) (K split in 2); every thread walks ~181 weight rows for 8 positions
+  if (tid < kPolKSplit * kColsPerCta) {
+    const int col = tid % kColsPerCta, ks = tid / kColsPerCta;
+    float acc[kCluPos];
+#pragma unroll
+    for (int p = 0; p < kCluPos; ++p) acc[p] = 0.f;
+    const int klen = (((pin + kPolKSplit - 1) / kPolKSplit) + 3) & ~3;
+    const int k0 = ks * klen, k1 = min(pin, k0 + klen);
+    if (col < ncol && k0 < k1) fc_column8(hw.pfc_w + (size_t)k0 * kMoves + c0 + col, kMoves, fp + k0, pstr, k1 - k0, acc);
+#pragma unroll
+    for (int p = 0; p < kCluPos; ++p) part[(ks * kCluPos + p) * 96 + col] = acc[p];
+  } else if (tid >= 384) {
+    for (int t = tid - 384; t < kValKSplit * hper; t += kCluThreads - 384) {
+      const int u = t % hper, ks = t / hper;
+      float acc[kCluPos];
+#pragma unroll
+      for (int p = 0; p < kCluPos; ++p) acc[p] = 0.f;
+      const int klen = (((vin + kValKSplit - 1) / kValKSplit) + 3) & ~3;
+      const int k0 = ks * klen, k1 = min(vin, k0 + klen);
+      if (u < nh && k0 < k1) fc_column8(hw.v1_w + (size_t)k0 * H + h0 + u, H, fv + k0, vstr, k1 - k0, acc);
+#pragma unroll
+      for (int p = 0; p < kCluPos; ++p) vpart[(ks * kCluPos + p) * hper + u] = acc[p];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kCluPos * kColsPerCta; i += blockDim.x) {
+    const int p = i / kColsPerCta, col = i - p * kColsPerCta;
+    float sacc = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < kPolKSplit; ++ks) sacc += part[(ks * kCluPos + p) * 96 + col];
+    logit[p * 96 + col] = col < ncol ? sacc + __ldg(hw.pfc_b + c0 + col) : -CUDART_INF_F;
+  }
+  for (int i = tid; i < kCluPos * hper; i += blockDim.x) {
+    const int p = i / hper, u = i - p * hper;
+    float sacc = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < kValKSplit; ++ks) sacc += vpart[(ks * kCluPos + p) * hper + u];
+    hid[p * hper + u] = u < nh ? fmaxf(sacc + __ldg(hw.v1_b + h0 + u), 0.f) : 0.f;
+  }
+  __syncthreads();
+
+  // ---- per position (warp p): local max of the logits, local value partial; publish to every CTA of the cluster
+  float* x_max = xch;                       // [kClu][8]
+  float* x_sum = xch + kClu * kCluPos;
+  float* x_leg = xch + 2 * kClu * kCluPos;
+  float* x_val = xch + 3 * kClu * kCluPos;
+  if (warp < kCluPos) {
+    const int p = warp;
+    float m = -CUDART_INF_F, vpart = 0.f;
+    for (int c = lane; c < ncol; c += 32) m = fmaxf(m, logit[p * 96 + c]);
+    for (int u = lane; u < nh; u += 32) vpart = fmaf(hid[p * hper + u], __ldg(hw.v2_w + h0 + u), vpart);
+    m = warp_max(m);
+    vpart = warp_sum(vpart);
+    if (lane < kClu) {
+      dsmem_store(x_max + rank * kCluPos + p, lane, m);
+      dsmem_store(x_val + rank * kCluPos + p, lane, vpart);
+    }
+  }
+  cluster_barrier();
+  float e_keep[3] = {0.f, 0.f, 0.f};  // this lane's exponentials (ncol <= 96 = 3 per lane)
+  if (warp < kCluPos) {
+    const int p = warp;
+    float gmax = -CUDART_INF_F;
+#pragma unroll
+    for (int r = 0; r < kClu; ++r) gmax = fmaxf(gmax, x_max[r * kCluPos + p]);
+    float lsum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int c = lane + 32 * k;
+      if (c < ncol) {
+        e_keep[k] = hw.policy_softmax ? expf(logit[p * 96 + c] - gmax) : logit[p * 96 + c];
+        lsum += e_keep[k];
+      }
+    }
+    lsum = warp_sum(lsum);
+    if (lane < kClu) dsmem_store(x_sum + rank * kCluPos + p, lane, lsum);
+    if (rank == 0 && lane == 0 && p < np) {  // value: tanh(w2 . hidden + b2), value_transform
+      float v = __ldg(hw.v2_b);
+#pragma unroll
+      for (int r = 0; r < kClu; ++r) v += x_val[r * kCluPos + p];
+      if (hw.value_tanh) v = tanhf(v);
+      if (vt == UG_TR_FLIP_SIGN) v = -v;
+      else if (vt == UG_TR_FLIP_PROB) v = 1.f - v;
+      value[p0 + p] = v;
+    }
+  }
+  cluster_barrier();
+  if (warp < kCluPos) {
+    const int p = warp;
+    float tot = 0.f;
+#pragma unroll
+    for (int r = 0; r < kClu; ++r) tot += x_sum[r * kCluPos + p];
+    const float inv = hw.policy_softmax ? 1.f / tot : 1.f;
+    float lleg = 0.f;
+    bool ok[3] = {true, true, true};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int c = lane + 32 * k;
+      e_keep[k] *= inv;
+      if (legal != nullptr && c < ncol && p < np) {
+        const int j = c0 + c;
+        ok[k] = (__ldg(legal + (size_t)(p0 + p) * UG_MASK_WORDS + (j >> 5)) >> (j & 31)) & 1u;
+        if (ok[k]) lleg += e_keep[k];
+      }
+    }
+    if (legal != nullptr) {  // UpdatePrior: prior = p[idx] / sum over legal children; illegal moves get 0
+      lleg = warp_sum(lleg);
+      if (lane < kClu) dsmem_store(x_leg + rank * kCluPos + p, lane, lleg);
+    }
+    if (legal == nullptr && p < np) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int c = lane + 32 * k;
+        if (c < ncol) policy[(size_t)(p0 + p) * kMoves + c0 + c] = e_keep[k];
+      }
+    }
+    if (legal != nullptr) {  // illegal moves get 0; the legal ones are renormalised after one more exchange
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (!ok[k]) e_keep[k] = 0.f;
+    }
+  }
+  if (legal != nullptr) {
+    cluster_barrier();
+    if (warp < kCluPos && warp < np) {
+      const int p = warp;
+      float lt = 0.f;
+#pragma unroll
+      for (int r = 0; r < kClu; ++r) lt += x_leg[r * kCluPos + p];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int c = lane + 32 * k;
+        if (c < ncol) policy[(size_t)(p0 + p) * kMoves + c0 + c] = e_keep[k] / lt;
+      }
+    }
+  }
+  // no CTA may exit while a peer can still write into its shared memory
+  cluster_barrier();
+}
+
 template <typename T>
 void head_conv_dispatch(const T* act, const T* act_lo, int f16, const HeadWeights& w, float* feat, int n,
                         cudaStream_t s) {
@@ -304,9 +559,34 @@ void launch_head_conv(const void* act, const void* act_lo, int act_fmt, const He
                                          static_cast<const __nv_bfloat16*>(act_lo), act_fmt == 2, w, feat, n, s);
 }
 
+static bool use_cluster_fc() {
+  static const bool on = [] {
+    const char* e = getenv("UGEVAL_HEAD_FC_CLUSTER");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* legal, int vt, float* policy,
                     float* value, int n, cudaStream_t s) {
   if (n <= 0) return;
+  const int hper = (w.H + kClu - 1) / kClu;
+  if (use_cluster_fc() && hper <= 96 && w.pc + w.vc <= kMaxHeadCh) {
+    const int pstr = (kPoints * w.pc + 3) & ~3, vstr = (kPoints * w.vc + 3) & ~3;
+    const size_t smem = sizeof(float) * ((size_t)kCluPos * (pstr + vstr) + (size_t)kPolKSplit * kCluPos * 96 +
+                                         (size_t)kValKSplit * kCluPos * hper + (size_t)kCluPos * 96 +
+                                         (size_t)kCluPos * hper + 4 * kClu * kCluPos);
+    static size_t set_c[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && smem > set_c[dev & 63]) {
+      cudaFuncSetAttribute(head_fc_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      set_c[dev & 63] = smem;
+    }
+    const int clusters = (n + kCluPos - 1) / kCluPos;
+    head_fc_cluster_kernel<<<clusters * kClu, kCluThreads, smem, s>>>(feat, w, legal, vt, policy, value, n);
+    return;
+  }
   const size_t smem =
       sizeof(float) * ((size_t)kPosPerCta * (((kPoints * w.pc + 3) & ~3) + ((kPoints * w.vc + 3) & ~3) + w.H + kPolThreads) + 32);
   static size_t smem_set[64] = {};  // per device (function attributes are per device)
