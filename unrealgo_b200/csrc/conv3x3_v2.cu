@@ -601,7 +601,9 @@ int conv3x3_v2_smem_bytes(int ck) { return ck == 64 ? Cfg<64, true>::kSmem : Cfg
 
 cudaError_t conv3x3_v2_launch(const ConvV2Maps& maps, ConvV2Args a, int ck, int device, int sms,
                               cudaStream_t stream) {
-  if (a.cout > 256 || a.cout % 32 != 0 || a.cin % ck != 0 || (ck != 64 && ck != 32)) return cudaErrorInvalidValue;
+  // cout: whole pairs of 32-column epilogue steps (the two epilogue warp groups alternate steps, and the residual
+  // ring pairs a step's parity with a slot)
+  if (a.cout > 256 || a.cout % 64 != 0 || a.cin % ck != 0 || (ck != 64 && ck != 32)) return cudaErrorInvalidValue;
   if (!maps.a || !maps.w || !maps.out_hi) return cudaErrorInvalidValue;
   if (!upload_masks(device)) return cudaErrorUnknown;  // no-op after conv3x3_v2_prepare()
   a.num_tiles = (a.M + 2 * kTileM - 1) / (2 * kTileM);

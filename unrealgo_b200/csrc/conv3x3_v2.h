@@ -17,7 +17,7 @@ struct ConvV2Args {
   int head_channels;
   int M;                  // n * 361 output pixels
   int cin;                // input channels as stored (multiple of ck)
-  int cout;               // <= 256, multiple of 32
+  int cout;               // <= 256, multiple of 64
   int relu;
   int f16;                // operands/outputs are fp16 (else bf16)
   int has_res, has_res_lo, has_out_lo;
