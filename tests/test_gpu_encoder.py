@@ -37,6 +37,10 @@ def test_transform_feature_bool_semantics(ev):
 
 def test_encoder_many_positions(ev):
     import oracle
-    packed, planes = oracle.synthetic_positions(3000, seed=77)
-    assert np.array_equal(ev.encode_planes(packed), planes)
-    assert np.array_equal(ev.encode_nhwc(packed), oracle.transform_feature(planes, 0, True))
+    total = 0
+    for seed in (77, 78, 79):  # 10 500 seeded positions, in evaluator-sized chunks
+        packed, planes = oracle.synthetic_positions(3500, seed=seed)
+        assert np.array_equal(ev.encode_planes(packed), planes)
+        assert np.array_equal(ev.encode_nhwc(packed), oracle.transform_feature(planes, 0, True))
+        total += len(packed)
+    assert total >= 10000
