@@ -247,7 +247,9 @@ struct Board {
     for (int idx = 0; idx < 361; ++idx) {
       if (((masks[0][idx >> 5] | masks[1][idx >> 5]) >> (idx & 31)) & 1u) continue;
       const int b = to_b(idx);
-      if (!simple_eye(b, to_play) && legal(b, to_play)) {
+      // fast path: an empty neighbour makes the move legal (it keeps a liberty) and rules out an eye
+      const bool open = color[b - W] == EMPTY || color[b - 1] == EMPTY || color[b + 1] == EMPTY || color[b + W] == EMPTY;
+      if (open ? b != ko : (!simple_eye(b, to_play) && legal(b, to_play))) {
         moves[n++] = (uint16_t)idx;
         legal_mask[idx >> 5] |= 1u << (idx & 31);
       }
