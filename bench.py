@@ -335,7 +335,7 @@ def main():
     # self-play playouts/s (BASELINE configs[2]/[3]): games sharded per GPU, no collective on the data path
     sp = None
     if not args.no_selfplay:
-        threads = args.sp_threads or max(2, min(12, (os.cpu_count() or 8) // max(world, 1) - 1))
+        threads = args.sp_threads or max(2, min(12, (os.cpu_count() or 8) // max(world, 1)))
         if world > 1:
             dist.barrier()
         st, _ = selfplay(ev, games=args.sp_games, threads=threads, playouts_per_move=args.sp_playouts,
