@@ -61,8 +61,8 @@ struct ug_eval {
   int conv_impl = 2;  // 1 = im2col kernel (conv3x3_tc.cu), 2 = resident-tile kernel (conv3x3_v2.cu)
   bool fuse_heads = true;   // head 1x1 convolutions in the last tower layer's epilogue (UGEVAL_FUSE_HEADS=0 disables)
   // Layers depend on each other tile by tile (per-tile completion counters) instead of grid by grid.  Measured
-  // +0..1 % at batch 256 (the tail it can recover is the 2.4 % of 361 tiles on 74 CTA pairs), so it stays opt-in:
-  // UGEVAL_TILE_DEPS=1.
+  // -2 % at batch 256 against the final kernel (the tail it can recover is the 2.4 % of 361 tiles on 74 CTA pairs):
+  // an experiment kept behind UGEVAL_TILE_DEPS=1.
   bool tile_deps = false;
   bool use_pdl = true;      // programmatic dependent launch between tower layers (UGEVAL_PDL=0 disables)
   bool resid_split = true;  // carry the residual stream as hi + lo 16-bit pair (numerics)
