@@ -247,6 +247,15 @@ int ug_tfrecord_write_example_named(ug_tfrecord* w, const char* feature_name, co
 int ug_tfrecord_flush(ug_tfrecord* w);      /* Flush(), .cc:34-37 */
 int64_t ug_tfrecord_close(ug_tfrecord* w);  /* ~DlTFRecordWriter, .cc:24-32; returns the number of records written */
 
+/* ------------------------------------------------------------------ checkpoint info files (DlCheckPoint) */
+/* GetCheckPointInfo, funcapproximator/DlCheckPoint.cc:162-172: three lines — name, sha1, url.  0 ok; 1 when the file is
+ * missing or has fewer than three lines (outputs untouched, as the reference). */
+int ug_ckptinfo_read(const char* path, char* name, char* sha1, char* url, int cap);
+/* WriteCheckpointInfo, .cc:188-203 (no newline after the url); 1 when the file exists and override_if_exists is 0 */
+int ug_ckptinfo_write(const char* path, const char* name, const char* sha1, const char* url, int override_if_exists);
+/* CheckDefaultCheckPoint, .cc:130-137: <prefix>.index and <prefix>.data-00000-of-00001 both exist */
+int ug_checkpoint_files_exist(const char* prefix);
+
 /* ------------------------------------------------------------------ dlcfg (DlConfig) */
 /* DlConfig(filename) + parse(), funcapproximator/DlConfig.cc:20-41. A missing file yields an empty map. */
 ug_dlcfg* ug_dlcfg_open(const char* path);

@@ -97,3 +97,32 @@ def test_40_block_graph_walk():
     tfformat.write_metagraph(os.path.join(d, "big.meta"), gd)
     info = inspect_model(os.path.join(d, "big.meta"))
     assert info["blocks"] == 40 and len(info["tower"]) == 80
+
+
+def test_checkpoint_info_file_round_trip(tmp_path):
+    """DlCheckPoint's three-line info file (funcapproximator/DlCheckPoint.cc:162-203) and the bundle-presence check
+    (:130-137) that gate a checkpoint hot swap."""
+    import ctypes as C
+
+    from unrealgo_b200 import _lib, tfformat
+    lib = _lib.load()
+    path = str(tmp_path / "bestcheckpoint.info").encode()
+    bufs = [C.create_string_buffer(512) for _ in range(3)]
+    assert lib.ug_ckptinfo_read(path, *bufs, 512) == 1                      # missing file: outputs untouched
+    assert lib.ug_ckptinfo_write(path, b"ckpt-1200", b"da39a3ee5e6b4b0d3255bfef95601890afd80709",
+                                 b"http://host/ckpt-1200.zip", 1) == 0
+    assert open(path, "rb").read() == (b"ckpt-1200\nda39a3ee5e6b4b0d3255bfef95601890afd80709\n"
+                                       b"http://host/ckpt-1200.zip")      # no newline after the url
+    assert lib.ug_ckptinfo_read(path, *bufs, 512) == 0
+    assert [b.value for b in bufs] == [b"ckpt-1200", b"da39a3ee5e6b4b0d3255bfef95601890afd80709",
+                                       b"http://host/ckpt-1200.zip"]
+    assert lib.ug_ckptinfo_write(path, b"other", b"", b"", 0) == 1          # exists, no override
+    assert lib.ug_ckptinfo_read(path, *bufs, 512) == 0 and bufs[0].value == b"ckpt-1200"
+    short = str(tmp_path / "short.info")
+    open(short, "w").write("only\ntwo")
+    assert lib.ug_ckptinfo_read(short.encode(), *bufs, 512) == 1           # fewer than three lines: ignored
+    # bundle presence
+    meta, prefix = tfformat.write_synthetic_checkpoint(str(tmp_path / "ck"), 1, 64, seed=1)
+    assert lib.ug_checkpoint_files_exist(prefix.encode()) == 1
+    assert lib.ug_checkpoint_files_exist((prefix + "-nope").encode()) == 0
+    assert lib.ug_checkpoint_files_exist(b"") == 0

@@ -115,6 +115,9 @@ SIGNATURES = {
                                                   C.c_size_t, C.c_char_p, C.c_float]),
     "ug_tfrecord_flush": (C.c_int, [C.c_void_p]),
     "ug_tfrecord_close": (C.c_int64, [C.c_void_p]),
+    "ug_ckptinfo_read": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+    "ug_ckptinfo_write": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+    "ug_checkpoint_files_exist": (C.c_int, [C.c_char_p]),
     "ug_dlcfg_open": (C.c_void_p, [C.c_char_p]),
     "ug_dlcfg_close": (None, [C.c_void_p]),
     "ug_dlcfg_get": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
