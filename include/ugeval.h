@@ -171,6 +171,10 @@ int ug_k_conv3x3_v2(int device, const void* d_in, const void* d_w, const float* 
                     const void* d_res_lo, void* d_out_hi, void* d_out_lo, int n, int n_alloc, int cin, int cout,
                     int relu, int f16, int desc_mode, int iters, float* ms_out, long long* d_prof);
 
+/* planning probe: clusters of `cluster_size` CTAs of the tower kernel that fit on the device at once (a part that
+ * strands SM pairs for clusters of 4 returns fewer than SMs/4) */
+int ug_debug_max_active_clusters(int device, int cluster_size);
+
 /* ------------------------------------------------------------------ leaf-batching queue (Q1) */
 /* Replaces EvalBuffer/EvalMsg + NetworkEvalThread's spin loop (search/UctSearch.h:59-72,126-130;
  * search/UctSearch.cpp:164-205): lock-free multi-producer ring, the consumer thread gathers up to max_batch

@@ -92,6 +92,7 @@ SIGNATURES = {
     "ug_k_conv3x3_v2": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_float), C.c_void_p]),
+    "ug_debug_max_active_clusters": (C.c_int, [C.c_int, C.c_int]),
     "ug_queue_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "ug_queue_destroy": (None, [C.c_void_p]),
     "ug_queue_submit": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_void_p]),

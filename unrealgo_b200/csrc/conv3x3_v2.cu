@@ -592,6 +592,28 @@ cudaError_t dispatch_v2(const ConvV2Maps& m, const ConvV2Args& a, int sms, cudaS
 
 bool conv3x3_v2_prepare(int device) { return upload_masks(device); }
 
+int conv3x3_v2_max_active_clusters(int cluster_size) {
+  auto kfn = conv3x3_v2_kernel<64, true, 2, true, 0>;
+  constexpr int smem = Cfg<64, true>::kSmem;
+  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+  if (cluster_size > 8 &&
+      cudaFuncSetAttribute(kfn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return -1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(148 / cluster_size * cluster_size);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kfn, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return n;
+}
+
 bool conv3x3_v2_can_fuse_heads(int ck, int has_res, int has_res_lo, int has_out_lo, int head_channels) {
   if (ck != 64 || head_channels != 3 || !has_res) return false;
   return (has_res_lo && has_out_lo) || (!has_res_lo && !has_out_lo);

@@ -57,5 +57,7 @@ int conv3x3_v2_smem_bytes(int ck);
 bool conv3x3_v2_can_fuse_heads(int ck, int has_res, int has_res_lo, int has_out_lo, int head_channels);
 // uploads the lane-mask table for `device` (cudaMalloc + copy): call once outside any stream capture
 bool conv3x3_v2_prepare(int device);
+// how many clusters of `cluster_size` CTAs of the tower kernel the current device can hold at once (planning probe)
+int conv3x3_v2_max_active_clusters(int cluster_size);
 
 }  // namespace ug

@@ -938,6 +938,11 @@ int ug_k_conv3x3_bf16(int device, const void* d_in, const void* d_w, const float
   return 0;
 }
 
+int ug_debug_max_active_clusters(int device, int cluster_size) {
+  cudaSetDevice(device);
+  return conv3x3_v2_max_active_clusters(cluster_size);
+}
+
 int ug_k_conv3x3_v2(int device, const void* d_in, const void* d_w, const float* d_bias, const void* d_res_hi,
                     const void* d_res_lo, void* d_out_hi, void* d_out_lo, int n, int n_alloc, int cin, int cout,
                     int relu, int f16, int desc_mode, int iters, float* ms_out, long long* d_prof) {
