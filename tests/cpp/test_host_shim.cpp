@@ -34,6 +34,17 @@ int main(int argc, char** argv) {
   printf("loaded_after %d\n", evaluator.GraphLoaded() ? 1 : 0);
   evaluator.UpdateCheckPoint(DlConfig::GetInstance().default_checkpoint());
   evaluator.EvaluateState(eb.feature_buf, eb.policy_out, eb.values_out, n);
+  // the same call again with the EvalBuffer page-locked (extension): results must be bit-identical
+  static EvalBuffer eb2;
+  memcpy(eb2.feature_buf, eb.feature_buf, sizeof(eb.feature_buf));
+  const bool reg = evaluator.Evaluator().RegisterHostBuffer(&eb2, sizeof(eb2));
+  evaluator.EvaluateState(eb2.feature_buf, eb2.policy_out, eb2.values_out, n);
+  bool same = true;
+  for (int i = 0; i < n; ++i) {
+    same = same && eb2.values_out[i] == eb.values_out[i];
+    for (int j = 0; j < GO_MAX_MOVES; ++j) same = same && eb2.policy_out[i][j] == eb.policy_out[i][j];
+  }
+  printf("registered %d identical %d\n", reg ? 1 : 0, same ? 1 : 0);
   for (int i = 0; i < n; ++i) {
     printf("value %d %.17g\n", i, eb.values_out[i]);
     printf("policy %d", i);

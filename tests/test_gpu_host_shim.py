@@ -35,9 +35,12 @@ def test_uct_board_evaluator_cpp(small_ckpt, positions, tmp_path):
             val[int(t[1])] = float(t[2])
         elif t[0] == "policy":
             pol[int(t[1])] = [float(x) for x in t[2:]]
+        elif t[0] == "registered":
+            flags["registered"], flags["identical"] = int(t[1]), int(t[3])
         else:
             flags[t[0]] = int(t[1])
-    assert flags == {"loaded_before": 0, "bad_path_throws": 1, "untouched": 1, "loaded_after": 1}
+    assert flags == {"loaded_before": 0, "bad_path_throws": 1, "untouched": 1, "loaded_after": 1,
+                     "registered": 1, "identical": 1}
     assert "Running model failed" in r.stderr  # the reference logs and carries on (.cc:315-317)
     want_p, want_v = GraphOracle(meta, prefix).evaluate_reference(planes[:n], value_transform=1)
     assert np.abs(pol - want_p).max() <= 1e-3 and np.abs(val - want_v).max() <= 5e-3

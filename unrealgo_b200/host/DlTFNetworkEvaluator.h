@@ -97,6 +97,9 @@ class DlTFNetworkEvaluator {
   }
 
   ug_eval* handle() { return m_h; }  // for the leaf queue (ug_queue_create)
+  // extension (not in the reference): page-lock a caller array that Evaluate() is always called with — EvalBuffer's
+  // feature_buf / policy_out / values_out — so it is copied from/to directly (ug_eval_register_host)
+  bool RegisterHostBuffer(void* p, size_t bytes) { return ug_eval_register_host(m_h, p, bytes) == 0; }
 
  protected:
   // default arithmetic: fp16 operands / fp32 accumulation (meets the stated tolerance); UGEVAL_PRECISION=bf16|fp32
