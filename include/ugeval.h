@@ -215,6 +215,12 @@ typedef struct ug_selfplay_config {
   const char* record_dir;
   float komi;              /* 0 = 7.5 (DEFAULT_KOMI, go/GoRules.h:9) */
   int game_index_base;     /* global index of this evaluator's first game (rank * games when sharded) */
+  /* 0/1: one leaf per game in flight — the shipped FORCE_SINGLE_THREAD search (CMakeLists.txt:15).  k > 1: up to k
+   * descents of one tree in flight with the reference's multi-thread virtual-loss bookkeeping (a counter on every node
+   * of a descent until its backup, search/UctSearch.cpp:814-850; Select adds the parent's count minus one to the
+   * visit total, :1066-1070; GetMeanValue counts a child's virtual losses as zero-valued visits, :664-680), so that a
+   * single game can fill a batch.  Results then depend on the order evaluations return. */
+  int leaves_per_game;
 } ug_selfplay_config;
 typedef struct ug_selfplay_stats {
   uint64_t playouts, evaluations, batches, flush_timeouts, moves, games_finished, terminal_leaves;

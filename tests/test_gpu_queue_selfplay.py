@@ -175,3 +175,27 @@ def test_selfplay_records_follow_write_tfrecord(small_ckpt, tmp_path):
             if i >= 2:  # after the random opening the move played is the most visited child (first wins ties)
                 assert pol[moves[i]] == pol.max()
             assert list(f["reward"].float_list.value) == [reward if k % 2 == 0 else -reward]
+
+
+def test_selfplay_virtual_loss_leaves_fill_batches_from_few_games(small_ckpt):
+    """leaves_per_game > 1: the reference's multi-thread search (virtual-loss counters on the descent path) lets two
+    games keep dozens of leaves in flight.  Every playout is still counted exactly once, every move is legal, the
+    virtual-loss counters net out (a second run from the same state plays on), and the batches are far larger than
+    the two leaves a one-leaf-per-game search can offer."""
+    import oracle
+    from unrealgo_b200 import selfplay
+    ev = _ev(small_ckpt, max_batch=64)
+    kw = dict(games=2, threads=2, playouts_per_move=96, max_moves=8, random_opening_moves=2, seed=5,
+              record_moves=True, max_batch=64, timeout_us=200)
+    st1, g1 = selfplay(ev, leaves_per_game=1, **kw)
+    st16, g16 = selfplay(ev, leaves_per_game=16, **kw)
+    ev.close()
+    for st in (st1, st16):
+        assert st["moves"] == 2 * 8 and st["playouts"] == 2 * 8 * 96
+        assert st["playouts"] == st["evaluations"] + st["terminal_leaves"]
+    assert st1["mean_batch"] <= 2.0 and st16["mean_batch"] >= 8.0
+    for g in g16:
+        b = oracle.Board()
+        for mv in g:
+            assert b.is_legal(mv), (g, mv)
+            b.play(mv)

@@ -41,7 +41,8 @@ class SelfplayConfig(C.Structure):
     _fields_ = [("games", C.c_int), ("threads", C.c_int), ("playouts_per_move", C.c_int), ("max_moves", C.c_int),
                 ("max_batch", C.c_int), ("timeout_us", C.c_int), ("reuse_tree", C.c_int),
                 ("random_opening_moves", C.c_int), ("puct", C.c_float), ("seed", C.c_uint64),
-                ("record_dir", C.c_char_p), ("komi", C.c_float), ("game_index_base", C.c_int)]
+                ("record_dir", C.c_char_p), ("komi", C.c_float), ("game_index_base", C.c_int),
+                ("leaves_per_game", C.c_int)]
 
 
 class SelfplayStats(C.Structure):

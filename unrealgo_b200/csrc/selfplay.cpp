@@ -38,25 +38,33 @@ struct Tree {
   std::vector<uint32_t> parent;
   std::vector<uint16_t> n_children;
   std::vector<uint16_t> move;        // policy index, 361 = pass
+  std::vector<uint16_t> vloss;       // UctNode::v_loss_cnt (search/UctSearchTree.h:242-252); empty unless several
+                                     // leaves of one game are in flight (use_vloss)
+  bool use_vloss = false;
   size_t size() const { return visits.size(); }
   void clear() {
     prior.clear(); w.clear(); visits.clear(); first_child.clear(); parent.clear(); n_children.clear(); move.clear();
+    vloss.clear();
   }
   void reserve(size_t n) {
     prior.reserve(n); w.reserve(n); visits.reserve(n); first_child.reserve(n); parent.reserve(n); n_children.reserve(n);
     move.reserve(n);
+    if (use_vloss) vloss.reserve(n);
   }
   void resize(size_t n) {
     prior.resize(n, 0.f); w.resize(n, 0.f); visits.resize(n, 0u); first_child.resize(n, 0u); parent.resize(n, 0u);
     n_children.resize(n, 0); move.resize(n, 0);
+    if (use_vloss) vloss.resize(n, 0);
   }
   void swap(Tree& o) {
     prior.swap(o.prior); w.swap(o.w); visits.swap(o.visits); first_child.swap(o.first_child); parent.swap(o.parent);
     n_children.swap(o.n_children); move.swap(o.move);
+    vloss.swap(o.vloss);
   }
   void copy_node(size_t dst, const Tree& src, size_t s) {
     prior[dst] = src.prior[s]; w[dst] = src.w[s]; visits[dst] = src.visits[s]; first_child[dst] = src.first_child[s];
     parent[dst] = src.parent[s]; n_children[dst] = src.n_children[s]; move[dst] = src.move[s];
+    if (use_vloss) vloss[dst] = 0;  // no leaf is in flight when a subtree is carried over
   }
 };
 
@@ -65,8 +73,12 @@ struct Game {
   ugo::Board work;              // board at the pending leaf
   Tree tree, scratch;
   std::vector<uint32_t> map_src;  // scratch of reuse_subtree
-  uint32_t leaf = 0;
-  int64_t ticket = -1;          // >= 0: a leaf is waiting for its evaluation
+  // leaves waiting for their evaluation: one in the shipped single-thread configuration, up to leaves_per_game
+  // with the reference's multi-thread virtual-loss search
+  static constexpr int kMaxLeaves = 64;
+  struct Pending { uint32_t leaf; int64_t ticket; };
+  Pending pend[kMaxLeaves];
+  int npend = 0;
   int playouts_this_move = 0;
   bool finished = false;
   std::vector<int16_t> moves;
@@ -190,6 +202,32 @@ uint32_t select_child(const Tree& t, uint32_t parent, float c_puct) {
   return base + best;
 }
 
+// The same selection with several descents of one tree in flight (the reference with num_threads > 1 and
+// use_virtual_loss): the parent's total gains its virtual-loss count minus one (search/UctSearch.cpp:1066-1070) and a
+// child's mean is diluted by its virtual losses counted as zero-valued visits (GetMeanValue, :664-680).
+uint32_t select_child_vloss(const Tree& t, uint32_t parent, float c_puct) {
+  const uint32_t base = t.first_child[parent];
+  uint32_t n = t.n_children[parent];
+  double total = 0;
+  for (uint32_t i = 0; i < n; ++i) total += t.visits[base + i];
+  if (t.vloss[parent] > 1) total += (double)(t.vloss[parent] - 1);
+  const float spc = (float)std::max(std::sqrt(total), 1.0);
+  const uint32_t pv = t.visits[parent];
+  const double default_mean = pv ? -(double)(t.w[parent] / (float)pv) : 0.0;
+  if (n > 1 && t.move[base + n - 1] == ugo::PASS) --n;
+  else if (n == 1) return base;
+  double best_v = 0;
+  uint32_t best = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t vis = t.visits[base + i], vl = t.vloss[base + i];
+    double q = default_mean;
+    if (vis + vl > 0) q = (double)t.w[base + i] / (double)(vis + vl);  // mean * count / (count + virtual losses)
+    const double v = q + (double)c_puct * (double)t.prior[base + i] * (double)spc / (1.0 + (double)vis);
+    if (i == 0 || v > best_v) { best = i; best_v = v; }
+  }
+  return base + best;
+}
+
 void new_root(Game& g) {
   g.tree.clear();
   g.tree.resize(1);
@@ -225,20 +263,34 @@ void reuse_subtree(Game& g, uint32_t child) {
   src.swap(dst);
 }
 
+// RemoveVirtualLoss on every node of a finished descent (:847-850): from the leaf up to the root
+void remove_virtual_loss(Tree& t, uint32_t leaf) {
+  uint32_t cur = leaf;
+  for (;;) {
+    --t.vloss[cur];
+    if (cur == 0) break;
+    cur = t.parent[cur];
+  }
+}
+
 // one descent; returns true if a leaf was submitted (false: terminal leaf, counted as a playout like the
 // reference's ExpandAndBackup returning false, search/UctSearch.cpp:478-490)
 bool start_playout(Game& g, Shared& sh) {
   g.work = g.root_board;
   uint32_t node = 0;
+  const bool vl = g.tree.use_vloss;
+  if (vl) ++g.tree.vloss[0];  // DeepUctSearchTree adds a virtual loss to every node of the path (:814-829)
   while (g.tree.n_children[node]) {
-    node = select_child(g.tree, node, sh.cfg.puct);
+    node = vl ? select_child_vloss(g.tree, node, sh.cfg.puct) : select_child(g.tree, node, sh.cfg.puct);
     g.work.play(g.tree.move[node]);
+    if (vl) ++g.tree.vloss[node];
   }
   uint16_t moves[UG_NUM_MOVES];
   uint32_t legal[UG_MASK_WORDS];
   const int n = g.work.generate_moves(moves, legal);
   if (n == 0) {
     sh.terminal_leaves.fetch_add(1, std::memory_order_relaxed);
+    if (vl) remove_virtual_loss(g.tree, node);
     return false;
   }
   const uint32_t base = (uint32_t)g.tree.size();
@@ -251,18 +303,23 @@ bool start_playout(Game& g, Shared& sh) {
   }
   ug_packed_pos pos;
   g.work.pack(&pos);
-  g.leaf = node;
-  g.ticket = ug_queue_submit(sh.q, &pos, legal);
-  if (g.ticket < 0) sh.stop.store(true);  // queue closed or evaluator failed: every worker winds down
-  return g.ticket >= 0;
+  const int64_t ticket = ug_queue_submit(sh.q, &pos, legal);
+  if (ticket < 0) {
+    sh.stop.store(true);  // queue closed or evaluator failed: every worker winds down
+    return false;
+  }
+  g.pend[g.npend].leaf = node;
+  g.pend[g.npend].ticket = ticket;
+  ++g.npend;
+  return true;
 }
 
-void finish_playout(Game& g, float value) {
+void finish_playout(Game& g, uint32_t leaf, float value) {
   Tree& t = g.tree;
-  const uint32_t base = t.first_child[g.leaf], nc = t.n_children[g.leaf];
+  const uint32_t base = t.first_child[leaf], nc = t.n_children[leaf];
   for (uint32_t i = 0; i < nc; ++i)
     t.prior[base + i] = g.policy[t.move[base + i]];  // already renormalised over the legal children on the GPU
-  uint32_t cur = g.leaf;
+  uint32_t cur = leaf;
   float v = value;
   for (;;) {  // BackupTree, search/UctSearch.cpp:1282-1295
     t.visits[cur] += 1;
@@ -271,6 +328,7 @@ void finish_playout(Game& g, float value) {
     if (cur == 0) break;
     cur = t.parent[cur];
   }
+  if (t.use_vloss) remove_virtual_loss(t, leaf);
 }
 
 // after playouts_per_move playouts: play the most visited child (first wins ties), keep or drop the tree
@@ -316,16 +374,19 @@ void make_move(Game& g, Shared& sh) {
   }
 }
 
-// after a playout completed (or at game start): play the move when the budget is used up, then put the next
-// leaf in flight.  Terminal leaves (no moves after two passes) cost a playout but no evaluation.
-// Postcondition: the game is finished or has a ticket >= 0.
+// after playouts completed (or at game start): play the move when the budget is used up and nothing is in flight,
+// otherwise put leaves in flight up to leaves_per_game.  Terminal leaves (no moves after two passes) cost a playout
+// but no evaluation.  Postcondition: the game is finished or has at least one leaf in flight.
 void advance(Game& g, Shared& sh) {
+  const int max_leaves = sh.cfg.leaves_per_game > 1 ? sh.cfg.leaves_per_game : 1;
   while (!g.finished) {
-    if (g.playouts_this_move >= sh.cfg.playouts_per_move) {
+    if (g.playouts_this_move + g.npend >= sh.cfg.playouts_per_move) {
+      if (g.npend > 0) return;  // the move is decided once the outstanding evaluations are back
       make_move(g, sh);
       continue;
     }
-    if (start_playout(g, sh)) return;
+    if (g.npend >= max_leaves) return;
+    if (start_playout(g, sh)) continue;
     if (sh.stop.load(std::memory_order_relaxed)) return;  // queue closed
     ++g.playouts_this_move;
     sh.playouts.fetch_add(1, std::memory_order_relaxed);
@@ -340,14 +401,20 @@ void worker(std::vector<Game>& games, size_t lo, size_t hi, Shared& sh) {
     for (size_t i = lo; i < hi; ++i) {
       Game& g = games[i];
       if (g.finished) continue;
-      float value = 0.f;
-      const int rc = ug_queue_poll(sh.q, g.ticket, g.policy, &value);
-      if (rc == 0) continue;  // not ready yet: look at the next game
-      if (rc < 0) { sh.stop.store(true); return; }
-      g.ticket = -1;
-      finish_playout(g, value);
-      ++g.playouts_this_move;
-      sh.playouts.fetch_add(1, std::memory_order_relaxed);
+      bool any = false;
+      for (int k = g.npend - 1; k >= 0; --k) {
+        float value = 0.f;
+        const int rc = ug_queue_poll(sh.q, g.pend[k].ticket, g.policy, &value);
+        if (rc == 0) continue;  // not ready yet
+        if (rc < 0) { sh.stop.store(true); return; }
+        const uint32_t leaf = g.pend[k].leaf;
+        g.pend[k] = g.pend[--g.npend];
+        finish_playout(g, leaf, value);
+        ++g.playouts_this_move;
+        sh.playouts.fetch_add(1, std::memory_order_relaxed);
+        any = true;
+      }
+      if (!any) continue;  // nothing came back for this game: look at the next one
       advance(g, sh);
       if (g.finished) --live;
       progressed = true;
@@ -367,9 +434,10 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
   if (cfg.threads > cfg.games) cfg.threads = cfg.games;
   if (cfg.puct <= 0) cfg.puct = 2.5f;  // puct_const, search/UctSearch.cpp:370
   if (cfg.max_batch <= 0) cfg.max_batch = 256;
+  if (cfg.leaves_per_game > Game::kMaxLeaves) cfg.leaves_per_game = Game::kMaxLeaves;
   Shared sh;
   sh.cfg = cfg;
-  sh.q = ug_queue_create(h, cfg.max_batch, cfg.timeout_us > 0 ? cfg.timeout_us : 200, 4 * cfg.games + 1024);
+  sh.q = ug_queue_create(h, cfg.max_batch, cfg.timeout_us > 0 ? cfg.timeout_us : 200, 4 * cfg.games * (cfg.leaves_per_game > 1 ? cfg.leaves_per_game : 1) + 1024);
   if (!sh.q) return -2;
   std::vector<Game> games((size_t)cfg.games);
   {
@@ -391,6 +459,7 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
           Game& g = games[i];
           g.rng.seed(cfg.seed * 1000003ull + (uint64_t)i);
           g.index = (int)i;
+          g.tree.use_vloss = g.scratch.use_vloss = cfg.leaves_per_game > 1;
           g.tree.reserve(cap);
           if (cfg.reuse_tree) g.scratch.reserve(cap / 2);
           if (prefault) {
