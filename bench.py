@@ -352,6 +352,18 @@ def main():
               "mean_batch_rank0": st["mean_batch"], "flush_timeouts_rank0": st["flush_timeouts"],
               "mean_tree_nodes_rank0": st["mean_tree_nodes"], "reuse_searchtree": True,
               "sharding": "independent games per GPU, weights replicated, no collective"}
+        # one game alone (GTP-style use): one leaf in flight vs the reference's virtual-loss multi-thread search
+        try:
+            s1, _ = selfplay(ev, games=1, threads=1, playouts_per_move=400, max_moves=2, max_batch=SP_BATCH,
+                             timeout_us=300, reuse_tree=True, random_opening_moves=1, seed=77, leaves_per_game=1)
+            s64, _ = selfplay(ev, games=1, threads=1, playouts_per_move=args.sp_playouts, max_moves=3,
+                              max_batch=SP_BATCH, timeout_us=300, reuse_tree=True, random_opening_moves=1, seed=77,
+                              leaves_per_game=64)
+            sp["single_game"] = {"one_leaf_playouts_per_s": s1["playouts_per_s"],
+                                 "virtual_loss_64_leaves_playouts_per_s": s64["playouts_per_s"],
+                                 "virtual_loss_mean_batch": s64["mean_batch"]}
+        except Exception as e:  # an extra, never part of the headline
+            sp["single_game"] = {"error": repr(e)}
 
     # roofline of the dominant kernel (3x3 CxC tower conv): CUDA-event brackets inside the library, on its stream
     br = ev.bench(host_packed[0], 20)
