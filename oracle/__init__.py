@@ -84,6 +84,23 @@ def ref_lib():
         R.ref_dlcfg_value_transform.argtypes = [C.c_void_p]
         R.ref_dlcfg_reuse_search_tree.argtypes = [C.c_void_p]
         R.ref_get_offset.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        if hasattr(R, "ref_board_new"):
+            R.ref_board_new.restype = C.c_void_p
+            R.ref_board_free.argtypes = [C.c_void_p]
+            for n in ("ref_board_to_play", "ref_board_move_number", "ref_board_undo", "ref_board_last_move",
+                      "ref_board_ko_point"):
+                getattr(R, n).argtypes = [C.c_void_p]
+            R.ref_board_undo.restype = None
+            R.ref_board_set_to_play.argtypes = [C.c_void_p, C.c_int]
+            R.ref_board_is_legal.argtypes = [C.c_void_p, C.c_int, C.c_int]
+            R.ref_board_play.argtypes = [C.c_void_p, C.c_int, C.c_int]
+            R.ref_board_colors.argtypes = [C.c_void_p, C.c_void_p]
+            R.ref_collect_features.argtypes = [C.c_void_p, C.c_void_p]
+            R.ref_board_tromp_taylor.argtypes = [C.c_void_p, C.c_float]
+            R.ref_board_tromp_taylor.restype = C.c_float
+            R.ref_board_is_simple_eye.argtypes = [C.c_void_p, C.c_int, C.c_int]
+            R.ref_board_two_passes.argtypes = [C.c_void_p]
+            R.ref_board_generate.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _REF = R
     return _REF
 
@@ -140,6 +157,74 @@ class Board:
         """-> uint32[196] in ug_packed_pos layout"""
         out = np.zeros(196, np.uint32)
         lib().og_pack_position(self._b, out.ctypes.data)
+        return out
+
+
+class RefBoard:
+    """The reference's OWN GoBoard (go/GoBoard.cpp compiled into oracle/_ref/libugref.so by oracle/Makefile), ko rule
+    SIMPLEKO as GoUctState::Execute sets it (gouct/GoUctSearch.cpp:90-100).  Same interface as Board; exists only
+    where the reference tree was present at build time — used to pin Board and to generate tests/golden/ref_board.npz."""
+
+    def __init__(self):
+        self._r = ref_lib()
+        if self._r is None or not hasattr(self._r, "ref_board_new"):
+            raise RuntimeError("oracle/_ref/libugref.so (with the board) is not built")
+        self._b = self._r.ref_board_new()
+
+    def __del__(self):
+        if getattr(self, "_b", None):
+            self._r.ref_board_free(self._b)
+            self._b = None
+
+    @property
+    def to_play(self):
+        return self._r.ref_board_to_play(self._b)
+
+    def set_to_play(self, c):
+        self._r.ref_board_set_to_play(self._b, c)
+
+    @property
+    def move_number(self):
+        return self._r.ref_board_move_number(self._b)
+
+    def colors(self):
+        out = np.empty(NPTS, np.int8)
+        self._r.ref_board_colors(self._b, out.ctypes.data)
+        return out
+
+    def is_legal(self, p, color=None):
+        return bool(self._r.ref_board_is_legal(self._b, p, self.to_play if color is None else color))
+
+    def play(self, p, color=None):
+        """-> True when the reference board flagged the move illegal"""
+        return bool(self._r.ref_board_play(self._b, p, self.to_play if color is None else color))
+
+    def undo(self):
+        self._r.ref_board_undo(self._b)
+
+    def last_move(self):
+        return self._r.ref_board_last_move(self._b)
+
+    def ko_point(self):
+        return self._r.ref_board_ko_point(self._b)
+
+    def is_simple_eye(self, p, color=None):
+        """GoEyeUtil::IsSimpleEye of the reference (go/GoEyeUtil.h:133-176) on an empty point"""
+        return bool(self._r.ref_board_is_simple_eye(self._b, p, self.to_play if color is None else color))
+
+    def generate(self, initial_move_number=0):
+        """the move list of GenerateLegalMoves (gouct/GoUctGlobalSearch.h:308-330), as policy indices"""
+        out = np.zeros(362, np.int16)
+        n = self._r.ref_board_generate(self._b, initial_move_number, out.ctypes.data)
+        return out[:n].copy()
+
+    def score(self, komi=7.5):
+        """GoBoardUtil::TrompTaylorScore of the reference (go/GoBoardUtil.h:626-680), positive = Black ahead"""
+        return float(self._r.ref_board_tromp_taylor(self._b, komi))
+
+    def collect_features(self):
+        out = np.empty((NUM_MAPS, 19, 19), np.int8)
+        self._r.ref_collect_features(self._b, out.ctypes.data)
         return out
 
 

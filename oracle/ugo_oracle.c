@@ -6,12 +6,19 @@
  * unrealgo_b200/ may link or call this file.
  *
  * Pinning: the reference holds no golden vectors or tests for this path (CollectFeatures is
- * an empty stub in search/test/UctSearchTest.cpp:98-102).  The functions below are pinned by (1) the
- * self-made known-answer vectors in tests/golden/ (empty board, one stone, capture, ko, short history, pass)
- * and (2) the reference's own DlConfig/ArrayUtil sources compiled into oracle/_ref (see oracle/Makefile).
- * The board logic (captures, simple ko) is only an input generator and is itself restated from
- * go/GoBoard.cpp:648-702; it is not pinned against the reference's GoBoard ("parity unpinned" for whole-game
- * board evolution; the encoder contract — colours + move stack -> planes — is what is checked).
+ * an empty stub in search/test/UctSearchTest.cpp:98-102).  The functions below are pinned by
+ *  (1) outputs of the reference itself run in the build container: its own GoBoard, GoBoardUtil and GoEyeUtil
+ *      (go/GoBoard.cpp ... compiled where they lie into oracle/_ref/libugref.so, oracle/Makefile) played through
+ *      seeded games, with the planes produced by driving that board the way CollectFeatures does — committed as
+ *      tests/golden/ref_board.npz (generator tests/golden/make_ref_board_golden.py) and replayed bit for bit by
+ *      tests/test_ref_board_golden.py: colours, side to move, GetLastMove, legality of all 362 moves for both
+ *      colours (captures, simple ko, suicide), undo, and the 17 planes;
+ *  (2) the reference's own DlConfig/ArrayUtil sources compiled into the same library;
+ *  (3) self-made known-answer vectors in tests/golden/encoder_kat.npz.
+ * What stays a restatement: the ~40-line CollectFeatures loop itself (its template sits on the search stack and
+ * does not compile here; oracle/ref_board_shim.cc performs the same board calls on the real board),
+ * TransformFeature's loop (TensorFlow-dependent file; its index formula GetOffset IS pinned), value_transform and
+ * UpdatePrior (inside TensorFlow- and search-dependent files).
  *
  * Each function cites the reference lines it follows.
  */
@@ -94,12 +101,12 @@ static int block_liberties(const board_t* b, int p, int16_t* members, int* n_mem
   return libs;
 }
 
-/* 1 if playing p for `color` is legal: empty, not the simple-ko point, not suicide
+/* 1 if playing p for `color` is legal: empty, not the simple-ko point (for the side to move), not suicide
  * (GoBoard::IsLegal with SIMPLEKO, as used in-tree: gouct/GoUctSearch.cpp:93-96) */
 int og_board_is_legal(board_t* b, int p, int color) {
   if (p == PASS) return 1;
   if (p < 0 || p >= NPTS || b->color[p] != EMPTY) return 0;
-  if (p == b->ko_point) return 0;
+  if (p == b->ko_point && color == b->to_play) return 0; /* go/GoBoard.h:796: the ko binds the side to move only */
   int nb[4];
   int k = neighbors(p, nb);
   for (int i = 0; i < k; ++i) if (b->color[nb[i]] == EMPTY) return 1;

@@ -44,3 +44,31 @@ def test_encoder_many_positions(ev):
         assert np.array_equal(ev.encode_nhwc(packed), oracle.transform_feature(planes, 0, True))
         total += len(packed)
     assert total >= 10000
+
+
+def test_encoder_matches_the_reference_boards_planes(ev):
+    """planes written by the REFERENCE's own board driven like CollectFeatures (tests/golden/ref_board.npz, generator
+    tests/golden/make_ref_board_golden.py): the games are replayed on the host board the self-play driver uses
+    (csrc/goboard.h), its packed history goes through the CUDA encoder, and the result must be those planes"""
+    import os
+    from unrealgo_b200 import ProductBoard
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_board.npz"))
+    packed, want = [], []
+    for g in range(int(G["op_game"].max()) + 1):
+        sel = np.nonzero(G["op_game"] == g)[0]
+        ops, cols = G["ops"][sel].tolist(), G["op_color"][sel].tolist()
+        if -3 in ops:
+            cut = ops.index(-3)
+            ops, cols = ops[:cut], cols[:cut]
+        if -2 in ops or cols != [k & 1 for k in range(len(ops))]:
+            continue
+        samples = {int(G["s_after"][i]): i for i in np.nonzero(G["s_game"] == g)[0]}
+        pb = ProductBoard()
+        for n, op in enumerate([None] + ops):
+            if op is not None:
+                pb.play(op)
+            if n in samples and G["s_has_planes"][samples[n]]:
+                packed.append(pb.pack())
+                want.append(np.unpackbits(G["s_planes"][samples[n]])[:17 * 361].reshape(17, 19, 19).astype(np.int8))
+    assert len(packed) > 350
+    assert np.array_equal(ev.encode_planes(np.stack(packed)), np.stack(want))

@@ -1,0 +1,139 @@
+"""tests/golden/ref_board.npz holds answers of the REFERENCE's own GoBoard (go/GoBoard.cpp compiled by oracle/Makefile;
+generator: tests/golden/make_ref_board_golden.py).  It pins, bit for bit:
+  * the oracle's board restatement and its CollectFeatures planes,
+  * the product's host board (csrc/goboard.h) — colours via the planes, legal moves, generated move lists, Tromp-Taylor score,
+and, where oracle/_ref/libugref.so exists (the build container), the live reference board against the file."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from unrealgo_b200 import ProductBoard
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_board.npz"))
+UNDO, SET_TO_PLAY = -2, -3
+N_GAMES = int(G["op_game"].max()) + 1
+
+
+def _samples_of(g):
+    return {int(G["s_after"][i]): i for i in np.nonzero(G["s_game"] == g)[0]}
+
+
+def _ops_of(g):
+    sel = np.nonzero(G["op_game"] == g)[0]
+    return [(int(G["ops"][i]), int(G["op_color"][i])) for i in sel]
+
+
+def _apply(b, op, col):
+    if op == UNDO:
+        b.undo()
+    elif op == SET_TO_PLAY:
+        b.set_to_play(col)
+    else:
+        b.play(op, col)
+
+
+def _check_board(b, i, what):
+    assert np.array_equal(b.colors(), G["s_colors"][i]), what
+    assert b.to_play == G["s_to_play"][i] and b.last_move() == G["s_last"][i], what
+    for c in (0, 1):
+        want = np.unpackbits(G["s_legal"][i, c])[:362].astype(bool)
+        got = np.array([b.is_legal(p, c) for p in range(362)])
+        assert np.array_equal(got, want), (what, c, np.nonzero(got != want)[0])
+    if G["s_has_planes"][i]:
+        want = np.unpackbits(G["s_planes"][i])[:17 * 361].reshape(17, 19, 19).astype(np.int8)
+        assert np.array_equal(b.collect_features(), want), what
+    if hasattr(b, "score"):
+        assert b.score(0.0) == G["s_score"][i, 0] and b.score(7.5) == G["s_score"][i, 1], what
+
+
+def _replay(make_board):
+    checked = 0
+    for g in range(N_GAMES):
+        b = make_board()
+        samples = _samples_of(g)
+        if 0 in samples:
+            _check_board(b, samples[0], (g, 0))
+            checked += 1
+        for n, (op, col) in enumerate(_ops_of(g), start=1):
+            _apply(b, op, col)
+            if n in samples:
+                _check_board(b, samples[n], (g, n))
+                checked += 1
+    return checked
+
+
+def test_fixture_shape():
+    assert N_GAMES >= 27 and len(G["s_game"]) > 500 and (G["s_ko"] >= 0).sum() >= 5
+    assert (G["ops"] == UNDO).sum() > 20 and (G["ops"] == SET_TO_PLAY).sum() >= 4 and (G["ops"] == 361).sum() > 50
+    # out-of-turn moves exist in the mixed games only
+    assert G["s_has_planes"].sum() > 350
+
+
+def test_oracle_board_and_planes_match_the_reference_board():
+    assert _replay(oracle.Board) == len(G["s_game"])
+
+
+def test_live_reference_board_reproduces_the_fixture():
+    try:
+        oracle.RefBoard()
+    except RuntimeError:
+        pytest.skip("oracle/_ref/libugref.so not built here (needs the reference tree)")
+    assert _replay(oracle.RefBoard) == len(G["s_game"])
+
+
+def test_simple_eye_rule_of_the_fixture_is_the_two_block_rule():
+    """the generated lists drop exactly the legal points whose neighbours are all own stones of at most two blocks
+    (go/GoEyeUtil.h:133-176); a weaker 'all neighbours own' rule would drop more — make sure the file can tell"""
+    dropped = weaker = 0
+    for i in range(len(G["s_game"])):
+        tp = int(G["s_to_play"][i])
+        legal = np.unpackbits(G["s_legal"][i, tp])[:361].astype(bool)
+        gen = np.unpackbits(G["s_gen"][i])[:361].astype(bool)
+        if not gen.any() and not np.unpackbits(G["s_gen"][i])[361]:
+            continue  # two passes: nothing generated at all
+        assert not (gen & ~legal).any()
+        c = np.full((21, 21), 3, np.int8)
+        c[1:20, 1:20] = G["s_colors"][i].reshape(19, 19)
+        nb = np.stack([c[:-2, 1:-1], c[2:, 1:-1], c[1:-1, :-2], c[1:-1, 2:]])
+        all_own = ((nb == tp) | (nb == 3)).all(0).reshape(-1)
+        assert not (legal & ~gen & ~all_own).any()      # whatever was dropped has only own stones around it
+        dropped += int((legal & ~gen).sum())
+        weaker += int((legal & all_own).sum())
+    assert dropped > 100 and weaker > dropped + 10      # some all-own points are NOT eyes and must be generated
+
+
+def test_product_host_board_matches_the_reference_board():
+    """csrc/goboard.h (the self-play driver's incremental board) on the games that alternate colours, which is all it
+    supports: legal moves for the side to move, planes and side to move at every sampled position"""
+    checked = games = 0
+    for g in range(N_GAMES):
+        ops = _ops_of(g)
+        if SET_TO_PLAY in [op for op, _ in ops]:
+            ops = ops[:[op for op, _ in ops].index(SET_TO_PLAY)]
+        colours = [col for _, col in ops]
+        if UNDO in [op for op, _ in ops] or colours != [k & 1 for k in range(len(ops))]:
+            continue  # a mixed game
+        games += 1
+        pb = ProductBoard()
+        samples = _samples_of(g)
+        for n, (op, _) in enumerate([(None, None)] + ops):
+            if op is not None:
+                pb.play(op)
+            if n in samples:
+                i = samples[n]
+                assert pb.to_play == G["s_to_play"][i]
+                want = np.unpackbits(G["s_legal"][i, pb.to_play])[:362].astype(bool)
+                got = np.array([pb.legal(p) for p in range(362)])
+                assert np.array_equal(got, want), (g, n, np.nonzero(got != want)[0])
+                if G["s_has_planes"][i]:
+                    planes = np.unpackbits(G["s_planes"][i])[:17 * 361].reshape(17, 19, 19).astype(np.int8)
+                    assert np.array_equal(pb.planes(), planes), (g, n)
+                moves, mask = pb.generate()   # GenerateLegalMoves: eyes of the side to move dropped, empty after two passes
+                want_gen = np.nonzero(np.unpackbits(G["s_gen"][i])[:362])[0]
+                assert np.array_equal(moves.astype(np.int64), want_gen), (g, n)
+                assert np.array_equal(np.nonzero(np.unpackbits(mask.view(np.uint8), bitorder="little")[:362])[0], want_gen)
+                assert pb.score(0.0) == G["s_score"][i, 0] and pb.score(7.5) == G["s_score"][i, 1], (g, n)
+                checked += 1
+    assert games >= 21 and checked > 350

@@ -57,9 +57,10 @@ struct Board {
 
   static inline void nbrs(int b, int out[4]) { out[0] = b - W; out[1] = b - 1; out[2] = b + 1; out[3] = b + W; }
 
-  // legality of a stone at bordered index b for colour c: empty, not ko, not suicide
+  // legality of a stone at bordered index b for colour c: empty, not the ko point (which binds the side to move
+  // only, go/GoBoard.h:796), not suicide
   bool legal(int b, int c) const {
-    if (color[b] != EMPTY || b == ko) return false;
+    if (color[b] != EMPTY || (b == ko && c == to_play)) return false;
     int nb[4];
     nbrs(b, nb);
     // count adjacencies of b to each neighbouring block (pseudo-liberties count an empty point once per adjacency)
