@@ -19,6 +19,7 @@ bool UnrealGo::FileExists(const std::string& fileName) {
   return stat(fileName.c_str(), &buffer) == 0;
 }
 
+#ifndef UGREF_FILE_EXISTS_ONLY
 extern "C" {
 
 void* ref_dlcfg_open(const char* path) { return new DlConfig(path); }
@@ -61,3 +62,4 @@ int ref_get_offset(const int* dims, int ndims, const int* idx) {
 }
 
 }  // extern "C"
+#endif  // UGREF_FILE_EXISTS_ONLY

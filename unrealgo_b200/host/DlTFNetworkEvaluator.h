@@ -22,11 +22,14 @@
 #include <vector>
 
 #include "../../include/ugeval.h"
+// Built inside the reference tree (host/overlay/funcapproximator/DlTFNetworkEvaluator.h), the reference's own
+// BoardStaticConfig.h, DataFormat.h and DlConfig.h are already in; standalone, the host-side stand-ins are used.
+#ifndef UGEVAL_WITH_REFERENCE_TREE
 #include "DlConfig.h"
-
-#ifndef GO_MAX_SIZE
 static const int GO_MAX_SIZE = UG_BOARD_SIZE;
 static const int GO_MAX_MOVES = UG_NUM_MOVES;
+#else
+static_assert(GO_MAX_SIZE == UG_BOARD_SIZE && GO_MAX_MOVES == UG_NUM_MOVES, "ugeval is built for 19x19");
 #endif
 const int BD_SIZE = UG_BOARD_SIZE;
 const int NUM_MAPS = UG_NUM_PLANES;
@@ -38,7 +41,11 @@ const int MAX_BATCHES = 16;
 #define UGEVAL_MAX_BATCH 512
 #endif
 
+#ifndef UGEVAL_WITH_REFERENCE_TREE
 enum DataFormat { DF_HWC = UG_DF_HWC, DF_CHW = UG_DF_CHW };  // funcapproximator/DataFormat.h:22-25
+#else
+static_assert(DF_HWC == UG_DF_HWC && DF_CHW == UG_DF_CHW, "DataFormat values differ from the C ABI's");
+#endif
 
 namespace tensorflow {  // kept so that `tensorflow::DlTFNetworkEvaluator<bool>` in UctBoardEvaluator.h still names it
 
