@@ -56,3 +56,42 @@ def test_dropin_binary_builds_and_has_no_cpu_fallback(tmp_path):
     (tmp_path / "planes.bin").write_bytes(bytes(17 * 361))
     r = subprocess.run([exe, "planes.bin", "1"], cwd=str(tmp_path), capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr   # the reference's call path fails loudly without a GPU
+
+
+@needs_ref
+def test_reference_record_writer_header_over_ug_tfrecord(tmp_path):
+    """funcapproximator/DlTFRecordWriter.h is used UNMODIFIED (it only forward-declares TensorFlow types);
+    unrealgo_b200/host/DlTFRecordWriter.cc supplies the members in place of the reference's TensorFlow-based .cc"""
+    import numpy as np
+    from tests.test_tfrecord import _example_class, read_records
+    libdir = os.path.join(ROOT, "unrealgo_b200", "lib")
+    if not os.path.exists(os.path.join(libdir, "libugeval.so")):
+        pytest.skip("libugeval.so not built")
+    exe = str(tmp_path / "ref_recordwriter")
+    subprocess.run(["g++", "-std=c++11", "-O1", "-include", "string", "-I" + REF,
+                    os.path.join(ROOT, "tests", "cpp", "ref_recordwriter_main.cc"),
+                    os.path.join(ROOT, "unrealgo_b200", "host", "DlTFRecordWriter.cc"),
+                    "-L" + libdir, "-lugeval", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    path = str(tmp_path / "out.tfrecord")
+    r = subprocess.run([exe, path, "7"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "bad_write -1" in r.stdout, r.stdout + r.stderr
+    recs = read_records(path)
+    assert len(recs) == 7
+    Example = _example_class()
+    s = 12345
+    for i, raw in enumerate(recs):
+        ex = Example.FromString(raw)
+        feat = np.empty(6137, np.uint8)
+        pol = np.empty(362, np.float32)
+        for k in range(6137):
+            s = (s * 1664525 + 1013904223) & 0xFFFFFFFF
+            feat[k] = (s >> 24) & 1
+        for k in range(362):
+            s = (s * 1664525 + 1013904223) & 0xFFFFFFFF
+            pol[k] = np.float32((s >> 8) / 16777216.0)
+        kf, kp, kr = ("feature", "policy", "reward") if i % 2 == 0 else ("f", "p", "r")
+        f = ex.features.feature
+        assert sorted(f.keys()) == sorted([kf, kp, kr])
+        assert f[kf].bytes_list.value[0] == feat.tobytes()
+        assert np.array_equal(np.array(f[kp].float_list.value, np.float32), pol)
+        assert list(f[kr].float_list.value) == [float(i % 3 - 1)]
