@@ -1,0 +1,69 @@
+// The reference's OWN search on the product library, test infrastructure only.  Everything below main() is the
+// reference's unmodified code compiled where it lies (search/UctSearch.cpp with its NetworkEvalThread and
+// ExpandAndBackup, search/UctBoardEvaluator.cpp, gouct/, go/, board/, lib/, platform/ — oracle/Makefile `refsearch`),
+// with unrealgo_b200/host/overlay ahead of the reference root on the include path and libugeval.so +
+// unrealgo_b200/host/DlTFRecordWriter.cc on the link line where TensorFlow used to be.  main() sets the search up the
+// way UctDeepPlayer does (search/UctDeepPlayer.cpp:18-51, :288-320) and runs it from the empty board.
+//   usage: ref_search <playouts per move> <moves> [threads]        (./dlcfg-19 names the graph and the checkpoint)
+// Output: one line per move — move index, games played, seconds — then the root's children (move:visits) of the last
+// search and the totals.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include <unistd.h>
+
+#include "platform/SgSystem.h"
+
+#include "GoBoard.h"
+#include "GoInit.h"
+#include "GoUctDefaultMoveFilter.h"
+#include "GoUctGlobalSearch.h"
+#include "GoUctPlayoutPolicy.h"
+#include "SgInit.h"
+#include "funcapproximator/DlConfig.h"
+#include "platform/SgTimer.h"
+
+typedef GoUctGlobalSearch<GoUctPlayoutPolicy<GoUctBoard>, GoUctPlayoutPolicyFactory<GoUctBoard> > SearchType;
+
+int main(int argc, char** argv) {
+  if (argc < 3) { fprintf(stderr, "usage: %s playouts moves [threads]\n", argv[0]); return 2; }
+  const double playouts = atof(argv[1]);
+  const int moves = atoi(argv[2]);
+  SgInit();
+  GoInit();
+  GoBoard bd(GO_MAX_SIZE);
+  GoUctPlayoutPolicyParam policyParam;
+  GoUctDefaultMoveFilterParam filterParam;
+  SearchType search(bd, new GoUctPlayoutPolicyFactory<GoUctBoard>(policyParam), policyParam, filterParam);
+  search.SetPruneMinCount(0);
+  if (argc > 3) search.SetNumberThreads((size_t)atoi(argv[3]));
+  search.UpdateCheckPoint(DlConfig::GetInstance().default_checkpoint());
+  double total_games = 0, total_time = 0;
+  for (int m = 0; m < moves; ++m) {
+    std::vector<GoMove> sequence;
+    std::vector<UctNode*> best;
+    std::vector<GoMove> rootFilter;
+    search.SetToPlay(bd.ToPlay());
+    SgTimer timer;
+    search.StartDeepUCTSearchThread(playouts, 1e9, sequence, &best, 0, 1.0, rootFilter, 0, 0, true);
+    const double t = timer.GetTime();
+    const GoMove mv = sequence.empty() ? GO_PASS : sequence[0];
+    printf("move %d idx %d games %.0f seconds %.4f\n", m, GoPointUtil::Point2Index(mv), (double)search.GamesPlayed(), t);
+    total_games += search.GamesPlayed();
+    total_time += t;
+    if (m + 1 == moves) {
+      printf("root");
+      for (UctChildNodeIterator it(search.Tree(), search.Tree().Root()); it; ++it)
+        if ((*it).VisitCount() > 0) printf(" %d:%.0f", GoPointUtil::Point2Index((*it).Move()), (double)(*it).VisitCount());
+      printf("\n");
+    }
+    bd.Play(mv);
+  }
+  printf("total games %.0f seconds %.4f playouts_per_s %.1f\n", total_games, total_time, total_games / total_time);
+  // Leave without running destructors, as the engine itself does: ~NetworkEvalThread (search/UctSearch.cpp:153-158) sets
+  // to_quit and joins, but a paused evaluation thread sits in wait(lock, !paused) (:170-172) and never looks at to_quit,
+  // so destroying a search that has been stopped blocks forever.
+  fflush(stdout);
+  _exit(0);
+}

@@ -19,6 +19,15 @@ bool UnrealGo::FileExists(const std::string& fileName) {
   return stat(fileName.c_str(), &buffer) == 0;
 }
 
+#if __cplusplus >= 201703L
+// lib/FileUtil.cc:178-184 (needed by platform/SgPlatform.cpp when the whole engine is linked, oracle/_ref/ref_search)
+std::string UnrealGo::GetNativeFileName(const boost::filesystem::path& file) {
+  boost::filesystem::path normalized = file;
+  normalized = normalized.lexically_normal();
+  return normalized.string();
+}
+#endif
+
 #ifndef UGREF_FILE_EXISTS_ONLY
 extern "C" {
 

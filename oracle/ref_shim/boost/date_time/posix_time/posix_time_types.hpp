@@ -15,6 +15,9 @@ namespace posix_time {
 struct time_duration {
   int64_t us;
   int64_t total_microseconds() const { return us; }
+  int64_t total_nanoseconds() const { return us * 1000; }
+  int64_t total_milliseconds() const { return us / 1000; }
+  int64_t total_seconds() const { return us / 1000000; }
 };
 struct ptime {
   int64_t us_since_epoch;

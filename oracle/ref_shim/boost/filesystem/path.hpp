@@ -1,0 +1,3 @@
+// Stand-in: see ../filesystem.hpp.  Test infrastructure only.
+#pragma once
+#include "../filesystem.hpp"

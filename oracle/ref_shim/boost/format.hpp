@@ -2,6 +2,7 @@
 // exception messages — "%N%"/"%s"-style directives are substituted in order.  Test infrastructure only.
 #pragma once
 #include <sstream>
+#include "io/ios_state.hpp"  // real Boost.Format pulls it in, and search/UctSearch.cpp relies on that
 #include <string>
 #include <vector>
 namespace boost {

@@ -1,0 +1,28 @@
+"""Probe (not a test): the reference's own search engine (oracle/_ref/ref_search) on libugeval with the flagship
+20-block x 256-filter network — what the unmodified engine reaches with its one-leaf-per-call hand-off — next to the
+product's self-play driver on one game.  Usage: python tests/gpu_reference_search_probe.py [playouts]"""
+import os
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from unrealgo_b200 import tfformat
+    playouts = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
+    d = tempfile.mkdtemp(prefix="refsearch_")
+    meta, prefix = tfformat.write_synthetic_checkpoint(os.path.join(d, "flagship"), 20, 256, seed=5)
+    outs = "resnet/tower_0/policy_head/policy_predict:resnet/tower_0/value_head/reward_predict"
+    with open(os.path.join(d, "dlcfg-19"), "w") as f:
+        f.write(f"meta_graph={meta}\ncheckpoint={prefix}\nnn_input=feature_input\nnn_outputs={outs}\n"
+                "value_transform=0\nreuse_searchtree=false\n")
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_search")
+    r = subprocess.run([exe, str(playouts), "2"], cwd=d, capture_output=True, text=True, timeout=600)
+    print("reference engine on libugeval (20x256):", [ln for ln in r.stdout.splitlines() if ln.startswith("total")], "rc", r.returncode)
+
+
+if __name__ == "__main__":
+    main()

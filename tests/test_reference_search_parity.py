@@ -1,0 +1,89 @@
+"""Search parity against the reference's OWN engine, no GPU needed.
+
+oracle/_ref/ref_search is the reference's unmodified search (search/UctSearch.cpp, gouct/, go/ ... 93 sources, built
+by oracle/Makefile `refsearch` with the ugeval include overlay).  Here it runs with tests/cpp/ugeval_stub.c preloaded in
+front of libugeval.so — a stand-in network whose policy/value are a hash of the 17 planes — and the product's
+self-play driver (csrc/selfplay.cpp) runs on a stub leaf queue that computes the same function of the same planes
+(tests/cpp/selfplay_stub.cpp).  One game, one search thread, no tree reuse, PUCT 2.5 (the reference's defaults,
+search/UctSearch.cpp:370-372): the two must choose the same moves and end with the same root visit counts.
+
+The stub answers in its UGSTUB_SYNC mode, i.e. only once the caller's buffer holds the new leaf's features.  Without
+that the reference's free-running NetworkEvalThread (search/UctSearch.cpp:164-199) hands a leaf whatever evaluation
+was in flight when its state_ready flag was raised — with a 150 us evaluator 1989 of 2000 answers were computed from
+the previous leaf's planes (UGSTUB_STATS=1 prints the count) — which is the behaviour the ticketed leaf queue removes,
+not one to reproduce."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SEARCH = os.path.join(ROOT, "oracle", "_ref", "ref_search")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(REF_SEARCH),
+                                reason="oracle/_ref/ref_search not built (needs the reference tree and libugeval.so)")
+
+
+@pytest.fixture(scope="module")
+def tools(tmp_path_factory):
+    d = tmp_path_factory.mktemp("refsearch")
+    stub = str(d / "ugeval_stub.so")
+    exe = str(d / "selfplay_stub")
+    cpp = os.path.join(ROOT, "tests", "cpp")
+    subprocess.run(["gcc", "-O1", "-shared", "-fPIC", "-o", stub, os.path.join(cpp, "ugeval_stub.c")], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I/usr/local/cuda/include",
+                    os.path.join(cpp, "selfplay_stub.cpp"), os.path.join(ROOT, "unrealgo_b200", "csrc", "selfplay.cpp"),
+                    "-o", exe], check=True, capture_output=True)
+    (d / "dlcfg-19").write_text("meta_graph=stub.meta\ncheckpoint=stub\nvalue_transform=0\nreuse_searchtree=false\n")
+    return str(d), stub, exe
+
+
+def _reference(tools, playouts, moves, **env):
+    cwd, stub, _ = tools
+    e = dict(os.environ, LD_PRELOAD=stub, **env)
+    r = subprocess.run([REF_SEARCH, str(playouts), str(moves)], cwd=cwd, env=e, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    mv, root = [], {}
+    for line in r.stdout.splitlines():
+        t = line.split()
+        if t and t[0] == "move":
+            assert float(t[5]) == playouts
+            mv.append(int(t[3]))
+        elif t and t[0] == "root":
+            root = {int(x.split(":")[0]): int(float(x.split(":")[1])) for x in t[1:]}
+    return mv, root, r.stderr
+
+
+def _product(tools, playouts, moves):
+    cwd, _, exe = tools
+    e = dict(os.environ, UGSTUB_PRINT_VISITS="1")
+    r = subprocess.run([exe, "1", "1", str(playouts), str(moves), "0", "1", "0"], cwd=cwd, env=e, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    mv, visits = [], {}
+    for line in r.stdout.splitlines():
+        t = line.split()
+        if t and t[0] == "game":
+            mv = [int(x) for x in t[2:]]
+        elif t and t[0] == "visits":
+            visits[int(t[1])] = {int(x.split(":")[0]): int(float(x.split(":")[1])) for x in t[2:]}
+    return mv, visits
+
+
+@pytest.mark.parametrize("playouts,moves", [(300, 30), (800, 8)])
+def test_product_search_matches_the_reference_engine(tools, playouts, moves):
+    ref_moves, ref_root, _ = _reference(tools, playouts, moves, UGSTUB_SYNC="1")
+    got_moves, got_visits = _product(tools, playouts, moves)
+    assert len(ref_moves) == moves and got_moves == ref_moves
+    # the game record is walked from the last move back (UctDeepPlayer::WriteTFRecord): record 0 is the last search
+    assert {k: v for k, v in got_visits[0].items() if v > 0} == ref_root
+    assert sum(ref_root.values()) == playouts - 1      # the first playout expands the root
+
+
+def test_reference_hand_off_delivers_stale_evaluations_without_sync(tools):
+    """documents why the comparison needs UGSTUB_SYNC: a free-running evaluator of realistic latency answers almost
+    every leaf from the previous leaf's planes"""
+    _, _, err = _reference(tools, 1000, 1, UGSTUB_DELAY_US="150", UGSTUB_STATS="1")
+    line = [ln for ln in err.splitlines() if ln.startswith("ugstub: 1000 calls")][0]
+    stale = int(line.split(",")[1].split()[0])
+    assert stale > 900
