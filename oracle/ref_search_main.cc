@@ -3,7 +3,8 @@
 // ExpandAndBackup, search/UctBoardEvaluator.cpp, gouct/, go/, board/, lib/, platform/ — oracle/Makefile `refsearch`),
 // with unrealgo_b200/host/overlay ahead of the reference root on the include path and libugeval.so +
 // unrealgo_b200/host/DlTFRecordWriter.cc on the link line where TensorFlow used to be.  main() sets the search up the
-// way UctDeepPlayer does (search/UctDeepPlayer.cpp:18-51, :288-320) and runs it from the empty board.
+// way UctDeepPlayer does (search/UctDeepPlayer.cpp:18-51, :288-320) and runs it from the empty board, one search per
+// move, carrying the subtree over when ./dlcfg-19 says reuse_searchtree=true.
 //   usage: ref_search <playouts per move> <moves> [threads]        (./dlcfg-19 names the graph and the checkpoint)
 // Output: one line per move — move index, games played, seconds — then the root's children (move:visits) of the last
 // search and the totals.
@@ -21,6 +22,7 @@
 #include "GoUctGlobalSearch.h"
 #include "GoUctPlayoutPolicy.h"
 #include "SgInit.h"
+#include "UctTreeUtil.h"
 #include "funcapproximator/DlConfig.h"
 #include "platform/SgTimer.h"
 
@@ -46,7 +48,16 @@ int main(int argc, char** argv) {
     std::vector<GoMove> rootFilter;
     search.SetToPlay(bd.ToPlay());
     SgTimer timer;
-    search.StartDeepUCTSearchThread(playouts, 1e9, sequence, &best, 0, 1.0, rootFilter, 0, 0, true);
+    // tree reuse as UctDeepPlayer::DoSearch / FindInitTree do it (search/UctDeepPlayer.cpp:223-231, :290-297): the
+    // subtree below the moves played since the last search becomes the initial tree of this one
+    UctSearchTree* initTree = 0;
+    if (DlConfig::GetInstance().reuse_search_tree()) {
+      initTree = &search.GetTempTree();
+      std::vector<GoPoint> played;
+      if (static_cast<GoUctSearch&>(search).BoardHistory().SequenceToCurrent(bd, played))
+        UctTreeUtil::ExtractSubtree(search.Tree(), *initTree, played, true, 1e9, search.PruneMinCount());
+    }
+    search.StartDeepUCTSearchThread(playouts, 1e9, sequence, &best, 0, 1.0, rootFilter, initTree, 0, true);
     const double t = timer.GetTime();
     const GoMove mv = sequence.empty() ? GO_PASS : sequence[0];
     printf("move %d idx %d games %.0f seconds %.4f\n", m, GoPointUtil::Point2Index(mv), (double)search.GamesPlayed(), t);

@@ -29,12 +29,17 @@ int ug_eval_run_planes(ug_eval* e, const int8_t* planes, int n, double* policy, 
     /* The reference's NetworkEvalThread calls EvaluateState in a free-running loop and hands the result to a search
      * thread whose state_ready flag it finds set AFTERWARDS (search/UctSearch.cpp:186-199), so an evaluation that
      * began before the leaf's features were written is delivered to that leaf.  To observe the search the code
-     * intends, this mode does not start until the buffer holds new, settled content (or 20 ms pass: end of search,
-     * or a transposition with identical history). */
+     * intends, this mode does not start until the buffer holds new content that stayed unchanged for UGSTUB_SETTLE_US (200)
+     * microseconds (or 20 ms pass: end of search, or a transposition with identical history).  A heuristic — the
+     * reference offers no ready-before-evaluate signal to hook — so a search thread descheduled in the middle of
+     * writing its planes for longer than that still gets a wrong answer; the test retries. */
     static uint64_t last = 0;
-    for (int spin = 0; spin < 400; ++spin) {
+    const char* w = getenv("UGSTUB_SETTLE_US");
+    const useconds_t settle = w ? (useconds_t)atoi(w) : 200;
+    for (int spin = 0; spin < 20000 / (int)(2 * settle + 1) + 1; ++spin) {
+      usleep(settle);
       const uint64_t h1 = hash_planes(planes, bytes);
-      usleep(50);
+      usleep(settle);
       const uint64_t h2 = hash_planes(planes, bytes);
       if (h1 == h2 && h1 != last) { last = h1; break; }
     }

@@ -4,8 +4,9 @@ oracle/_ref/ref_search is the reference's unmodified search (search/UctSearch.cp
 by oracle/Makefile `refsearch` with the ugeval include overlay).  Here it runs with tests/cpp/ugeval_stub.c preloaded in
 front of libugeval.so — a stand-in network whose policy/value are a hash of the 17 planes — and the product's
 self-play driver (csrc/selfplay.cpp) runs on a stub leaf queue that computes the same function of the same planes
-(tests/cpp/selfplay_stub.cpp).  One game, one search thread, no tree reuse, PUCT 2.5 (the reference's defaults,
-search/UctSearch.cpp:370-372): the two must choose the same moves and end with the same root visit counts.
+(tests/cpp/selfplay_stub.cpp).  One game, one search thread, PUCT 2.5 (the reference's defaults,
+search/UctSearch.cpp:370-372), with and without carrying the subtree of the played move into the next search: the
+two must choose the same moves and end with the same root visit counts.
 
 The stub answers in its UGSTUB_SYNC mode, i.e. only once the caller's buffer holds the new leaf's features.  Without
 that the reference's free-running NetworkEvalThread (search/UctSearch.cpp:164-199) hands a leaf whatever evaluation
@@ -54,10 +55,10 @@ def _reference(tools, playouts, moves, **env):
     return mv, root, r.stderr
 
 
-def _product(tools, playouts, moves):
+def _product(tools, playouts, moves, reuse=False):
     cwd, _, exe = tools
     e = dict(os.environ, UGSTUB_PRINT_VISITS="1")
-    r = subprocess.run([exe, "1", "1", str(playouts), str(moves), "0", "1", "0"], cwd=cwd, env=e, capture_output=True,
+    r = subprocess.run([exe, "1", "1", str(playouts), str(moves), "1" if reuse else "0", "1", "0"], cwd=cwd, env=e, capture_output=True,
                        text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
     mv, visits = [], {}
@@ -70,19 +71,35 @@ def _product(tools, playouts, moves):
     return mv, visits
 
 
-@pytest.mark.parametrize("playouts,moves", [(300, 30), (800, 8)])
-def test_product_search_matches_the_reference_engine(tools, playouts, moves):
-    ref_moves, ref_root, _ = _reference(tools, playouts, moves, UGSTUB_SYNC="1")
-    got_moves, got_visits = _product(tools, playouts, moves)
+def _write_cfg(tools, reuse):
+    with open(os.path.join(tools[0], "dlcfg-19"), "w") as f:
+        f.write(f"meta_graph=stub.meta\ncheckpoint=stub\nvalue_transform=0\nreuse_searchtree={'true' if reuse else 'false'}\n")
+
+
+@pytest.mark.parametrize("playouts,moves,reuse", [(300, 30, False), (800, 8, False), (300, 30, True), (1000, 6, True)])
+def test_product_search_matches_the_reference_engine(tools, playouts, moves, reuse):
+    """reuse=True: the reference carries the subtree below the played move into the next search
+    (UctTreeUtil::ExtractSubtree, as UctDeepPlayer::FindInitTree does), the product with reuse_tree=1"""
+    _write_cfg(tools, reuse)
+    got_moves, got_visits = _product(tools, playouts, moves, reuse)
+    for attempt in range(3):  # the stub's wait-for-settled-inputs is a heuristic (see ugeval_stub.c): retry under load
+        ref_moves, ref_root, _ = _reference(tools, playouts, moves, UGSTUB_SYNC="1",
+                                            UGSTUB_SETTLE_US=str(200 * (attempt + 1)))
+        if ref_moves == got_moves:
+            break
     assert len(ref_moves) == moves and got_moves == ref_moves
     # the game record is walked from the last move back (UctDeepPlayer::WriteTFRecord): record 0 is the last search
     assert {k: v for k, v in got_visits[0].items() if v > 0} == ref_root
-    assert sum(ref_root.values()) == playouts - 1      # the first playout expands the root
+    if not reuse:
+        assert sum(ref_root.values()) == playouts - 1  # the first playout expands the root
+    else:
+        assert sum(ref_root.values()) > playouts       # visits carried over from the previous search
 
 
 def test_reference_hand_off_delivers_stale_evaluations_without_sync(tools):
     """documents why the comparison needs UGSTUB_SYNC: a free-running evaluator of realistic latency answers almost
     every leaf from the previous leaf's planes"""
+    _write_cfg(tools, False)
     _, _, err = _reference(tools, 1000, 1, UGSTUB_DELAY_US="150", UGSTUB_STATS="1")
     line = [ln for ln in err.splitlines() if ln.startswith("ugstub: 1000 calls")][0]
     stale = int(line.split(",")[1].split()[0])
