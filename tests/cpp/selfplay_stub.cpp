@@ -15,9 +15,12 @@
 struct StubSlot { ug_packed_pos pos; uint32_t legal[UG_MASK_WORDS]; };
 struct ug_queue { std::mutex mu; std::vector<StubSlot*> slots; std::vector<int64_t> free_ids; };
 struct ug_eval { int unused; };
+#ifndef UGSTUB_REAL_TFRECORD
 struct ug_tfrecord { int unused; };
+#endif
 
 extern "C" {
+#ifndef UGSTUB_REAL_TFRECORD  // (with it the real csrc/tfrecord.cpp is linked and UGSTUB_RECORD_DIR receives the files)
 // with UGSTUB_PRINT_VISITS=1 the driver is asked for game records and each record's policy block — the root's visit
 // counts of that move (search/UctSearch.cpp:782-801) — is printed instead of written
 static ug_tfrecord g_rec;
@@ -30,6 +33,7 @@ int ug_tfrecord_write_example(ug_tfrecord*, const void*, size_t, const float* po
   return 0;
 }
 int64_t ug_tfrecord_close(ug_tfrecord*) { return g_rec_no; }
+#endif
 ug_queue* ug_queue_create(ug_eval*, int, int, int) { return new ug_queue(); }
 void ug_queue_destroy(ug_queue* q) { for (StubSlot* s : q->slots) delete s; delete q; }
 int64_t ug_queue_submit(ug_queue* q, const ug_packed_pos* pos, const uint32_t* legal) {
@@ -82,6 +86,7 @@ int main(int argc, char** argv) {
   cfg.max_batch = 64; cfg.timeout_us = 100; cfg.random_opening_moves = argc > 7 ? atoi(argv[7]) : 2; cfg.seed = 9;
   if (argc > 8) cfg.puct = (float)atof(argv[8]);
   if (getenv("UGSTUB_PRINT_VISITS")) cfg.record_dir = "/tmp";
+  if (getenv("UGSTUB_RECORD_DIR")) cfg.record_dir = getenv("UGSTUB_RECORD_DIR");
   std::vector<int16_t> moves((size_t)cfg.games * cfg.max_moves);
   std::vector<int> n_moves((size_t)cfg.games);
   ug_selfplay_stats st{};

@@ -21,8 +21,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SEARCH = os.path.join(ROOT, "oracle", "_ref", "ref_search")
 
-pytestmark = pytest.mark.skipif(not os.path.exists(REF_SEARCH),
-                                reason="oracle/_ref/ref_search not built (needs the reference tree and libugeval.so)")
+REF_SELFPLAY = os.path.join(ROOT, "oracle", "_ref", "ref_selfplay")
+needs_engine = pytest.mark.skipif(not os.path.exists(REF_SEARCH),
+                                  reason="oracle/_ref/ref_search not built (needs the reference tree and libugeval.so)")
 
 
 @pytest.fixture(scope="module")
@@ -76,6 +77,7 @@ def _write_cfg(tools, reuse):
         f.write(f"meta_graph=stub.meta\ncheckpoint=stub\nvalue_transform=0\nreuse_searchtree={'true' if reuse else 'false'}\n")
 
 
+@needs_engine
 @pytest.mark.parametrize("playouts,moves,reuse", [(300, 30, False), (800, 8, False), (300, 30, True), (1000, 6, True)])
 def test_product_search_matches_the_reference_engine(tools, playouts, moves, reuse):
     """reuse=True: the reference carries the subtree below the played move into the next search
@@ -96,6 +98,7 @@ def test_product_search_matches_the_reference_engine(tools, playouts, moves, reu
         assert sum(ref_root.values()) > playouts       # visits carried over from the previous search
 
 
+@needs_engine
 def test_reference_hand_off_delivers_stale_evaluations_without_sync(tools):
     """documents why the comparison needs UGSTUB_SYNC: a free-running evaluator of realistic latency answers almost
     every leaf from the previous leaf's planes"""
@@ -104,3 +107,55 @@ def test_reference_hand_off_delivers_stale_evaluations_without_sync(tools):
     line = [ln for ln in err.splitlines() if ln.startswith("ugstub: 1000 calls")][0]
     stale = int(line.split(",")[1].split()[0])
     assert stale > 900
+
+
+# ---- whole self-play games: the reference's own player (search/UctDeepPlayer.cpp) against the product's driver
+
+
+@pytest.fixture(scope="module")
+def recorder(tmp_path_factory):
+    """the product's self-play driver on the stub queue, linked with the real record writer (csrc/tfrecord.cpp)"""
+    d = tmp_path_factory.mktemp("recorder")
+    exe = str(d / "selfplay_stub_rec")
+    cpp, csrc = os.path.join(ROOT, "tests", "cpp"), os.path.join(ROOT, "unrealgo_b200", "csrc")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-DUGSTUB_REAL_TFRECORD", "-I/usr/local/cuda/include",
+                    os.path.join(cpp, "selfplay_stub.cpp"), os.path.join(csrc, "selfplay.cpp"),
+                    os.path.join(csrc, "tfrecord.cpp"), os.path.join(csrc, "tfmodel.cpp"), "-o", exe],
+                   check=True, capture_output=True)
+    return str(d), exe
+
+
+def _product_game(recorder, moves):
+    d, exe = recorder
+    rec = os.path.join(d, f"rec{moves}")
+    os.makedirs(rec, exist_ok=True)
+    # 4000 playouts per move = MAX_SEARCH_ITERATIONS (search/UctDeepPlayer.cpp:15), tree reuse on, komi 7.5 by default
+    r = subprocess.run([exe, "1", "1", "4000", str(moves), "1", "1", "0"], env=dict(os.environ, UGSTUB_RECORD_DIR=rec),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    return open(os.path.join(rec, "selfplay_0.tfrecord"), "rb").read()
+
+
+def test_selfplay_records_equal_the_reference_players_golden_file(recorder):
+    """tests/golden/ref_selfplay_14.tfrecords.gz was written by the reference's own UctDeepPlayer (generator:
+    tests/golden/make_ref_selfplay_golden.py): 14 moves x 4000 playouts with tree reuse, then WriteTFRecord — planes,
+    visit-count policies and rewards of every position.  The product's driver must write the same bytes."""
+    import gzip
+    want = gzip.decompress(open(os.path.join(ROOT, "tests", "golden", "ref_selfplay_14.tfrecords.gz"), "rb").read())
+    got = _product_game(recorder, 14)
+    assert len(want) == 14 * 7665 and got == want
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SELFPLAY), reason="oracle/_ref/ref_selfplay not built")
+def test_live_reference_player_writes_the_same_records(tools, recorder):
+    cwd, stub, _ = tools
+    _write_cfg(tools, True)
+    got = _product_game(recorder, 4)
+    for attempt in range(3):
+        out = os.path.join(cwd, f"ref_game_{attempt}.tfrecords")
+        e = dict(os.environ, LD_PRELOAD=stub, UGSTUB_SYNC="1", UGSTUB_SETTLE_US=str(150 * (attempt + 1)))
+        r = subprocess.run([REF_SELFPLAY, "4", out], cwd=cwd, env=e, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+        if open(out, "rb").read() == got:
+            break
+    assert open(out, "rb").read() == got
