@@ -10,6 +10,7 @@
 // search and the totals.
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include <unistd.h>
@@ -28,8 +29,51 @@
 
 typedef GoUctGlobalSearch<GoUctPlayoutPolicy<GoUctBoard>, GoUctPlayoutPolicyFactory<GoUctBoard> > SearchType;
 
+// `ref_search features <games.txt> <out.bin>`: no search, no evaluator — for every game (one line of policy indices,
+// 361 = pass) the moves are played on the engine's board and after each one the search thread's state is brought up
+// to date (GoUctState::StartSearch -> GoBoardSynchronizer) and asked for its planes with the reference's own
+// GoUctGlobalSearchState::CollectFeatures (gouct/GoUctGlobalSearch.h:160-206), the very call ExpandAndBackup makes
+// (search/UctSearch.cpp:512).  out.bin receives char[17][19][19] per position, the initial position first.
+static int dump_features(const char* games_path, const char* out_path) {
+  SgInit();
+  GoInit();
+  GoBoard bd(GO_MAX_SIZE);
+  GoUctPlayoutPolicyParam policyParam;
+  GoUctDefaultMoveFilterParam filterParam;
+  SearchType search(bd, new GoUctPlayoutPolicyFactory<GoUctBoard>(policyParam), policyParam, filterParam);
+  search.CreateThreads();
+  typedef GoUctGlobalSearchState<GoUctPlayoutPolicy<GoUctBoard> > StateType;
+  StateType& state = dynamic_cast<StateType&>(search.ThreadState(0));
+  FILE* in = fopen(games_path, "r");
+  FILE* out = fopen(out_path, "wb");
+  if (!in || !out) return 2;
+  static char line[1 << 16];
+  static char planes[NUM_MAPS][GO_MAX_SIZE][GO_MAX_SIZE];
+  long positions = 0;
+  while (fgets(line, sizeof(line), in)) {
+    bd.Init(GO_MAX_SIZE);
+    char* p = line;
+    for (;;) {
+      state.StartSearch();
+      state.CollectFeatures(planes, NUM_MAPS);
+      fwrite(planes, 1, sizeof(planes), out);
+      ++positions;
+      char* end;
+      const long idx = strtol(p, &end, 10);
+      if (end == p) break;
+      p = end;
+      bd.Play(idx == GO_MAX_ONBOARD ? GO_PASS : GoPointUtil::Pt((int)(idx % GO_MAX_SIZE) + 1, (int)(idx / GO_MAX_SIZE) + 1));
+    }
+  }
+  fclose(out);
+  printf("positions %ld\n", positions);
+  fflush(stdout);
+  _exit(0);
+}
+
 int main(int argc, char** argv) {
-  if (argc < 3) { fprintf(stderr, "usage: %s playouts moves [threads]\n", argv[0]); return 2; }
+  if (argc == 4 && std::string(argv[1]) == "features") return dump_features(argv[2], argv[3]);
+  if (argc < 3) { fprintf(stderr, "usage: %s playouts moves [threads] | features games.txt out.bin\n", argv[0]); return 2; }
   const double playouts = atof(argv[1]);
   const int moves = atoi(argv[2]);
   SgInit();

@@ -15,10 +15,12 @@
  *      colours (captures, simple ko, suicide), undo, and the 17 planes;
  *  (2) the reference's own DlConfig/ArrayUtil sources compiled into the same library;
  *  (3) self-made known-answer vectors in tests/golden/encoder_kat.npz.
- * What stays a restatement: the ~40-line CollectFeatures loop itself (its template sits on the search stack and
- * does not compile here; oracle/ref_board_shim.cc performs the same board calls on the real board),
- * TransformFeature's loop (TensorFlow-dependent file; its index formula GetOffset IS pinned), value_transform and
- * UpdatePrior (inside TensorFlow- and search-dependent files).
+ *      The CollectFeatures template itself is executed as well (oracle/_ref/ref_search `features`: the reference's
+ *      whole search stack compiles): its planes after every move of 21 games are tests/golden/ref_collect_features.npz
+ *      and og_collect_features reproduces all 2966.
+ * What stays a restatement: TransformFeature's loop (TensorFlow-dependent file; its index formula GetOffset IS
+ * pinned), value_transform and UpdatePrior as stand-alone functions (UpdatePrior runs inside the engine-level search
+ * parity, tests/test_reference_search_parity.py).
  *
  * Each function cites the reference lines it follows.
  */

@@ -95,5 +95,39 @@ def main():
           os.path.getsize(os.path.join(HERE, "ref_board.npz")), "bytes")
 
 
+def collect_features_golden():
+    """tests/golden/ref_collect_features.npz: the planes of the reference's own CollectFeatures TEMPLATE
+    (GoUctGlobalSearchState::CollectFeatures, gouct/GoUctGlobalSearch.h:160-206, compiled with the whole search stack into
+    oracle/_ref/ref_search — `ref_search features`) after every move of the alternating games of ref_board.npz."""
+    import subprocess
+    import tempfile
+    G = np.load(os.path.join(HERE, "ref_board.npz"))
+    games = []
+    for g in range(int(G["op_game"].max()) + 1):
+        sel = np.nonzero(G["op_game"] == g)[0]
+        ops, cols = G["ops"][sel].tolist(), G["op_color"][sel].tolist()
+        if -3 in ops:
+            cut = ops.index(-3)
+            ops, cols = ops[:cut], cols[:cut]
+        if UNDO in ops or cols != [k & 1 for k in range(len(ops))]:
+            continue
+        games.append(ops)
+    d = tempfile.mkdtemp(prefix="refplanes_")
+    with open(os.path.join(d, "games.txt"), "w") as f:
+        f.write("".join(" ".join(map(str, ops)) + "\n" for ops in games))
+    subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_search"), "features", "games.txt", "out.bin"], cwd=d,
+                   check=True, capture_output=True)
+    planes = np.fromfile(os.path.join(d, "out.bin"), np.int8).reshape(-1, 17 * 361)
+    assert len(planes) == sum(len(ops) + 1 for ops in games) and set(np.unique(planes).tolist()) <= {0, 1}
+    np.savez_compressed(os.path.join(HERE, "ref_collect_features.npz"),
+                        moves=np.array([m for ops in games for m in ops], np.int16),
+                        game_len=np.array([len(ops) for ops in games], np.int32),
+                        planes=np.packbits(planes.astype(np.uint8), axis=1))
+    print("ref_collect_features.npz:", len(games), "games,", len(planes), "positions,",
+          os.path.getsize(os.path.join(HERE, "ref_collect_features.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if "--planes-only" not in sys.argv:
+        main()
+    collect_features_golden()

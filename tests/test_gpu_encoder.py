@@ -72,3 +72,23 @@ def test_encoder_matches_the_reference_boards_planes(ev):
                 want.append(np.unpackbits(G["s_planes"][samples[n]])[:17 * 361].reshape(17, 19, 19).astype(np.int8))
     assert len(packed) > 350
     assert np.array_equal(ev.encode_planes(np.stack(packed)), np.stack(want))
+
+
+def test_encoder_matches_the_reference_collect_features_template(ev):
+    """tests/golden/ref_collect_features.npz holds the output of the reference's own CollectFeatures template
+    (`ref_search features`, see tests/golden/make_ref_board_golden.py) after every move of 21 games — 2966 positions.
+    Packed histories of the same games from the self-play driver's board, through the CUDA encoder, must equal it."""
+    import os
+    from unrealgo_b200 import ProductBoard
+    F = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_collect_features.npz"))
+    want = np.unpackbits(F["planes"], axis=1)[:, :17 * 361].reshape(-1, 17, 19, 19).astype(np.int8)
+    packed, at = [], 0
+    for n in F["game_len"].tolist():
+        pb = ProductBoard()
+        packed.append(pb.pack())
+        for mv in F["moves"][at:at + n].tolist():
+            pb.play(mv)
+            packed.append(pb.pack())
+        at += n
+    assert len(packed) == len(want) == 2966
+    assert np.array_equal(ev.encode_planes(np.stack(packed)), want)

@@ -137,3 +137,73 @@ def test_product_host_board_matches_the_reference_board():
                 assert pb.score(0.0) == G["s_score"][i, 0] and pb.score(7.5) == G["s_score"][i, 1], (g, n)
                 checked += 1
     assert games >= 21 and checked > 350
+
+
+def _template_fixture():
+    F = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_collect_features.npz"))
+    planes = np.unpackbits(F["planes"], axis=1)[:, :17 * 361].reshape(-1, 17, 19, 19).astype(np.int8)
+    games, at = [], 0
+    for n in F["game_len"].tolist():
+        games.append(F["moves"][at:at + n].tolist())
+        at += n
+    return games, planes
+
+
+def test_collect_features_template_golden():
+    """tests/golden/ref_collect_features.npz: planes written by the reference's own CollectFeatures template (generator:
+    make_ref_board_golden.py, `ref_search features`) after every move of 21 games, 2966 positions.  The oracle's
+    restatement and the product's host board reproduce every one."""
+    games, planes = _template_fixture()
+    assert len(planes) == sum(len(g) + 1 for g in games) == 2966
+    at = 0
+    for g in games:
+        ob, pb = oracle.Board(), ProductBoard()
+        for n in range(len(g) + 1):
+            if n > 0:
+                ob.play(g[n - 1])
+                pb.play(g[n - 1])
+            assert np.array_equal(ob.collect_features(), planes[at + n]), (at, n)
+            assert np.array_equal(pb.planes(), planes[at + n]), (at, n)
+        at += len(g) + 1
+
+
+REF_SEARCH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_search")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SEARCH), reason="oracle/_ref/ref_search not built (needs the reference tree)")
+def test_the_real_collect_features_template_on_every_position(tmp_path):
+    """`ref_search features` calls the reference's own GoUctGlobalSearchState::CollectFeatures (the template, compiled
+    with the whole search stack) on the search thread's state after every move of the alternating games: the fixture's
+    planes (made by oracle/ref_board_shim.cc driving the real board), the oracle's restatement and the product's host
+    board must all equal it — at every position, not only the sampled ones"""
+    import subprocess
+    games = []
+    for g in range(N_GAMES):
+        ops = _ops_of(g)
+        if SET_TO_PLAY in [op for op, _ in ops]:
+            ops = ops[:[op for op, _ in ops].index(SET_TO_PLAY)]
+        if UNDO in [op for op, _ in ops] or [c for _, c in ops] != [k & 1 for k in range(len(ops))]:
+            continue
+        games.append((g, [op for op, _ in ops]))
+    (tmp_path / "games.txt").write_text("".join(" ".join(map(str, ops)) + "\n" for _, ops in games))
+    r = subprocess.run([REF_SEARCH, "features", "games.txt", "out.bin"], cwd=str(tmp_path), capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    real = np.fromfile(str(tmp_path / "out.bin"), np.int8).reshape(-1, 17, 19, 19)
+    assert len(real) == sum(len(ops) + 1 for _, ops in games) > 2500
+    at = sampled = 0
+    for g, ops in games:
+        samples = _samples_of(g)
+        ob, pb = oracle.Board(), ProductBoard()
+        for n in range(len(ops) + 1):
+            if n > 0:
+                ob.play(ops[n - 1])
+                pb.play(ops[n - 1])
+            assert np.array_equal(ob.collect_features(), real[at + n]), (g, n)
+            assert np.array_equal(pb.planes(), real[at + n]), (g, n)
+            if n in samples and G["s_has_planes"][samples[n]]:
+                want = np.unpackbits(G["s_planes"][samples[n]])[:17 * 361].reshape(17, 19, 19).astype(np.int8)
+                assert np.array_equal(want, real[at + n]), (g, n)
+                sampled += 1
+        at += len(ops) + 1
+    assert sampled > 350
