@@ -104,6 +104,10 @@ int main(int argc, char** argv) {
     search.StartDeepUCTSearchThread(playouts, 1e9, sequence, &best, 0, 1.0, rootFilter, initTree, 0, true);
     const double t = timer.GetTime();
     const GoMove mv = sequence.empty() ? GO_PASS : sequence[0];
+    if (mv == GO_PASS && bd.GetLastMove() == GO_PASS) {  // the game is over, the second pass is not played
+      printf("game over after %d moves\n", m);         // (SelfPlayOneGame, search/UctDeepPlayer.cpp:82-88)
+      break;
+    }
     printf("move %d idx %d games %.0f seconds %.4f\n", m, GoPointUtil::Point2Index(mv), (double)search.GamesPlayed(), t);
     total_games += search.GamesPlayed();
     total_time += t;

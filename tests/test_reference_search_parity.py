@@ -86,7 +86,7 @@ def test_product_search_matches_the_reference_engine(tools, playouts, moves, reu
     got_moves, got_visits = _product(tools, playouts, moves, reuse)
     for attempt in range(3):  # the stub's wait-for-settled-inputs is a heuristic (see ugeval_stub.c): retry under load
         ref_moves, ref_root, _ = _reference(tools, playouts, moves, UGSTUB_SYNC="1",
-                                            UGSTUB_SETTLE_US=str(200 * (attempt + 1)))
+                                            UGSTUB_SETTLE_US=str(250 * (attempt + 1)))
         if ref_moves == got_moves:
             break
     assert len(ref_moves) == moves and got_moves == ref_moves
@@ -96,6 +96,26 @@ def test_product_search_matches_the_reference_engine(tools, playouts, moves, reu
         assert sum(ref_root.values()) == playouts - 1  # the first playout expands the root
     else:
         assert sum(ref_root.values()) > playouts       # visits carried over from the previous search
+
+
+@needs_engine
+def test_a_whole_game_through_the_endgame(tools):
+    """40 playouts per move with tree reuse until the game ends (more than 400 moves): captures, kos, eyes that may not
+    be filled, passes that are only chosen when nothing else is left, leaves without moves after two passes.  The
+    reference stops when the search answers a pass with a pass and does not play it (SelfPlayOneGame,
+    search/UctDeepPlayer.cpp:82-88); the product's driver records that second pass and then ends the game."""
+    _write_cfg(tools, True)
+    got_moves, _ = _product(tools, 40, 700, True)
+    assert got_moves[-2:] == [361, 361] and len(got_moves) > 300
+    for attempt in range(3):
+        cwd, stub, _ = tools
+        e = dict(os.environ, LD_PRELOAD=stub, UGSTUB_SYNC="1", UGSTUB_SETTLE_US=str(250 * (attempt + 1)))
+        r = subprocess.run([REF_SEARCH, "40", "700"], cwd=cwd, env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "game over" in r.stdout, r.stdout[-500:] + r.stderr[-500:]
+        ref_moves = [int(ln.split()[3]) for ln in r.stdout.splitlines() if ln.startswith("move ")]
+        if ref_moves == got_moves[:-1]:
+            break
+    assert ref_moves == got_moves[:-1]
 
 
 @needs_engine
