@@ -218,8 +218,9 @@ typedef struct ug_selfplay_config {
   /* 0/1: one leaf per game in flight — the shipped FORCE_SINGLE_THREAD search (CMakeLists.txt:15).  k > 1: up to k
    * descents of one tree in flight with the reference's multi-thread virtual-loss bookkeeping (a counter on every node
    * of a descent until its backup, search/UctSearch.cpp:814-850; Select adds the parent's count minus one to the
-   * visit total, :1066-1070; GetMeanValue counts a child's virtual losses as zero-valued visits, :664-680), so that a
-   * single game can fill a batch.  Results then depend on the order evaluations return. */
+   * visit total, :1066-1070; a child's virtual losses count as zero-valued visits in its mean — the statistics branch
+   * of GetMeanValue, :665-679, not the USE_DIRECT_VISITCOUNT one of the shipped build, :661-664, which ignores them),
+   * so that a single game can fill a batch.  Results then depend on the order evaluations return. */
   int leaves_per_game;
 } ug_selfplay_config;
 typedef struct ug_selfplay_stats {

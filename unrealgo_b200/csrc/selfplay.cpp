@@ -204,7 +204,10 @@ uint32_t select_child(const Tree& t, uint32_t parent, float c_puct) {
 
 // The same selection with several descents of one tree in flight (the reference with num_threads > 1 and
 // use_virtual_loss): the parent's total gains its virtual-loss count minus one (search/UctSearch.cpp:1066-1070) and a
-// child's mean is diluted by its virtual losses counted as zero-valued visits (GetMeanValue, :664-680).
+// child's mean is diluted by its virtual losses counted as zero-valued visits — the statistics branch of GetMeanValue
+// (:665-679).  The shipped build defines USE_DIRECT_VISITCOUNT (CMakeLists.txt:16), whose branch (:661-664) returns the
+// plain mean and so does not steer concurrent descents apart at all; with several leaves of one tree in flight that
+// would send every descent to the same leaf, hence the other branch here.
 uint32_t select_child_vloss(const Tree& t, uint32_t parent, float c_puct) {
   const uint32_t base = t.first_child[parent];
   uint32_t n = t.n_children[parent];
