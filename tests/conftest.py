@@ -13,6 +13,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_sessionstart(session):
+    """a fresh checkout has no built artefacts (they are git-ignored): build them once, as __graft_entry__.build() does
+    — the product library with nvcc, then the oracle and, where /root/reference exists, oracle/_ref"""
+    import shutil
+    lib = os.path.join(ROOT, "unrealgo_b200", "lib", "libugeval.so")
+    if not os.path.exists(lib) and shutil.which("nvcc"):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 @pytest.fixture(scope="session")
 def ckpt_dir(tmp_path_factory):
     return str(tmp_path_factory.mktemp("ckpt"))
