@@ -48,20 +48,21 @@ def test_reference_search_engine_runs_on_ugeval(small_ckpt, tmp_path):
     assert sum(visits.values()) >= 299 and len(visits) > 1 and out["playouts_per_s"] > 50
 
 
+@pytest.mark.parametrize("playouts,moves,reuse", [(160, 10, False), (200, 12, True)])
 @pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/ref_search not prebuilt (needs the reference tree)")
-def test_reference_engine_and_product_driver_play_the_same_game_on_the_gpu(small_ckpt, tmp_path):
+def test_reference_engine_and_product_driver_play_the_same_game_on_the_gpu(small_ckpt, tmp_path, playouts, moves, reuse):
     """Both on the CUDA evaluator: the reference's engine through UctBoardEvaluator -> ug_eval_run_planes (host planes
     in, doubles out, its own UpdatePrior in double), the product's self-play driver through the leaf queue
     (packed positions, legal-mask renormalisation in the head kernel, floats).  With the reference's hand-off made
-    leaf-accurate (tests/cpp/ugeval_sync_preload.c) the two searches must choose the same moves."""
+    leaf-accurate (tests/cpp/ugeval_sync_preload.c) the two searches must choose the same moves, from a fresh tree per
+    move and with the played move's subtree carried over."""
     from unrealgo_b200 import DlTFNetworkEvaluator, selfplay
     meta, prefix = small_ckpt
-    playouts, moves = 160, 10
     ev = DlTFNetworkEvaluator("", feature_input="feature_input", outputs=OUTS.split(":"), max_batch=64)
     try:
         ev.LoadGraph(meta)
         ev.UpdateCheckPoint(prefix)
-        _, games = selfplay(ev, games=1, threads=1, playouts_per_move=playouts, max_moves=moves, reuse_tree=False,
+        _, games = selfplay(ev, games=1, threads=1, playouts_per_move=playouts, max_moves=moves, reuse_tree=reuse,
                             random_opening_moves=0, record_moves=True, max_batch=64, leaves_per_game=1)
     finally:
         ev.close()
@@ -70,7 +71,7 @@ def test_reference_engine_and_product_driver_play_the_same_game_on_the_gpu(small
                     "-ldl"], check=True)
     with open(os.path.join(str(tmp_path), "dlcfg-19"), "w") as f:
         f.write(f"meta_graph={meta}\ncheckpoint={prefix}\nnn_input=feature_input\nnn_outputs={OUTS}\n"
-                "value_transform=0\nreuse_searchtree=false\n")
+                f"value_transform=0\nreuse_searchtree={'true' if reuse else 'false'}\n")
     ref_moves = None
     for attempt in range(3):
         e = dict(os.environ, LD_PRELOAD=so, UGSTUB_SETTLE_US=str(250 * (attempt + 1)))
