@@ -207,3 +207,35 @@ def test_the_real_collect_features_template_on_every_position(tmp_path):
                 sampled += 1
         at += len(ops) + 1
     assert sampled > 350
+
+
+def test_live_fuzz_product_board_against_the_reference_board():
+    """where libugref.so exists: 30 more random games to the end (moves drawn from the reference's GenerateLegalMoves
+    list, so eyes are never filled and games finish by two passes) — after every move the product board's move list
+    equals the reference's, every fourth move also planes, Tromp-Taylor score and the oracle's planes"""
+    try:
+        oracle.RefBoard()
+    except RuntimeError:
+        pytest.skip("oracle/_ref/libugref.so not built here (needs the reference tree)")
+    rng = np.random.default_rng(77)
+    positions = finished = 0
+    for g in range(30):
+        rb, pb, ob = oracle.RefBoard(), ProductBoard(), oracle.Board()
+        for n in range(500):
+            want = rb.generate()
+            got, _ = pb.generate()
+            assert np.array_equal(got.astype(np.int64), want.astype(np.int64)), (g, n)
+            if len(want) == 0:
+                finished += 1
+                break
+            if n % 4 == 0:
+                planes = rb.collect_features()
+                assert np.array_equal(pb.planes(), planes) and np.array_equal(ob.collect_features(), planes), (g, n)
+                assert pb.score(7.5) == rb.score(7.5), (g, n)
+            # mostly a random non-pass move; the pass (last entry) when it is the only one or now and then
+            mv = int(want[-1]) if len(want) == 1 or rng.random() < 0.01 else int(rng.choice(want[:-1]))
+            assert not rb.play(mv)
+            pb.play(mv)
+            ob.play(mv)
+            positions += 1
+    assert positions > 8000 and finished >= 25
