@@ -20,8 +20,14 @@ def main():
         f.write(f"meta_graph={meta}\ncheckpoint={prefix}\nnn_input=feature_input\nnn_outputs={outs}\n"
                 "value_transform=0\nreuse_searchtree=false\n")
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_search")
-    r = subprocess.run([exe, str(playouts), "2"], cwd=d, capture_output=True, text=True, timeout=600)
-    print("reference engine on libugeval (20x256):", [ln for ln in r.stdout.splitlines() if ln.startswith("total")], "rc", r.returncode)
+    for threads in (1, 16):  # 16 = MAX_BATCHES, the most the engine's EvalBuffer holds (DlTFNetworkEvaluator.h:15)
+        try:
+            r = subprocess.run([exe, str(playouts * (4 if threads > 1 else 1)), "2", str(threads)], cwd=d,
+                               capture_output=True, text=True, timeout=90)
+            print(f"reference engine on libugeval (20x256), {threads} search thread(s):",
+                  [ln for ln in r.stdout.splitlines() if ln.startswith("total")], "rc", r.returncode)
+        except subprocess.TimeoutExpired:
+            print(f"reference engine with {threads} search thread(s): no result within 90 s")
 
 
 if __name__ == "__main__":
