@@ -49,6 +49,10 @@ typedef struct ug_packed_pos {
   uint32_t to_play;
   uint32_t reserved[3];
 } ug_packed_pos; /* 784 bytes */
+/* For a caller that already holds CollectFeatures' output (char[17][19][19], gouct/GoUctGlobalSearch.h:160-206) — the
+ * reference's own search state — and wants to hand the leaf to the queue: the same information, 784 bytes instead
+ * of 6137.  Any non-zero byte counts as a stone; plane 16 (1 - to_play) gives the side to move.  Host only. */
+void ug_pack_planes(const int8_t* planes_chw, ug_packed_pos* out);
 
 typedef struct ug_net_info {
   int blocks;           /* residual blocks */

@@ -12,8 +12,6 @@
 #include "../../include/ugeval.h"
 #include "stub_eval.h"
 
-struct StubSlot { ug_packed_pos pos; uint32_t legal[UG_MASK_WORDS]; };
-struct ug_queue { std::mutex mu; std::vector<StubSlot*> slots; std::vector<int64_t> free_ids; };
 struct ug_eval { int unused; };
 #ifndef UGSTUB_REAL_TFRECORD
 struct ug_tfrecord { int unused; };
@@ -34,49 +32,8 @@ int ug_tfrecord_write_example(ug_tfrecord*, const void*, size_t, const float* po
 }
 int64_t ug_tfrecord_close(ug_tfrecord*) { return g_rec_no; }
 #endif
-ug_queue* ug_queue_create(ug_eval*, int, int, int) { return new ug_queue(); }
-void ug_queue_destroy(ug_queue* q) { for (StubSlot* s : q->slots) delete s; delete q; }
-int64_t ug_queue_submit(ug_queue* q, const ug_packed_pos* pos, const uint32_t* legal) {
-  std::lock_guard<std::mutex> lk(q->mu);
-  int64_t id;
-  if (!q->free_ids.empty()) { id = q->free_ids.back(); q->free_ids.pop_back(); }
-  else { id = (int64_t)q->slots.size(); q->slots.push_back(new StubSlot()); }
-  q->slots[(size_t)id]->pos = *pos;
-  memcpy(q->slots[(size_t)id]->legal, legal, sizeof(q->slots[0]->legal));
-  return id;
 }
-int ug_queue_poll(ug_queue* q, int64_t ticket, float* policy, float* value) {
-  if (ticket < 0) return -1;
-  StubSlot s;
-  {
-    std::lock_guard<std::mutex> lk(q->mu);
-    s = *q->slots[(size_t)ticket];
-    q->free_ids.push_back(ticket);
-  }
-  // the 17 planes CollectFeatures would hand the network (csrc/encode.cu does this on the GPU), then the shared stub
-  // network, then the legal-move renormalisation the head kernel applies in float (UpdatePrior)
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(&s.pos);
-  const uint32_t tp = w[2 * UG_HISTORY * UG_MASK_WORDS] & 1u;
-  int8_t planes[17 * 361];
-  for (int k = 0; k < UG_HISTORY; ++k)
-    for (int c = 0; c < 2; ++c) {
-      const uint32_t* m = w + (c * UG_HISTORY + k) * UG_MASK_WORDS;  // black[8][12] then white[8][12]
-      int8_t* out = planes + (2 * k + (int)(c ^ tp)) * 361;
-      for (int i = 0; i < 361; ++i) out[i] = (int8_t)((m[i >> 5] >> (i & 31)) & 1u);
-    }
-  memset(planes + 16 * 361, 1 - (int)tp, 361);
-  stub_eval(planes, policy, value);
-  float sum = 0.f;
-  for (int i = 0; i < UG_NUM_MOVES; ++i) {
-    if (!((s.legal[i >> 5] >> (i & 31)) & 1u)) policy[i] = 0.f;
-    sum += policy[i];
-  }
-  for (int i = 0; i < UG_NUM_MOVES; ++i) policy[i] /= sum;
-  return 1;
-}
-int ug_queue_wait(ug_queue* q, int64_t t, float* p, float* v) { return ug_queue_poll(q, t, p, v) == 1 ? 0 : -1; }
-int ug_queue_stats(ug_queue*, uint64_t* a, uint64_t* b, uint64_t* c) { *a = *b = *c = 0; return 0; }
-}
+#include "stub_queue.h"
 
 int main(int argc, char** argv) {
   if (argc < 7) { fprintf(stderr, "usage: games threads playouts moves reuse leaves_per_game [random_opening_moves=2] [puct]\n"); return 2; }

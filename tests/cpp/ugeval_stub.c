@@ -7,17 +7,18 @@
 #include <string.h>
 #include <unistd.h>
 
+#include "../../include/ugeval.h"
 #include "stub_eval.h"
 
-typedef struct ug_eval { int unused; } ug_eval;
+struct ug_eval { int unused; };
 ug_eval* ug_eval_create(int device, int precision, int max_batch) { return (ug_eval*)calloc(1, sizeof(ug_eval)); }
 void ug_eval_destroy(ug_eval* e) { free(e); }
 int ug_eval_load_graph(ug_eval* e, const char* path) { return 0; }
 int ug_eval_load_checkpoint(ug_eval* e, const char* prefix) { return 0; }
-int ug_eval_ready(ug_eval* e) { return 1; }
+int ug_eval_ready(const ug_eval* e) { return 1; }
 int ug_eval_set_io(ug_eval* e, const char* in, const char* const* outs, int n) { return 0; }
 int ug_eval_set_value_transform(ug_eval* e, int vt) { return 0; }
-const char* ug_last_error(ug_eval* e) { return "stub evaluator"; }
+const char* ug_last_error(const ug_eval* e) { return "stub evaluator"; }
 static uint64_t hash_planes(const volatile int8_t* p, size_t n) {
   uint64_t h = 1469598103934665603ull;
   for (size_t i = 0; i < n; ++i) { h ^= (uint8_t)p[i]; h *= 1099511628211ull; }

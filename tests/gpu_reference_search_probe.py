@@ -28,6 +28,16 @@ def main():
                   [ln for ln in r.stdout.splitlines() if ln.startswith("total")], "rc", r.returncode)
         except subprocess.TimeoutExpired:
             print(f"reference engine with {threads} search thread(s): no result within 90 s")
+    # the same engine with the leaf-queue patch: every search thread owns a ticket
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_search_queue")
+    for threads in (1, 16, 64, 128, 256):
+        try:
+            r = subprocess.run([exe, str(playouts * max(1, threads // 2)), "2", str(threads)], cwd=d,
+                               capture_output=True, text=True, timeout=60)
+            print(f"reference engine + ugeval leaf queue, {threads} search thread(s):",
+                  [ln for ln in r.stdout.splitlines() if ln.startswith("total")], "rc", r.returncode)
+        except subprocess.TimeoutExpired:
+            print(f"queue-patched engine with {threads} search thread(s): no result within 60 s")
 
 
 if __name__ == "__main__":

@@ -100,3 +100,25 @@ def test_score_and_host_planes_match_the_oracle():
         assert pb.score(0.5) == _tromp_taylor(ob.colors(), 0.5)
         # the planes written to self-play records == CollectFeatures' undo/replay walk
         assert np.array_equal(pb.planes(), ob.collect_features())
+
+
+def test_pack_planes_is_the_inverse_of_collect_features():
+    """ug_pack_planes: from CollectFeatures' char[17][19][19] back to the 784-byte packed leaf the queue takes — checked
+    on the planes of the reference's own CollectFeatures template (tests/golden/ref_collect_features.npz) against the
+    packed history the self-play driver's board keeps for the same positions"""
+    import os
+    from unrealgo_b200 import pack_planes
+    F = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_collect_features.npz"))
+    planes = np.unpackbits(F["planes"], axis=1)[:, :17 * 361].reshape(-1, 17, 19, 19).astype(np.int8)
+    got = pack_planes(planes)
+    want, at = [], 0
+    for n in F["game_len"].tolist():
+        pb = ProductBoard()
+        want.append(pb.pack())
+        for mv in F["moves"][at:at + n].tolist():
+            pb.play(mv)
+            want.append(pb.pack())
+        at += n
+    assert np.array_equal(got, np.stack(want))
+    # any non-zero byte is a stone, like (bool)char in TransformFeature
+    assert np.array_equal(pack_planes(planes[100:110] * 5), got[100:110])

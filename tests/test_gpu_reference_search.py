@@ -82,3 +82,32 @@ def test_reference_engine_and_product_driver_play_the_same_game_on_the_gpu(small
         if ref_moves == games[0]:
             break
     assert ref_moves == games[0]
+
+
+EXE_QUEUE = os.path.join(ROOT, "oracle", "_ref", "ref_search_queue")
+
+
+@pytest.mark.parametrize("playouts,moves,reuse", [(160, 10, False), (200, 12, True)])
+@pytest.mark.skipif(not os.path.exists(EXE_QUEUE), reason="oracle/_ref/ref_search_queue not prebuilt")
+def test_reference_engine_with_the_leaf_queue_patch(small_ckpt, tmp_path, playouts, moves, reuse):
+    """INTEGRATION.md section 2 applied for real: unrealgo_b200/host/patches/uctsearch_leaf_queue.patch puts
+    ug_queue_submit/ug_queue_wait where the reference's ExpandAndBackup handed its leaf to NetworkEvalThread.  Every
+    leaf now gets its own evaluation, so no synchronising shim is needed: the patched engine and the product's
+    self-play driver, both on the CUDA evaluator through the queue, play the same game."""
+    from unrealgo_b200 import DlTFNetworkEvaluator, selfplay
+    meta, prefix = small_ckpt
+    ev = DlTFNetworkEvaluator("", feature_input="feature_input", outputs=OUTS.split(":"), max_batch=64)
+    try:
+        ev.LoadGraph(meta)
+        ev.UpdateCheckPoint(prefix)
+        _, games = selfplay(ev, games=1, threads=1, playouts_per_move=playouts, max_moves=moves, reuse_tree=reuse,
+                            random_opening_moves=0, record_moves=True, max_batch=64, leaves_per_game=1)
+    finally:
+        ev.close()
+    with open(os.path.join(str(tmp_path), "dlcfg-19"), "w") as f:
+        f.write(f"meta_graph={meta}\ncheckpoint={prefix}\nnn_input=feature_input\nnn_outputs={OUTS}\n"
+                f"value_transform=0\nreuse_searchtree={'true' if reuse else 'false'}\n")
+    r = subprocess.run([EXE_QUEUE, str(playouts), str(moves)], cwd=str(tmp_path), capture_output=True, text=True,
+                       timeout=120)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    assert [int(ln.split()[3]) for ln in r.stdout.splitlines() if ln.startswith("move ")] == games[0]

@@ -18,6 +18,8 @@ import subprocess
 
 import pytest
 
+import oracle
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SEARCH = os.path.join(ROOT, "oracle", "_ref", "ref_search")
 
@@ -131,6 +133,44 @@ def test_reference_hand_off_delivers_stale_evaluations_without_sync(tools):
         if stale > 500:
             break
     assert stale > 500
+
+
+# ---- INTEGRATION.md section 2 applied to the reference's own UctSearch.cpp
+
+REF_SEARCH_QUEUE = os.path.join(ROOT, "oracle", "_ref", "ref_search_queue")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SEARCH_QUEUE), reason="oracle/_ref/ref_search_queue not built")
+@pytest.mark.parametrize("playouts,moves,reuse,threads", [(300, 30, True, 1), (40, 700, True, 1), (5000, 3, False, 48)])
+def test_reference_engine_with_the_leaf_queue_patch(tools, playouts, moves, reuse, threads):
+    """oracle/_ref/ref_search_queue = the reference's engine with unrealgo_b200/host/patches/uctsearch_leaf_queue.patch
+    (51 added lines: ug_pack_planes + ug_queue_submit/ug_queue_wait in ExpandAndBackup, queue creation where the
+    evaluation thread was started), here on the stub queue of tests/cpp/stub_queue.h.  A ticket per leaf makes the
+    hand-off leaf-accurate, so with one search thread the engine reproduces the product driver's games with no
+    synchronising shim at all — 30 moves at 300 playouts, and a complete game.  With 48 search threads on one tree
+    (the way the patch is meant to fill batches) it must simply run to the end and keep its books."""
+    cwd = tools[0]
+    stub = os.path.join(cwd, "ugqueue_stub.so")
+    if not os.path.exists(stub):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-o", stub,
+                        os.path.join(ROOT, "tests", "cpp", "ugqueue_stub.cpp")], check=True)
+    _write_cfg(tools, reuse)
+    args = [REF_SEARCH_QUEUE, str(playouts), str(moves)] + ([str(threads)] if threads > 1 else [])
+    r = subprocess.run(args, cwd=cwd, env=dict(os.environ, LD_PRELOAD=stub), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    lines = [ln.split() for ln in r.stdout.splitlines() if ln.startswith("move ")]
+    ref_moves = [int(t[3]) for t in lines]
+    if threads == 1:
+        got_moves, _ = _product(tools, playouts, moves, reuse)
+        if "game over" in r.stdout:
+            got_moves = got_moves[:-1]   # the product records the second pass, the reference stops before it
+        assert ref_moves == got_moves and len(ref_moves) >= min(moves, 300)
+    else:
+        b = oracle.Board()
+        for mv, t in zip(ref_moves, lines):
+            assert b.is_legal(mv) and float(t[5]) >= playouts   # threads finish the playout they are in
+            b.play(mv)
+        assert len(ref_moves) == moves
 
 
 # ---- whole self-play games: the reference's own player (search/UctDeepPlayer.cpp) against the product's driver

@@ -109,6 +109,7 @@ SIGNATURES = {
     "ug_board_to_play": (C.c_int, [C.c_void_p]),
     "ug_board_score": (C.c_float, [C.c_void_p, C.c_float]),
     "ug_board_planes": (None, [C.c_void_p, C.c_void_p]),
+    "ug_pack_planes": (None, [C.c_void_p, C.c_void_p]),
     "ug_queue_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ug_queue_swap_checkpoint": (C.c_int, [C.c_void_p, C.c_char_p]),
     "ug_tfrecord_open": (C.c_void_p, [C.c_char_p]),

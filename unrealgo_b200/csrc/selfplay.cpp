@@ -552,6 +552,21 @@ int ug_board_generate(void* b, uint16_t* moves, uint32_t* legal) {
 }
 int ug_board_to_play(void* b) { return static_cast<ugo::Board*>(b)->to_play; }
 float ug_board_score(void* b, float komi) { return static_cast<ugo::Board*>(b)->tromp_taylor(komi); }
+void ug_pack_planes(const int8_t* planes_chw, ug_packed_pos* out) {
+  memset(out, 0, sizeof(*out));
+  const uint32_t tp = planes_chw[16 * UG_NUM_POINTS] ? 0u : 1u;  // plane 16 = 1 - to_play
+  out->to_play = tp;
+  for (int k = 0; k < UG_HISTORY; ++k) {
+    uint32_t* mine = tp == 0 ? out->black[k] : out->white[k];      // plane 2k: the side to move, k moves ago
+    uint32_t* theirs = tp == 0 ? out->white[k] : out->black[k];    // plane 2k+1: the opponent
+    const int8_t* pm = planes_chw + (2 * k) * UG_NUM_POINTS;
+    const int8_t* pt = planes_chw + (2 * k + 1) * UG_NUM_POINTS;
+    for (int i = 0; i < UG_NUM_POINTS; ++i) {
+      if (pm[i]) mine[i >> 5] |= 1u << (i & 31);
+      if (pt[i]) theirs[i >> 5] |= 1u << (i & 31);
+    }
+  }
+}
 void ug_board_planes(void* b, int8_t* chw_out) {
   ug_packed_pos p;
   static_cast<ugo::Board*>(b)->pack(&p);

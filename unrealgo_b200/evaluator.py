@@ -390,6 +390,16 @@ class ProductBoard:
         return moves[:n].copy(), legal
 
 
+def pack_planes(planes):
+    """ug_pack_planes: CollectFeatures planes int8 [n][17][19][19] (or one [17][19][19]) -> packed uint32 [n][196]"""
+    lib = _lib.load()
+    planes = np.ascontiguousarray(planes, np.int8).reshape(-1, NUM_PLANES * 361)
+    out = np.zeros((planes.shape[0], PACKED_POS_BYTES // 4), np.uint32)
+    for i in range(planes.shape[0]):
+        lib.ug_pack_planes(planes[i].ctypes.data, out[i].ctypes.data)
+    return out
+
+
 def selfplay(evaluator, games, playouts_per_move, threads=4, max_moves=0, max_batch=256, timeout_us=200,
              reuse_tree=True, random_opening_moves=0, puct=0.0, seed=1, record_moves=False, record_dir=None,
              komi=0.0, game_index_base=0, leaves_per_game=1):
