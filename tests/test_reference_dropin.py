@@ -95,3 +95,25 @@ def test_reference_record_writer_header_over_ug_tfrecord(tmp_path):
         assert f[kf].bytes_list.value[0] == feat.tobytes()
         assert np.array_equal(np.array(f[kp].float_list.value, np.float32), pol)
         assert list(f[kr].float_list.value) == [float(i % 3 - 1)]
+
+
+@needs_ref
+def test_leaf_queue_patch_applies_to_the_reference_tree(tmp_path):
+    """unrealgo_b200/host/patches/uctsearch_leaf_queue.patch, `patch -p1` from the reference root:
+    applies without fuzz or rejects, everything it adds sits behind UGEVAL_LEAF_QUEUE, and what it adds calls only
+    declared C-ABI entry points"""
+    import shutil
+    os.makedirs(tmp_path / "search")
+    shutil.copy(os.path.join(REF, "search", "UctSearch.cpp"), tmp_path / "search" / "UctSearch.cpp")
+    patch = os.path.join(ROOT, "unrealgo_b200", "host", "patches", "uctsearch_leaf_queue.patch")
+    r = subprocess.run(["patch", "-p1", "-i", patch], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0 and "fuzz" not in r.stdout and "rej" not in r.stdout, r.stdout + r.stderr
+    patched = open(tmp_path / "search" / "UctSearch.cpp").read()
+    original = open(os.path.join(REF, "search", "UctSearch.cpp")).read()
+    assert patched.count("UGEVAL_LEAF_QUEUE") >= 5 and "UGEVAL_LEAF_QUEUE" not in original
+    header = open(os.path.join(ROOT, "include", "ugeval.h")).read()
+    added = [ln[1:] for ln in open(patch).read().splitlines() if ln.startswith("+") and not ln.startswith("+++")]
+    used = set(re.findall(r"\b(ug_[a-z_]+)\s*\(", "\n".join(added)))
+    assert used == {"ug_pack_planes", "ug_queue_submit", "ug_queue_wait", "ug_queue_create", "ug_queue_swap_checkpoint"}
+    for s in used:
+        assert re.search(r"\b%s\s*\(" % s, header), s
