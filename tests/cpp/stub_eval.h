@@ -5,6 +5,7 @@
 #ifndef UG_TEST_STUB_EVAL_H
 #define UG_TEST_STUB_EVAL_H
 #include <stdint.h>
+#include <stdlib.h>
 
 static inline void stub_eval(const int8_t* planes /* [17][361] */, float* policy /* [362] */, float* value) {
   uint64_t h = 1469598103934665603ull;
@@ -19,4 +20,13 @@ static inline void stub_eval(const int8_t* planes /* [17][361] */, float* policy
   for (int i = 0; i < 362; ++i) policy[i] /= sum;
   *value = 0.05f * (float)((int)(h % 21) - 10);
 }
+
+/* value_transform (funcapproximator/DlTFNetworkEvaluator.cc:300-310): set through ug_eval_set_value_transform like on
+ * the product; a driver that has no evaluator object (selfplay_stub.cpp) passes it in UGSTUB_VT. */
+static int g_stub_vt = -1;
+static inline int stub_vt(void) {
+  if (g_stub_vt < 0) { const char* e = getenv("UGSTUB_VT"); g_stub_vt = e ? atoi(e) : 0; }
+  return g_stub_vt;
+}
+static inline float stub_transform(float v) { return stub_vt() == 1 ? -v : (stub_vt() == 2 ? 1.f - v : v); }
 #endif

@@ -48,6 +48,7 @@ int ug_queue_poll(ug_queue* q, int64_t ticket, float* policy, float* value) {
     }
   memset(planes + 16 * 361, 1 - (int)tp, 361);
   stub_eval(planes, policy, value);
+  *value = stub_transform(*value);  // the head kernel applies value_transform on the packed path
   float sum = 0.f;
   for (int i = 0; i < UG_NUM_MOVES; ++i) {
     if (!((s.legal[i >> 5] >> (i & 31)) & 1u)) policy[i] = 0.f;

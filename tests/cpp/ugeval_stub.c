@@ -17,7 +17,8 @@ int ug_eval_load_graph(ug_eval* e, const char* path) { return 0; }
 int ug_eval_load_checkpoint(ug_eval* e, const char* prefix) { return 0; }
 int ug_eval_ready(const ug_eval* e) { return 1; }
 int ug_eval_set_io(ug_eval* e, const char* in, const char* const* outs, int n) { return 0; }
-int ug_eval_set_value_transform(ug_eval* e, int vt) { return 0; }
+/* value_transform: state and helpers in stub_eval.h (shared with the stub leaf queue) */
+int ug_eval_set_value_transform(ug_eval* e, int vt) { g_stub_vt = (vt == 1 || vt == 2) ? vt : 0; return 0; }
 const char* ug_last_error(const ug_eval* e) { return "stub evaluator"; }
 static uint64_t hash_planes(const volatile int8_t* p, size_t n) {
   uint64_t h = 1469598103934665603ull;
@@ -54,7 +55,7 @@ int ug_eval_run_planes(ug_eval* e, const int8_t* planes, int n, double* policy, 
     float p[362], v;
     stub_eval(snap + (size_t)b * 17 * 361, p, &v);
     for (int i = 0; i < 362; ++i) policy[(size_t)b * 362 + i] = (double)p[i];  /* float -> double, as ug_eval_run_planes */
-    value[b] = (double)v;
+    value[b] = stub_vt() == 1 ? -(double)v : (stub_vt() == 2 ? 1 - (double)v : (double)v);  /* in double, as .cc:300-310 */
   }
   if (getenv("UGSTUB_STATS")) {  /* how often the answer was computed from something other than what the buffer holds now */
     static uint64_t calls = 0, stale = 0;

@@ -144,7 +144,7 @@ REF_SEARCH_QUEUE = os.path.join(ROOT, "oracle", "_ref", "ref_search_queue")
 @pytest.mark.parametrize("playouts,moves,reuse,threads", [(300, 30, True, 1), (40, 700, True, 1), (5000, 3, False, 48)])
 def test_reference_engine_with_the_leaf_queue_patch(tools, playouts, moves, reuse, threads):
     """oracle/_ref/ref_search_queue = the reference's engine with unrealgo_b200/host/patches/uctsearch_leaf_queue.patch
-    (51 added lines: ug_pack_planes + ug_queue_submit/ug_queue_wait in ExpandAndBackup, queue creation where the
+    (53 added lines: ug_pack_planes + ug_queue_submit/ug_queue_wait in ExpandAndBackup, queue creation where the
     evaluation thread was started), here on the stub queue of tests/cpp/stub_queue.h.  A ticket per leaf makes the
     hand-off leaf-accurate, so with one search thread the engine reproduces the product driver's games with no
     synchronising shim at all — 30 moves at 300 playouts, and a complete game.  With 48 search threads on one tree
@@ -166,9 +166,15 @@ def test_reference_engine_with_the_leaf_queue_patch(tools, playouts, moves, reus
             got_moves = got_moves[:-1]   # the product records the second pass, the reference stops before it
         assert ref_moves == got_moves and len(ref_moves) >= min(moves, 300)
     else:
+        # What the reference guarantees under racing threads: it runs to the end and every chosen move is legal.  The
+        # root's count is NOT exact: UctNode::AddValue does `visit_count += 1` on a plain volatile int
+        # (search/UctSearchTree.h:127,360-365) and GamesPlayed() reads that counter (search/UctSearch.cpp:398-400), so
+        # concurrent backups can lose increments (seen: 4973 of 5000 with 48 threads on 8 cores) while the search
+        # stops on the same racy counter.  Allow a small lost-update margin instead of an exact count.
         b = oracle.Board()
         for mv, t in zip(ref_moves, lines):
-            assert b.is_legal(mv) and float(t[5]) >= playouts   # threads finish the playout they are in
+            assert b.is_legal(mv)
+            assert float(t[5]) >= 0.97 * playouts, t
             b.play(mv)
         assert len(ref_moves) == moves
 
@@ -223,3 +229,35 @@ def test_live_reference_player_writes_the_same_records(tools, recorder):
         if open(out, "rb").read() == got:
             break
     assert open(out, "rb").read() == got
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SEARCH_QUEUE), reason="oracle/_ref/ref_search_queue not built")
+@pytest.mark.parametrize("vt", [1, 2])
+def test_leaf_queue_patch_applies_value_transform(tools, vt):
+    """dlcfg value_transform != 0: Evaluate() reads it from DlConfig on every call (DlTFNetworkEvaluator.cc:300-310); the
+    patched ExpandAndBackup never calls Evaluate(), so the patch hands it to the evaluator itself
+    (ug_eval_set_value_transform where the queue is created).  The patched engine must play the product driver's game
+    for the same transform, and that game must differ from the untransformed one (so a dropped transform is seen)."""
+    cwd = tools[0]
+    stub = os.path.join(cwd, "ugqueue_stub.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-o", stub,
+                    os.path.join(ROOT, "tests", "cpp", "ugqueue_stub.cpp")], check=True)
+    exe = tools[2]
+
+    def product(v):
+        r = subprocess.run([exe, "1", "1", "300", "12", "0", "1", "0"], cwd=cwd, env=dict(os.environ, UGSTUB_VT=str(v)),
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-500:]
+        return [int(x) for x in [ln for ln in r.stdout.splitlines() if ln.startswith("game 0:")][0].split()[2:]]
+
+    with open(os.path.join(cwd, "dlcfg-19"), "w") as f:
+        f.write(f"meta_graph=stub.meta\ncheckpoint=stub\nvalue_transform={vt}\nreuse_searchtree=false\n")
+    try:
+        r = subprocess.run([REF_SEARCH_QUEUE, "300", "12"], cwd=cwd, env=dict(os.environ, LD_PRELOAD=stub),
+                           capture_output=True, text=True, timeout=300)
+    finally:
+        _write_cfg(tools, False)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    ref_moves = [int(ln.split()[3]) for ln in r.stdout.splitlines() if ln.startswith("move ")]
+    assert ref_moves == product(vt)
+    assert ref_moves != product(0)
