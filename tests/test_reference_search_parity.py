@@ -144,7 +144,7 @@ REF_SEARCH_QUEUE = os.path.join(ROOT, "oracle", "_ref", "ref_search_queue")
 @pytest.mark.parametrize("playouts,moves,reuse,threads", [(300, 30, True, 1), (40, 700, True, 1), (5000, 3, False, 48)])
 def test_reference_engine_with_the_leaf_queue_patch(tools, playouts, moves, reuse, threads):
     """oracle/_ref/ref_search_queue = the reference's engine with unrealgo_b200/host/patches/uctsearch_leaf_queue.patch
-    (53 added lines: ug_pack_planes + ug_queue_submit/ug_queue_wait in ExpandAndBackup, queue creation where the
+    (52 added lines: ug_pack_planes + ug_queue_submit/ug_queue_wait in ExpandAndBackup, queue creation where the
     evaluation thread was started), here on the stub queue of tests/cpp/stub_queue.h.  A ticket per leaf makes the
     hand-off leaf-accurate, so with one search thread the engine reproduces the product driver's games with no
     synchronising shim at all — 30 moves at 300 playouts, and a complete game.  With 48 search threads on one tree
