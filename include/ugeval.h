@@ -65,6 +65,7 @@ typedef struct ug_net_info {
   int conv_ctas;        /* 1 or 2: cta_group of the tower kernel in use */
   int sm_count;
   int conv_impl;        /* 1 = TMA-im2col tower kernel, 2 = resident-tile kernel (see ug_eval_set_conv_impl) */
+  int small_batch_max;  /* batches up to this size run the small-batch tower kernel (see ug_eval_set_small_batch) */
 } ug_net_info;
 
 typedef struct ug_eval ug_eval;
@@ -108,6 +109,11 @@ int ug_efficient_batch_for_sms(int sm_count, int n);
 /* tower kernel generation: 1 = TMA-im2col operand staging (conv3x3_tc.cu), 2 = shared-memory-resident input tile
  * with shifted-descriptor taps and TMA-staged epilogue (conv3x3_v2.cu, default); testing/benchmark knob */
 int ug_eval_set_conv_impl(ug_eval* h, int impl);
+/* Batches of at most max_batch positions run the tower on the small-batch kernel (conv3x3_sb.cu: 128-row x nt-column
+ * tiles on many SMs) — the batch sizes the reference's engine issues (1 .. MAX_BATCHES = 16,
+ * funcapproximator/DlTFNetworkEvaluator.h:15; search/UctSearch.cpp:183-186).  max_batch 0 disables; nt = output
+ * channels per CTA (16/32/64/128, 0 = chosen from the grid size).  Default 24 / 0 (UGEVAL_SB_MAX, UGEVAL_SB_NT). */
+int ug_eval_set_small_batch(ug_eval* h, int max_batch, int nt);
 /* carry the residual stream as a hi+lo pair of 16-bit tensors (1) or as one 16-bit tensor (0); numerics knob */
 int ug_eval_set_residual_split(ug_eval* h, int on);
 
@@ -174,6 +180,11 @@ int ug_k_conv3x3_bf16(int device, const void* d_in, const void* d_w, const float
 int ug_k_conv3x3_v2(int device, const void* d_in, const void* d_w, const float* d_bias, const void* d_res_hi,
                     const void* d_res_lo, void* d_out_hi, void* d_out_lo, int n, int n_alloc, int cin, int cout,
                     int relu, int f16, int desc_mode, int iters, float* ms_out, long long* d_prof);
+
+/* Raw entry of the small-batch conv kernel (same buffers as ug_k_conv3x3_v2; nt as ug_eval_set_small_batch). */
+int ug_k_conv3x3_sb(int device, const void* d_in, const void* d_w, const float* d_bias, const void* d_res_hi,
+                    const void* d_res_lo, void* d_out_hi, void* d_out_lo, int n, int n_alloc, int cin, int cout,
+                    int relu, int f16, int nt, int pdl, int iters, float* ms_out);
 
 /* planning probe: clusters of `cluster_size` CTAs of the tower kernel that fit on the device at once (a part that
  * strands SM pairs for clusters of 4 returns fewer than SMs/4) */

@@ -14,7 +14,9 @@ from unrealgo_b200 import _lib  # noqa: E402
 lib = None
 
 
-def run(n, cin, cout, taps, desc_mode, residual, out_lo, f16=True, relu=True, seed=1, iters=0, n_alloc=None, prof=False, split_res=True):
+def run(n, cin, cout, taps, desc_mode, residual, out_lo, f16=True, relu=True, seed=1, iters=0, n_alloc=None, prof=False, split_res=True,
+        impl="v2", nt=0, pdl=0):
+    """impl "v2": conv3x3_v2 (ug_k_conv3x3_v2); "sb": the small-batch kernel (ug_k_conv3x3_sb, nt = tile width, 0 = auto)"""
     global lib
     if lib is None:
         lib = _lib.load()
@@ -40,10 +42,16 @@ def run(n, cin, cout, taps, desc_mode, residual, out_lo, f16=True, relu=True, se
     dol = torch.full((n_alloc, 19, 19, cout), float("nan"), dtype=dt, device="cuda") if out_lo else None
     ms = C.c_float(0)
     dprof = torch.zeros(74, 64, dtype=torch.int64, device="cuda") if prof else None
-    rc = lib.ug_k_conv3x3_v2(0, dx.data_ptr(), dw.data_ptr(), db.data_ptr(), drh.data_ptr() if residual else None,
-                             drl.data_ptr() if drl is not None else None, doh.data_ptr(), dol.data_ptr() if out_lo else None,
-                             n, n_alloc, cin, cout, 1 if relu else 0, 1 if f16 else 0, desc_mode, iters, C.byref(ms),
-                             dprof.data_ptr() if prof else None)
+    if impl == "sb":
+        rc = lib.ug_k_conv3x3_sb(0, dx.data_ptr(), dw.data_ptr(), db.data_ptr(), drh.data_ptr() if residual else None,
+                                 drl.data_ptr() if drl is not None else None, doh.data_ptr(),
+                                 dol.data_ptr() if out_lo else None, n, n_alloc, cin, cout, 1 if relu else 0,
+                                 1 if f16 else 0, nt, pdl, iters, C.byref(ms))
+    else:
+        rc = lib.ug_k_conv3x3_v2(0, dx.data_ptr(), dw.data_ptr(), db.data_ptr(), drh.data_ptr() if residual else None,
+                                 drl.data_ptr() if drl is not None else None, doh.data_ptr(), dol.data_ptr() if out_lo else None,
+                                 n, n_alloc, cin, cout, 1 if relu else 0, 1 if f16 else 0, desc_mode, iters, C.byref(ms),
+                                 dprof.data_ptr() if prof else None)
     if rc != 0:
         return f"rc={rc} {lib.ug_last_error(None)}"
     torch.cuda.synchronize()
@@ -113,6 +121,17 @@ if __name__ == "__main__":
     if which == "probe":
         for dm in (0, 2, 4, 6):
             print(f"probe desc_mode={dm} conv1:", run(256, 256, 256, ALL, dm, False, False, iters=20, prof=True), flush=True)
+    if which == "sb":
+        print("sb centre  n=3 64->64 nt32 :", run(3, 64, 64, [(1, 1)], 0, False, False, impl="sb", nt=32), flush=True)
+        for tap in [(1, 0), (0, 1), (2, 2)]:
+            print(f"sb tap {tap} n=3 64->64 nt16:", run(3, 64, 64, [tap], 0, False, False, impl="sb", nt=16), flush=True)
+        for nt in (16, 32, 64, 128):
+            print(f"sb all taps n=5 256->256 res+lo nt={nt}:", run(5, 256, 256, ALL, 0, True, True, impl="sb", nt=nt), flush=True)
+        print("sb stem n=7 32->256 lo auto:", run(7, 32, 256, ALL, 0, False, True, impl="sb"), flush=True)
+        for n in (1, 2, 4, 8, 16, 32):
+            for nt in (16, 32, 64, 128):
+                print(f"sb time conv2 n={n} nt={nt} pdl:", run(n, 256, 256, ALL, 0, True, True, impl="sb", nt=nt, pdl=1, iters=200).split("|")[-1], flush=True)
+            print(f"v2 time conv2 n={n} pdl      :", run(n, 256, 256, ALL, 8, True, True, iters=200).split("|")[-1], flush=True)
     if which in ("all", "time"):
         dm = int(sys.argv[2]) if len(sys.argv) > 2 else 0
         print("time conv1 n=256 256->256         :", run(256, 256, 256, ALL, dm, False, False, iters=20, prof=True), flush=True)

@@ -67,6 +67,27 @@ def test_flagship_batch256_parity_and_properties(flagship):
     evb.close()
 
 
+def test_flagship_small_batches(flagship):
+    """The batch sizes the reference's own engine can issue (1 .. MAX_BATCHES = 16): the small-batch tower kernel on
+    the 20x256 net, against the oracle and bit-identical to the same positions inside a batch of 256."""
+    import oracle
+    from oracle.net_oracle import GraphOracle
+    from unrealgo_b200 import DlTFNetworkEvaluator
+    packed, planes = oracle.synthetic_positions(256, seed=20260119)
+    ev = DlTFNetworkEvaluator(flagship[0], max_batch=256)
+    assert ev.UpdateCheckPoint(flagship[1])
+    assert ev.info()["small_batch_max"] >= 16
+    p256, v256 = ev.evaluate_packed(packed)
+    want_p, want_v = GraphOracle(*flagship).evaluate_reference(planes[:16])
+    for n in (1, 7, 16):
+        p, v = ev.evaluate_packed(packed[:n])
+        dp, dv = np.abs(p - want_p[:n]).max(), np.abs(v - want_v[:n]).max()
+        print(f"flagship n={n} (small-batch kernel): max|dpolicy|={dp:.3e} max|dvalue|={dv:.3e}")
+        assert dp <= 1e-3 and dv <= 5e-3
+        assert np.array_equal(p, p256[:n]) and np.array_equal(v, v256[:n])
+    ev.close()
+
+
 @pytest.fixture(scope="module")
 def agz40(tmp_path_factory):
     """BASELINE.json configs[4]: 40 blocks x 256 filters, random-init weights"""

@@ -33,7 +33,7 @@ class NetInfo(C.Structure):
     _fields_ = [
         ("blocks", C.c_int), ("filters", C.c_int), ("policy_channels", C.c_int), ("value_channels", C.c_int),
         ("value_hidden", C.c_int), ("input_planes", C.c_int), ("flops_per_position", C.c_double),
-        ("conv_ctas", C.c_int), ("sm_count", C.c_int), ("conv_impl", C.c_int),
+        ("conv_ctas", C.c_int), ("sm_count", C.c_int), ("conv_impl", C.c_int), ("small_batch_max", C.c_int),
     ]
 
 
@@ -93,6 +93,10 @@ SIGNATURES = {
     "ug_k_conv3x3_v2": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_float), C.c_void_p]),
+    "ug_k_conv3x3_sb": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.POINTER(C.c_float)]),
+    "ug_eval_set_small_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "ug_debug_max_active_clusters": (C.c_int, [C.c_int, C.c_int]),
     "ug_queue_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "ug_queue_destroy": (None, [C.c_void_p]),

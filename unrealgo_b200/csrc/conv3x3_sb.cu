@@ -1,0 +1,375 @@
+// K3/K4 (small batches) — the 3x3 SAME tower convolution for 1 .. a few dozen positions.
+//
+// Same contract as conv3x3_v2.cu (Conv2D + FusedBatchNorm + Relu (+ Add) of the graph the reference runs inside
+// tensorflow::Session::Run, funcapproximator/DlTFNetworkEvaluator.cc:295).  The reference's own engine never
+// evaluates more than MAX_BATCHES = 16 positions per call (funcapproximator/DlTFNetworkEvaluator.h:15) and exactly
+// one in the shipped FORCE_SINGLE_THREAD build (CMakeLists.txt:15; search/UctSearch.cpp:183-186): 361 .. 5776 GEMM
+// rows.  conv3x3_v2's persistent 256-row x 256-column CTA-pair tiles put such a layer on 2 .. 23 of the 74 SM pairs and
+// a layer then costs one full tile time (~30 us) whatever the batch.  Here the layer is cut the other way:
+//
+//   grid   (ceil(M / 128), cout / NT): one 128-row x NT-column tile per CTA, cta_group::1, NT in {16, 32, 64, 128}
+//          chosen so that the grid is as large as one wave of the SMs allows (n = 1 -> 3 x 8 CTAs at NT = 32,
+//          n = 16 -> 46 x 2 at NT = 128), so the 1.2 MB of a layer's weights are pulled through many SMs at once;
+//   A      the whole K extent of the tile resident: cin/64 TMA loads of 168 consecutive pixel rows (tile + 20-row halo
+//          either side), taps = the same slot read through a descriptor shifted by (20 + 19 dy + dx) rows, off-board
+//          rows switched off per tap with tcgen05.mma's disable-output-lane mask (exactly conv3x3_v2's scheme);
+//   B      [NT x 64] weight tile per (chunk, tap) through a ring of up to 36 stages (96 KB), 16 rows per TMA box;
+//   D      NT TMEM columns; one tile per CTA, so no double buffering;
+//   epilogue  all 8 warps (two per TMEM lane quarter, alternating 16-column steps): residual rows prefetched from
+//          global memory before the accumulator is ready, tcgen05.ld -> +bias (+residual hi/lo) -> ReLU -> 16-bit hi
+//          (+lo) -> 32-byte global stores per thread.  Small tensors: the uncoalesced per-row accesses that bounded
+//          the first-generation kernel at batch 256 cost a few hundred nanoseconds here.
+//
+// Warp roles (256 threads): 0 = A producer (waits for the previous layer: griddepcontrol.wait), 1 = MMA issuer,
+// 2 = TMEM allocator, 3 = weight producer (starts before the previous layer has finished); then every warp joins the
+// epilogue.
+#include <cuda_bf16.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "conv3x3_sb.h"
+#include "numfmt.cuh"
+#include "ptx.cuh"
+
+namespace ug {
+
+namespace {
+
+constexpr int kBoard = 19;
+constexpr int kPix = 361;
+constexpr int kTileM = 128;
+constexpr int kHalo = kBoard + 1;           // 20
+constexpr int kARows = kTileM + 2 * kHalo;  // 168
+constexpr int kThreads = 256;
+constexpr int kMaxStages = 36;              // one per (chunk, tap) of a 256-channel layer
+constexpr int kBRing = 96 * 1024;
+constexpr int kMaxEpiSteps = 4;             // 16-column steps per warp: NT = 128 -> 8 steps over two warp groups
+
+template <int CK>
+struct SbCfg {
+  static constexpr int kRowBytes = CK * 2;
+  static constexpr int kMaxChunks = CK == 64 ? 4 : 1;   // cin <= 256 (CK = 64) / the 32-channel stem (CK = 32)
+  static constexpr int kASlot = kARows * kRowBytes;     // 21504 / 10752
+  static constexpr int kOffB = (kMaxChunks * kASlot + 1023) & ~1023;
+  static constexpr int kOffBars = kOffB + kBRing;
+  static constexpr int kNumBars = kMaxChunks + 2 * kMaxStages + 1;
+  static constexpr int kBytes = kOffBars + kNumBars * 8 + 16;
+  static constexpr int kSmem = kBytes + 1024;  // alignment slack
+  static_assert(kSmem <= 232448, "exceeds the 227 KB of shared memory a CTA can opt in to");
+};
+
+// same table as conv3x3_v2.cu (a __constant__ symbol is private to its translation unit): c_edge_mask_sb[tap][q] bit i
+// is set when pixel (q + i) mod 361 of an image has no in-board source for filter tap `tap`
+__constant__ uint32_t c_edge_mask_sb[9][kPix];
+
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2_sat(float lo, float hi) {
+  uint32_t r;
+  if constexpr (F16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack2_t(uint32_t w) {
+  if constexpr (F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  else return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+
+template <int CK, bool F16>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const ConvSbArgs args) {
+  using C = SbCfg<CK>;
+  constexpr int kRowBytes = C::kRowBytes;
+  constexpr int kMmaPerStep = CK / 16;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + C::kOffB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
+  uint64_t* a_full = bars;
+  uint64_t* b_full = a_full + C::kMaxChunks;
+  uint64_t* b_empty = b_full + kMaxStages;
+  uint64_t* acc_full = b_empty + kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler too
+  const int lane = threadIdx.x & 31;
+  const int nt = args.nt;
+  const int stages = args.stages;
+  const int chunks = args.cin / CK;
+  const int m0 = (int)blockIdx.x * kTileM;
+  const int n0 = (int)blockIdx.y * nt;
+  const uint32_t stage_bytes = (uint32_t)nt * kRowBytes;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int j = 0; j < C::kMaxChunks; ++j) mbar_init(&a_full[j], 1);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<1>(tmem_slot, nt < 32 ? 32u : (uint32_t)nt);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: the next layer's CTAs may be scheduled from here on (their prologue and weight
+  // loads do not depend on this layer); they read this layer's output only behind their own griddepcontrol.wait.
+  pdl_launch_dependents();
+
+  // Producer and MMA warps run their loops on all 32 lanes with warp-uniform values and predicate only the TMA / MMA
+  // instruction on one elected lane (see conv3x3_v2.cu: issuing from inside `if (lane == 0)` costs an
+  // ELECT + R2UR.BROADCAST loop per instruction).
+  const uint32_t elected = elect_one();
+  if (warp == 0) {
+    // ===================== A producer: the previous layer's output =====================
+    pdl_wait();
+    for (int j = 0; j < chunks; ++j) {
+      if (elected) {
+        mbar_expect_tx(&a_full[j], C::kASlot);
+        tma_load_2d(smA + j * C::kASlot, &tmA, &a_full[j], j * CK, m0 - kHalo);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 3) {
+    // ===================== weight producer =====================
+    int sb = 0;
+    uint32_t phb = 0;
+    for (int j = 0; j < chunks; ++j) {
+#pragma unroll 1
+      for (int t = 0; t < 9; ++t) {
+        const int tap = (t == 0) ? 4 : (t <= 4 ? t - 1 : t);  // centre first, then 0,1,2,3,5,6,7,8
+        mbar_wait(&b_empty[sb], phb ^ 1);
+        if (elected) {
+          mbar_expect_tx(&b_full[sb], stage_bytes);
+          uint8_t* dst = smB + (size_t)sb * stage_bytes;
+          for (int i = 0; i < nt; i += 16)
+            tma_load_2d(dst + i * kRowBytes, &tmW, &b_full[sb], tap * args.cin + j * CK, n0 + i);
+        }
+        __syncwarp();
+        if (++sb == stages) { sb = 0; phb ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_16(kTileM, nt, F16 ? 1 : 0);
+    // pixel-in-image index of the tile's first row; the lane mask of 32 consecutive rows depends only on
+    // (tap, that index mod 361)
+    const int q0 = m0 % kPix;
+    int sb = 0;
+    uint32_t phb = 0;
+    for (int j = 0; j < chunks; ++j) {
+      mbar_wait(&a_full[j], 0);
+      const uint32_t a_slot = smem_u32(smA + j * C::kASlot);
+#pragma unroll 1
+      for (int t = 0; t < 9; ++t) {
+        const int tap = (t == 0) ? 4 : (t <= 4 ? t - 1 : t);
+        const int r = tap / 3, s = tap - 3 * r;
+        const int shift = kHalo + (r - 1) * kBoard + (s - 1);
+        uint32_t m[8];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          int q = q0 + 32 * w;
+          if (q >= kPix) q -= kPix;  // q0 < 361 and 32*w <= 96
+          m[w] = c_edge_mask_sb[tap][q];
+        }
+        m[4] = m[5] = m[6] = m[7] = 0u;
+        mbar_wait(&b_full[sb], phb);
+        tc_fence_after();
+        const uint64_t adesc = make_kmajor_desc<kRowBytes>(a_slot + (uint32_t)shift * kRowBytes);
+        const uint64_t bdesc = make_kmajor_desc<kRowBytes>(smem_u32(smB + (size_t)sb * stage_bytes));
+        if (elected) {
+#pragma unroll
+          for (int k = 0; k < kMmaPerStep; ++k) {
+            if (tap == 4)  // the centre tap never needs a mask; it goes first and initialises the accumulator
+              umma_f16<1>(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (j | t | k) != 0);
+            else
+              umma_f16_1sm_masked(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u, m);
+          }
+          umma_commit(&b_empty[sb]);
+        }
+        __syncwarp();
+        if (++sb == stages) { sb = 0; phb ^= 1; }
+      }
+    }
+    if (elected) umma_commit(acc_full);
+    __syncwarp();
+  }
+
+  // ===================== epilogue: every warp =====================
+  {
+    const int quarter = warp & 3;            // TMEM lanes [32*quarter, +32)
+    const int grp = warp < 4 ? 1 : 0;        // the role-free warps 4-7 take the even 16-column steps
+    const int total_steps = nt >> 4;
+    const long row = (long)m0 + quarter * 32 + lane;
+    const bool row_ok = row < args.M;
+    const float act_floor = args.relu ? 0.f : -3.0e38f;
+    const bool has_res = args.res_hi != nullptr, has_res_lo = args.res_lo != nullptr, has_out_lo = args.out_lo != nullptr;
+    const size_t row_off = (size_t)(row_ok ? row : 0) * args.cout + n0;
+    pdl_wait();  // the residual was written two layers back; every warp must be ordered behind it
+    uint4 rh[kMaxEpiSteps][2], rl[kMaxEpiSteps][2];
+    if (has_res) {
+#pragma unroll
+      for (int s = 0; s < kMaxEpiSteps; ++s) {
+        const int step = 2 * s + grp;
+        if (step < total_steps && row_ok) {
+          const uint4* p = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(args.res_hi) + row_off + step * 16);
+          rh[s][0] = __ldg(p);
+          rh[s][1] = __ldg(p + 1);
+          if (has_res_lo) {
+            const uint4* q = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(args.res_lo) + row_off + step * 16);
+            rl[s][0] = __ldg(q);
+            rl[s][1] = __ldg(q + 1);
+          }
+        }
+      }
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+    for (int s = 0; s < kMaxEpiSteps; ++s) {
+      const int step = 2 * s + grp;
+      if (step < total_steps) {   // warp-uniform
+        const int c0 = step * 16;
+        uint32_t v[16];
+        tmem_ld_32x16(t_row + c0, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          uint32_t ph[8], pl[8];
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rh[s][0]);
+          const uint32_t* lw = reinterpret_cast<const uint32_t*>(&rl[s][0]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float2 b2 = __ldg(reinterpret_cast<const float2*>(args.bias + n0 + c0) + e);
+            float f0 = __uint_as_float(v[2 * e]) + b2.x;
+            float f1 = __uint_as_float(v[2 * e + 1]) + b2.y;
+            if (has_res) {
+              const float2 r2 = unpack2_t<F16>(rw[e]);
+              f0 += r2.x;
+              f1 += r2.y;
+              if (has_res_lo) {
+                const float2 l2 = unpack2_t<F16>(lw[e]);
+                f0 += l2.x;
+                f1 += l2.y;
+              }
+            }
+            f0 = fmaxf(f0, act_floor);
+            f1 = fmaxf(f1, act_floor);
+            ph[e] = pack2_sat<F16>(f0, f1);
+            if (has_out_lo) {
+              const float2 hi = unpack2_t<F16>(ph[e]);
+              pl[e] = pack2_sat<F16>(f0 - hi.x, f1 - hi.y);
+            }
+          }
+          uint4* o = reinterpret_cast<uint4*>(static_cast<uint16_t*>(args.out_hi) + row_off + c0);
+          o[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          o[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+          if (has_out_lo) {
+            uint4* ol = reinterpret_cast<uint4*>(static_cast<uint16_t*>(args.out_lo) + row_off + c0);
+            ol[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            ol[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, nt < 32 ? 32u : (uint32_t)nt);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+std::mutex g_mask_mu;
+bool g_mask_done[64] = {};  // per device
+
+bool upload_masks(int device) {
+  std::lock_guard<std::mutex> lk(g_mask_mu);
+  if (device < 0 || device >= 64) return false;
+  if (g_mask_done[device]) return true;
+  std::vector<uint32_t> h((size_t)9 * kPix, 0u);
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    for (int q = 0; q < kPix; ++q)
+      for (int i = 0; i < 32; ++i) {
+        const int p = (q + i) % kPix;
+        const int y = p / kBoard + dy, x = p % kBoard + dx;
+        if (y < 0 || y >= kBoard || x < 0 || x >= kBoard) h[(size_t)tap * kPix + q] |= 1u << i;
+      }
+  }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  cudaSetDevice(device);
+  const cudaError_t e = cudaMemcpyToSymbol(c_edge_mask_sb, h.data(), h.size() * 4);
+  cudaSetDevice(cur);
+  if (e != cudaSuccess) return false;
+  g_mask_done[device] = true;
+  return true;
+}
+
+template <int CK, bool F16>
+cudaError_t launch_sb(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvSbArgs& a, cudaStream_t stream) {
+  auto kfn = conv3x3_sb_kernel<CK, F16>;
+  constexpr int smem = SbCfg<CK>::kSmem;
+  static std::atomic<uint64_t> attr_done{0};  // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr_done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((a.M + kTileM - 1) / kTileM), (unsigned)(a.cout / a.nt));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = a.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kfn, tmA, tmW, a);
+}
+
+}  // namespace
+
+bool conv3x3_sb_prepare(int device) { return upload_masks(device); }
+
+int conv3x3_sb_pick_nt(int M, int cout, int sms) {
+  const int m_tiles = (M + kTileM - 1) / kTileM;
+  // the smallest tile width (largest grid) that still fits one wave; 16-column tiles only pay their 144 tiny MMAs
+  // back when nothing else fills the machine, so 32 is the floor unless asked for explicitly
+  for (int nt = 32; nt <= 128; nt <<= 1)
+    if (cout % nt == 0 && m_tiles * (cout / nt) <= sms) return nt;
+  for (int nt = 128; nt >= 16; nt >>= 1)
+    if (cout % nt == 0) return nt;
+  return 0;
+}
+
+cudaError_t conv3x3_sb_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, ConvSbArgs a, int ck, int device, int sms,
+                              cudaStream_t stream) {
+  if (ck != 64 && ck != 32) return cudaErrorInvalidValue;
+  if (a.cin % ck != 0 || a.cin / ck > (ck == 64 ? 4 : 1)) return cudaErrorInvalidValue;
+  if (a.nt == 0) a.nt = conv3x3_sb_pick_nt(a.M, a.cout, sms);
+  if (a.nt != 16 && a.nt != 32 && a.nt != 64 && a.nt != 128) return cudaErrorInvalidValue;
+  if (a.cout % a.nt != 0 || a.M <= 0 || !a.out_hi || !a.bias) return cudaErrorInvalidValue;
+  if (a.res_lo && !a.res_hi) return cudaErrorInvalidValue;
+  if (!upload_masks(device)) return cudaErrorUnknown;  // no-op after conv3x3_sb_prepare()
+  const int ksteps = 9 * (a.cin / ck);
+  const int fit = kBRing / (a.nt * ck * 2);
+  a.stages = fit < ksteps ? fit : ksteps;
+  if (a.stages > kMaxStages) a.stages = kMaxStages;
+  if (ck == 64) return a.f16 ? launch_sb<64, true>(tmA, tmW, a, stream) : launch_sb<64, false>(tmA, tmW, a, stream);
+  return a.f16 ? launch_sb<32, true>(tmA, tmW, a, stream) : launch_sb<32, false>(tmA, tmW, a, stream);
+}
+
+}  // namespace ug

@@ -12,6 +12,7 @@
 #include <cuda_fp16.h>
 
 #include "conv3x3_tc.h"
+#include "conv3x3_sb.h"
 #include "conv3x3_v2.h"
 #include "tmap.h"
 
@@ -137,6 +138,7 @@ bool make_conv_layer(const HostConv& hc, int cin_pad, bool f16, ConvLayer* L, st
   const int ck = (cin_pad % 64 == 0) ? 64 : 32;
   for (int ctas = 1; ctas <= 2; ++ctas)
     if (!make_tmap_weights(&L->tm_w[ctas - 1], L->w_bf16.p, hc.cout, ktot, ck, hc.cout / ctas, err)) return false;
+  if (!make_tmap_weights(&L->tm_w_sb, L->w_bf16.p, hc.cout, ktot, ck, 16, err)) return false;
   return true;
 }
 
@@ -281,7 +283,10 @@ bool ug_eval::ensure_workspace(int C) {
             make_tmap_rows(&v2_out_hi[i], d_s_hi[i].p, rows, C, 32, 32, &err) &&
             make_tmap_rows(&v2_out_lo[i], d_s_lo[i].p, rows, C, 32, 32, &err);
     if (!ok2) { last_error = err; return false; }
-    if (!conv3x3_v2_prepare(device)) { last_error = "cannot upload the conv lane-mask table"; return false; }
+    if (!conv3x3_v2_prepare(device) || !conv3x3_sb_prepare(device)) {
+      last_error = "cannot upload the conv lane-mask table";
+      return false;
+    }
   }
   if (!h_pinned) {
     h_pinned_bytes = nb * (sizeof(ug_packed_pos) + UG_MASK_WORDS * 4 + UG_NUM_PLANES * UG_NUM_POINTS +
@@ -330,7 +335,8 @@ int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act, const 
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   }
-  if (conv_impl == 2 && C % 64 == 0) return enqueue_tower_v2(n, s, final_act, final_lo);
+  if (conv_impl == 2 && C % 64 == 0)
+    return n <= sb_max_batch ? enqueue_tower_sb(n, s, final_act, final_lo) : enqueue_tower_v2(n, s, final_act, final_lo);
   const int ctas = conv_ctas;
   ConvArgs a{};
   a.M = n * UG_NUM_POINTS;
@@ -457,6 +463,80 @@ int ug_eval::enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, con
   return 0;
 }
 
+// The tower on the small-batch kernel: same buffers, same layer sequence and arithmetic as enqueue_tower_v2.
+int ug_eval::enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, const void** final_lo) {
+  const Weights& W = *weights;
+  const int C = W.C;
+  const bool split = resid_split;
+  ConvSbArgs a{};
+  a.M = n * UG_NUM_POINTS;
+  a.relu = 1;
+  a.f16 = precision == UG_PREC_FP16;
+  a.cout = C;
+  a.pdl = use_pdl ? 1 : 0;
+  a.nt = sb_nt;
+  a.cin = kCinPad;
+  a.bias = W.convs[0].bias.as<float>();
+  a.out_hi = d_s_hi[0].p;
+  a.out_lo = split ? d_s_lo[0].p : nullptr;
+  cudaError_t e = conv3x3_sb_launch(v2_a_in, W.convs[0].tm_w_sb, a, 32, device, sms, s);
+  if (e != cudaSuccess) return fail(-1, std::string("stem conv launch (small batch): ") + cudaGetErrorString(e));
+  a.cin = C;
+  *final_act = d_s_hi[0].p;
+  *final_lo = split ? d_s_lo[0].p : nullptr;
+  for (int b = 0; b < W.blocks && debug_stop != 0; ++b) {
+    const int x = b & 1, y = x ^ 1;
+    const ConvLayer& c1 = W.convs[1 + 2 * b];
+    const ConvLayer& c2 = W.convs[2 + 2 * b];
+    a.bias = c1.bias.as<float>();
+    a.res_hi = a.res_lo = nullptr;
+    a.out_hi = d_t.p;
+    a.out_lo = nullptr;
+    e = conv3x3_sb_launch(v2_a_s[x], c1.tm_w_sb, a, 64, device, sms, s);
+    if (e != cudaSuccess) return fail(-1, std::string("tower conv launch (small batch): ") + cudaGetErrorString(e));
+    *final_act = d_t.p;
+    *final_lo = nullptr;
+    if (debug_stop == 2 * b + 1) break;
+    // Last layer: through conv3x3_v2 with the head 1x1 convolutions fused into its epilogue, exactly as at large
+    // batches, so that a position's policy and value are bit-identical whatever batch it rides in (the fused heads read
+    // the fp32 accumulators; an unfused head kernel would read the 16-bit rounded activation).  One CTA-pair tile time
+    // for this one layer.
+    if (fuse_heads && debug_stop < 0 && b == W.blocks - 1 && conv3x3_v2_can_fuse_heads(64, 1, split, split, W.pc + W.vc)) {
+      ConvV2Args v{};
+      v.M = a.M;
+      v.relu = 1;
+      v.f16 = a.f16;
+      v.cin = v.cout = C;
+      v.pdl = a.pdl;
+      v.bias = c2.bias.as<float>();
+      v.has_res = 1;
+      v.has_res_lo = v.has_out_lo = split;
+      v.head_w = W.head_conv_w.as<float>();
+      v.head_b = W.head_conv_b.as<float>();
+      v.head_out = d_feat.as<float>();
+      v.head_channels = W.pc + W.vc;
+      const ConvV2Maps m{&v2_a_t, &c2.tm_w[1], &v2_res_hi[x], split ? &v2_res_lo[x] : nullptr, &v2_out_hi[y],
+                         split ? &v2_out_lo[y] : nullptr};
+      e = conv3x3_v2_launch(m, v, 64, device, sms, s);
+      if (e != cudaSuccess) return fail(-1, std::string("tower conv launch: ") + cudaGetErrorString(e));
+      *final_act = nullptr;  // d_feat already holds relu(head conv)
+      *final_lo = nullptr;
+      break;
+    }
+    a.bias = c2.bias.as<float>();
+    a.res_hi = d_s_hi[x].p;
+    a.res_lo = split ? d_s_lo[x].p : nullptr;
+    a.out_hi = d_s_hi[y].p;
+    a.out_lo = split ? d_s_lo[y].p : nullptr;
+    e = conv3x3_sb_launch(v2_a_t, c2.tm_w_sb, a, 64, device, sms, s);
+    if (e != cudaSuccess) return fail(-1, std::string("tower conv launch (small batch): ") + cudaGetErrorString(e));
+    *final_act = d_s_hi[y].p;
+    *final_lo = split ? d_s_lo[y].p : nullptr;
+    if (debug_stop == 2 * b + 2) break;
+  }
+  return 0;
+}
+
 int ug_eval::enqueue_heads(const void* act, const void* act_lo, int n, const uint32_t* d_leg, int vt, float* d_pol,
                            float* d_val, cudaStream_t s) {
   const HeadWeights hw = weights->head();
@@ -484,7 +564,8 @@ int ug_eval::enqueue(Src kind, const void* d_src, int n, const uint32_t* d_leg, 
   if (n <= 0 || n > max_batch) return fail(-1, "batch size " + std::to_string(n) + " outside [1, max_batch]");
   if (!use_graphs) return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
   const GraphKey key((int)kind, n, d_src, (const void*)d_leg, (const void*)d_pol, (const void*)d_val, vt,
-                     conv_ctas * 4 + precision + (resid_split ? 8192 : 0) + conv_impl * 16384 + (use_pdl ? 65536 : 0) + (fuse_heads ? 131072 : 0) + (tile_deps ? 262144 : 0) + (debug_stop + 1) * 16);
+                     conv_ctas * 4 + precision + (resid_split ? 8192 : 0) + conv_impl * 16384 + (use_pdl ? 65536 : 0) + (fuse_heads ? 131072 : 0) + (tile_deps ? 262144 : 0) + (debug_stop + 1) * 16 +
+                         (n <= sb_max_batch ? (1 << 19) + (sb_nt << 20) : 0));
   auto it = graphs.find(key);
   if (it == graphs.end()) {
     if (graphs.size() > 1024) drop_graphs();
@@ -551,6 +632,11 @@ ug_eval* ug_eval_create(int device, int precision, int max_batch) {
   if (pd && (pd[0] == '0' || pd[0] == '1')) h->use_pdl = pd[0] == '1';
   const char* ci = getenv("UGEVAL_CONV_IMPL");
   if (ci && (ci[0] == '1' || ci[0] == '2')) h->conv_impl = ci[0] - '0';
+  if (const char* sm = getenv("UGEVAL_SB_MAX")) h->sb_max_batch = atoi(sm) > 0 ? atoi(sm) : 0;
+  if (const char* sn = getenv("UGEVAL_SB_NT")) {
+    const int v = atoi(sn);
+    if (v == 16 || v == 32 || v == 64 || v == 128) h->sb_nt = v;
+  }
   const char* rs = getenv("UGEVAL_RESID_SPLIT");
   if (rs && (rs[0] == '0' || rs[0] == '1')) h->resid_split = rs[0] == '1';
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -672,6 +758,13 @@ int ug_eval_set_residual_split(ug_eval* h, int on) {
   return 0;
 }
 
+int ug_eval_set_small_batch(ug_eval* h, int max_batch, int nt) {
+  if (!h || max_batch < 0 || (nt != 0 && nt != 16 && nt != 32 && nt != 64 && nt != 128)) return -1;
+  h->sb_max_batch = max_batch;
+  h->sb_nt = nt;
+  return 0;
+}
+
 int ug_eval_info(const ug_eval* h, ug_net_info* out) {
   if (!h || !out || !h->weights) return -1;
   const Weights& W = *h->weights;
@@ -687,6 +780,7 @@ int ug_eval_info(const ug_eval* h, ug_net_info* out) {
   out->conv_ctas = h->conv_ctas;
   out->sm_count = h->sms;
   out->conv_impl = (h->conv_impl == 2 && W.C % 64 == 0) ? 2 : 1;
+  out->small_batch_max = out->conv_impl == 2 ? h->sb_max_batch : 0;
   return 0;
 }
 
@@ -934,6 +1028,56 @@ int ug_k_conv3x3_bf16(int device, const void* d_in, const void* d_w, const float
   a.relu = relu;
   cudaError_t e = conv3x3_tc_launch(ta, tb, a, ck, ctas, prop.multiProcessorCount, 0);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return -4; }
+  return 0;
+}
+
+int ug_k_conv3x3_sb(int device, const void* d_in, const void* d_w, const float* d_bias, const void* d_res_hi,
+                    const void* d_res_lo, void* d_out_hi, void* d_out_lo, int n, int n_alloc, int cin, int cout,
+                    int relu, int f16, int nt, int pdl, int iters, float* ms_out) {
+  cudaSetDevice(device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+  std::string err;
+  const int ck = (cin % 64 == 0) ? 64 : 32;
+  CUtensorMap ta, tw;
+  if (!make_tmap_rows(&ta, d_in, (long)n_alloc * UG_NUM_POINTS, cin, ck, 168, &err) ||
+      !make_tmap_weights(&tw, d_w, cout, 9 * cin, ck, 16, &err)) {
+    g_create_error = err;
+    return -2;
+  }
+  ConvSbArgs a{};
+  a.bias = d_bias;
+  a.res_hi = d_res_hi;
+  a.res_lo = d_res_lo;
+  a.out_hi = d_out_hi;
+  a.out_lo = d_out_lo;
+  a.M = n * UG_NUM_POINTS;
+  a.cin = cin;
+  a.cout = cout;
+  a.relu = relu;
+  a.f16 = f16;
+  a.nt = nt;
+  a.pdl = pdl;
+  cudaStream_t s = nullptr;
+  cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaError_t e = conv3x3_sb_launch(ta, tw, a, ck, device, prop.multiProcessorCount, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess && iters > 0) {
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < iters && e == cudaSuccess; ++i) e = conv3x3_sb_launch(ta, tw, a, ck, device, prop.multiProcessorCount, s);
+    cudaEventRecord(e1, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms_out) *ms_out = ms / iters;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaStreamDestroy(s);
   if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return -4; }
   return 0;
 }

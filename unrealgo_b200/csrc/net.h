@@ -40,6 +40,7 @@ struct ConvLayer {
   DevBuf w_f32;    // [3][3][cin][cout] folded (fp32 validation path)
   DevBuf bias;     // [cout] fp32
   CUtensorMap tm_w[2];  // index = ctas-1 (box rows differ)
+  CUtensorMap tm_w_sb;  // box {ck, 16}: the small-batch kernel loads its NT weight rows 16 at a time
 };
 
 struct Weights {
@@ -65,6 +66,11 @@ struct ug_eval {
   // an experiment kept behind UGEVAL_TILE_DEPS=1.
   bool tile_deps = false;
   bool use_pdl = true;      // programmatic dependent launch between tower layers (UGEVAL_PDL=0 disables)
+  // Batches of up to sb_max_batch positions run the tower on conv3x3_sb.cu (128 x NT tiles over many SMs) instead of
+  // conv3x3_v2.cu (256 x 256 CTA-pair tiles): the batch sizes the reference's own engine issues (1 .. 16).
+  // UGEVAL_SB_MAX / ug_eval_set_small_batch_max; 0 disables.  sb_nt: tile width override (0 = from the grid size).
+  int sb_max_batch = 24;
+  int sb_nt = 0;
   bool resid_split = true;  // carry the residual stream as hi + lo 16-bit pair (numerics)
   int value_transform = UG_TR_IDENTITY;
   bool use_graphs = true;
@@ -116,6 +122,7 @@ struct ug_eval {
   int enqueue_encoder(Src kind, const void* d_src, int n, cudaStream_t s);
   int enqueue_tower(int n, cudaStream_t s, const void** final_act, const void** final_lo);
   int enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, const void** final_lo);
+  int enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, const void** final_lo);
   int enqueue_heads(const void* act, const void* act_lo, int n, const uint32_t* d_legal, int vt, float* d_policy, float* d_value,
                     cudaStream_t s);
 };

@@ -147,6 +147,11 @@ class DlTFNetworkEvaluator:
         if self._lib.ug_eval_set_conv_impl(self._h, impl) != 0:
             raise ValueError("impl must be 1 or 2")
 
+    def set_small_batch(self, max_batch, nt=0):
+        """batches <= max_batch run the small-batch tower kernel (0 disables); nt = output channels per CTA (0 = auto)"""
+        if self._lib.ug_eval_set_small_batch(self._h, max_batch, nt) != 0:
+            raise ValueError("max_batch >= 0, nt in (0, 16, 32, 64, 128)")
+
     def set_residual_split(self, on):
         self._lib.ug_eval_set_residual_split(self._h, 1 if on else 0)
 
