@@ -112,7 +112,8 @@ int ug_eval_set_conv_impl(ug_eval* h, int impl);
 /* Batches of at most max_batch positions run the tower on the small-batch kernel (conv3x3_sb.cu: 128-row x nt-column
  * tiles on many SMs) — the batch sizes the reference's engine issues (1 .. MAX_BATCHES = 16,
  * funcapproximator/DlTFNetworkEvaluator.h:15; search/UctSearch.cpp:183-186).  max_batch 0 disables; nt = output
- * channels per CTA (16/32/64/128, 0 = chosen from the grid size).  Default 24 / 0 (UGEVAL_SB_MAX, UGEVAL_SB_NT). */
+ * channels per CTA (16/32/64/128, 0 = chosen from the grid size).  Default 32 / 0 (UGEVAL_SB_MAX, UGEVAL_SB_NT); a batch
+ * also has to fit one wave of the SMs at 128 channels per CTA (26 positions for 256 filters on 148 SMs). */
 int ug_eval_set_small_batch(ug_eval* h, int max_batch, int nt);
 /* carry the residual stream as a hi+lo pair of 16-bit tensors (1) or as one 16-bit tensor (0); numerics knob */
 int ug_eval_set_residual_split(ug_eval* h, int on);
@@ -237,12 +238,18 @@ typedef struct ug_selfplay_config {
    * of GetMeanValue, :665-679, not the USE_DIRECT_VISITCOUNT one of the shipped build, :661-664, which ignores them),
    * so that a single game can fill a batch.  Results then depend on the order evaluations return. */
   int leaves_per_game;
+  /* harness option (0 = reference behaviour): every game starts from a position reached by this many uniformly random
+   * legal moves (generated like the search's own moves, no pass unless forced) played before the first search, so
+   * that a bounded benchmark sample searches middle-game and endgame positions — captures on the board, fewer legal
+   * moves, longer capture/ko work per move — instead of near-empty boards.  Not recorded: incompatible with record_dir. */
+  int prelude_moves;
 } ug_selfplay_config;
 typedef struct ug_selfplay_stats {
   uint64_t playouts, evaluations, batches, flush_timeouts, moves, games_finished, terminal_leaves;
   double seconds, playouts_per_s, mean_batch, mean_tree_nodes;
 } ug_selfplay_stats;
-/* moves_out (optional): [games][max_moves or 722] policy indices (361 = pass); n_moves_out: [games] */
+/* moves_out (optional): [games][(max_moves or 722) + prelude_moves] policy indices (361 = pass), the prelude's moves
+ * first; n_moves_out: [games] */
 int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg, ug_selfplay_stats* stats, int16_t* moves_out,
                     int* n_moves_out);
 

@@ -36,15 +36,17 @@ int64_t ug_tfrecord_close(ug_tfrecord*) { return g_rec_no; }
 #include "stub_queue.h"
 
 int main(int argc, char** argv) {
-  if (argc < 7) { fprintf(stderr, "usage: games threads playouts moves reuse leaves_per_game [random_opening_moves=2] [puct]\n"); return 2; }
+  if (argc < 7) { fprintf(stderr, "usage: games threads playouts moves reuse leaves_per_game [random_opening_moves=2] [puct] [prelude_moves]\n"); return 2; }
   ug_selfplay_config cfg{};
   cfg.games = atoi(argv[1]); cfg.threads = atoi(argv[2]); cfg.playouts_per_move = atoi(argv[3]);
   cfg.max_moves = atoi(argv[4]); cfg.reuse_tree = atoi(argv[5]); cfg.leaves_per_game = atoi(argv[6]);
   cfg.max_batch = 64; cfg.timeout_us = 100; cfg.random_opening_moves = argc > 7 ? atoi(argv[7]) : 2; cfg.seed = 9;
   if (argc > 8) cfg.puct = (float)atof(argv[8]);
+  if (argc > 9) cfg.prelude_moves = atoi(argv[9]);
+  const int row = cfg.max_moves + cfg.prelude_moves;
   if (getenv("UGSTUB_PRINT_VISITS")) cfg.record_dir = "/tmp";
   if (getenv("UGSTUB_RECORD_DIR")) cfg.record_dir = getenv("UGSTUB_RECORD_DIR");
-  std::vector<int16_t> moves((size_t)cfg.games * cfg.max_moves);
+  std::vector<int16_t> moves((size_t)cfg.games * row);
   std::vector<int> n_moves((size_t)cfg.games);
   ug_selfplay_stats st{};
   ug_eval e{};
@@ -53,7 +55,7 @@ int main(int argc, char** argv) {
          (unsigned long long)st.moves, (unsigned long long)st.games_finished, (unsigned long long)st.terminal_leaves);
   for (int g = 0; g < cfg.games; ++g) {
     printf("game %d:", g);
-    for (int i = 0; i < n_moves[(size_t)g]; ++i) printf(" %d", moves[(size_t)g * cfg.max_moves + i]);
+    for (int i = 0; i < n_moves[(size_t)g]; ++i) printf(" %d", moves[(size_t)g * row + i]);
     printf("\n");
   }
   return rc;

@@ -20,8 +20,8 @@ def exe(tmp_path_factory):
     return out
 
 
-def _run(exe, games, threads, playouts, moves, reuse, leaves):
-    r = subprocess.run([exe] + [str(x) for x in (games, threads, playouts, moves, reuse, leaves)],
+def _run(exe, games, threads, playouts, moves, reuse, leaves, *more):
+    r = subprocess.run([exe] + [str(x) for x in (games, threads, playouts, moves, reuse, leaves) + more],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     lines = r.stdout.splitlines()
@@ -62,3 +62,18 @@ def test_virtual_loss_leaves_keep_the_books(exe):
         for mv in game:
             assert b.is_legal(mv)
             b.play(mv)
+
+
+def test_prelude_moves_start_the_search_in_the_middle_game(exe):
+    """the benchmark's mid-game sample: 150 random legal moves, then 3 searched moves per game"""
+    s1, g1 = _run(exe, 8, 1, 60, 3, 1, 1, 0, 0, 150)
+    s3, g3 = _run(exe, 8, 3, 60, 3, 1, 1, 0, 0, 150)
+    assert g1 == g3 and s1["playouts"] == 8 * 3 * 60 and s1["moves"] == 8 * 3
+    for g in g1:
+        assert len(g) == 153
+        b = oracle.Board()
+        for mv in g:
+            assert b.is_legal(mv)
+            b.play(mv)
+        assert sum(1 for mv in g[:150] if mv == 361) == 0   # no pass while other moves exist
+    assert len({tuple(g[:150]) for g in g1}) == 8

@@ -42,7 +42,7 @@ class SelfplayConfig(C.Structure):
                 ("max_batch", C.c_int), ("timeout_us", C.c_int), ("reuse_tree", C.c_int),
                 ("random_opening_moves", C.c_int), ("puct", C.c_float), ("seed", C.c_uint64),
                 ("record_dir", C.c_char_p), ("komi", C.c_float), ("game_index_base", C.c_int),
-                ("leaves_per_game", C.c_int)]
+                ("leaves_per_game", C.c_int), ("prelude_moves", C.c_int)]
 
 
 class SelfplayStats(C.Structure):

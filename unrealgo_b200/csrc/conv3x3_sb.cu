@@ -359,7 +359,8 @@ cudaError_t conv3x3_sb_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, Co
                               cudaStream_t stream) {
   if (ck != 64 && ck != 32) return cudaErrorInvalidValue;
   if (a.cin % ck != 0 || a.cin / ck > (ck == 64 ? 4 : 1)) return cudaErrorInvalidValue;
-  if (a.nt == 0) a.nt = conv3x3_sb_pick_nt(a.M, a.cout, sms);
+  // a forced width that does not divide this layer's channel count (a narrow net) falls back to the automatic choice
+  if (a.nt == 0 || (a.nt > 0 && a.cout % a.nt != 0)) a.nt = conv3x3_sb_pick_nt(a.M, a.cout, sms);
   if (a.nt != 16 && a.nt != 32 && a.nt != 64 && a.nt != 128) return cudaErrorInvalidValue;
   if (a.cout % a.nt != 0 || a.M <= 0 || !a.out_hi || !a.bias) return cudaErrorInvalidValue;
   if (a.res_lo && !a.res_hi) return cudaErrorInvalidValue;

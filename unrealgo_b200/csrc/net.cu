@@ -247,6 +247,10 @@ void ug_eval::drop_graphs() {
 bool ug_eval::ensure_workspace(int C) {
   if (ws_C == C) return true;
   drop_graphs();
+  // The buffers are resized in place.  Should an allocation fail midway (a hot swap to a wider tower on a full GPU),
+  // the old width's buffers and tensor maps are partly gone: ws_C = 0 marks the workspace invalid and the caller drops
+  // the old weights, so later runs fail with "no network loaded" instead of writing past smaller buffers.
+  ws_C = 0;
   const size_t nb = (size_t)max_batch;
   const size_t act_elems = nb * UG_NUM_POINTS * C;
   bool ok = d_pos.alloc(nb * sizeof(ug_packed_pos)) && d_legal.alloc(nb * UG_MASK_WORDS * 4) &&
@@ -309,6 +313,15 @@ int ug_eval::enqueue_encoder(Src kind, const void* d_src, int n, cudaStream_t s)
   return 0;
 }
 
+// The small-batch kernel wins while its grid at the widest tile (128 output channels per CTA) still fits one wave of
+// the SMs: 26 positions on a 148-SM part with 256 filters (measured on the 20x256 net: 0.62 ms against 0.82 ms at n = 24,
+// 1.10 ms against 0.84 ms at n = 32, where it needs two waves).
+bool ug_eval::use_small_batch(int n) const {
+  if (!weights || n > sb_max_batch) return false;
+  const int m_tiles = (n * UG_NUM_POINTS + 127) / 128;
+  return m_tiles * ((weights->C + 127) / 128) <= sms;
+}
+
 int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act, const void** final_lo) {
   const Weights& W = *weights;
   const int C = W.C;
@@ -336,7 +349,7 @@ int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act, const 
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   }
   if (conv_impl == 2 && C % 64 == 0)
-    return n <= sb_max_batch ? enqueue_tower_sb(n, s, final_act, final_lo) : enqueue_tower_v2(n, s, final_act, final_lo);
+    return use_small_batch(n) ? enqueue_tower_sb(n, s, final_act, final_lo) : enqueue_tower_v2(n, s, final_act, final_lo);
   const int ctas = conv_ctas;
   ConvArgs a{};
   a.M = n * UG_NUM_POINTS;
@@ -565,7 +578,7 @@ int ug_eval::enqueue(Src kind, const void* d_src, int n, const uint32_t* d_leg, 
   if (!use_graphs) return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
   const GraphKey key((int)kind, n, d_src, (const void*)d_leg, (const void*)d_pol, (const void*)d_val, vt,
                      conv_ctas * 4 + precision + (resid_split ? 8192 : 0) + conv_impl * 16384 + (use_pdl ? 65536 : 0) + (fuse_heads ? 131072 : 0) + (tile_deps ? 262144 : 0) + (debug_stop + 1) * 16 +
-                         (n <= sb_max_batch ? (1 << 19) + (sb_nt << 20) : 0));
+                         (use_small_batch(n) ? (1 << 19) + (sb_nt << 20) : 0));
   auto it = graphs.find(key);
   if (it == graphs.end()) {
     if (graphs.size() > 1024) drop_graphs();
@@ -704,7 +717,15 @@ int ug_eval_load_checkpoint(ug_eval* h, const char* prefix) {
   if (!ck.open(h->ckpt_prefix, &err)) return h->fail(1, err);
   Weights* W = build_weights(h->plan, ck, h->precision == UG_PREC_FP16, &err);
   if (!W) return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err);
-  if (!h->ensure_workspace(W->C)) { delete W; return 1; }
+  if (!h->ensure_workspace(W->C)) {
+    delete W;
+    if (h->weights && h->weights->C != h->ws_C) {  // the old network's workspace did not survive the attempt
+      cudaStreamSynchronize(h->stream);
+      delete h->weights;
+      h->weights = nullptr;
+    }
+    return 1;
+  }
   cudaStreamSynchronize(h->stream);
   h->drop_graphs();  // graphs bake weight pointers
   delete h->weights;

@@ -69,7 +69,7 @@ struct ug_eval {
   // Batches of up to sb_max_batch positions run the tower on conv3x3_sb.cu (128 x NT tiles over many SMs) instead of
   // conv3x3_v2.cu (256 x 256 CTA-pair tiles): the batch sizes the reference's own engine issues (1 .. 16).
   // UGEVAL_SB_MAX / ug_eval_set_small_batch_max; 0 disables.  sb_nt: tile width override (0 = from the grid size).
-  int sb_max_batch = 24;
+  int sb_max_batch = 32;
   int sb_nt = 0;
   bool resid_split = true;  // carry the residual stream as hi + lo 16-bit pair (numerics)
   int value_transform = UG_TR_IDENTITY;
@@ -111,6 +111,7 @@ struct ug_eval {
   int fail(int code, const std::string& msg) const { last_error = msg; return code; }
   bool ensure_workspace(int C);
   bool is_registered(const void* p, size_t bytes) const;
+  bool use_small_batch(int n) const;
   void drop_graphs();
   // source kinds for enqueue()
   enum Src { SRC_PACKED = 0, SRC_CHW = 1, SRC_HWC = 2 };

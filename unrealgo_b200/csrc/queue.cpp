@@ -42,6 +42,7 @@ struct Slot {
   uint32_t has_legal;
   float policy[UG_NUM_MOVES];
   float value;
+  int failed;                       // the batch this leaf rode in did not run: policy/value are not results
 };
 
 constexpr int kIdBits = 20;
@@ -59,6 +60,7 @@ struct Staging {
   int n = 0;
   bool any_legal = false;
   bool busy = false;
+  int rc = 0;                        // evaluator return code of this batch (failures belong to a batch, not the queue)
 };
 
 inline void cpu_relax() {
@@ -85,8 +87,8 @@ struct ug_queue {
   std::deque<int> inflight;         // staging indices in submission order
   std::atomic<bool> quit{false};
   bool pause_req = false, paused = false;
-  std::atomic<uint64_t> n_batches{0}, n_leaves{0}, n_timeouts{0};
-  std::atomic<int> error{0};
+  std::atomic<uint64_t> n_batches{0}, n_leaves{0}, n_timeouts{0}, n_failed{0};
+  std::atomic<int> error{0};        // set only by a CUDA (context-wide) error: closes the queue
 
   void gather_loop();
   void complete_loop();
@@ -177,7 +179,8 @@ void ug_queue::gather_loop() {
     if (n_run > max_batch) n_run = max_batch;
     const int rc = ug_eval_run_packed_device(eval, S.d_pos, n_run, S.any_legal ? S.d_legal : nullptr, S.d_policy,
                                              S.d_value, eval->stream);
-    if (rc != 0 && error.exchange(rc) == 0)
+    S.rc = rc;
+    if (rc != 0 && n_failed.fetch_add(1, std::memory_order_relaxed) == 0)
       fprintf(stderr, "ugeval queue: evaluator failure %d on a batch of %d: %s\n", rc, n_run, ug_last_error(eval));
     cudaEventRecord(S.ev_done, eval->stream);
     cudaStreamWaitEvent(s_out, S.ev_done, 0);
@@ -207,12 +210,17 @@ void ug_queue::complete_loop() {
     }
     Staging& S = st[which];
     const cudaError_t ce = cudaEventSynchronize(S.ev_out);
+    // a CUDA error is sticky for the whole context: every later batch fails too, so it closes the queue
     if (ce != cudaSuccess && error.exchange(-1) == 0)
       fprintf(stderr, "ugeval queue: CUDA error while waiting for a batch: %s\n", cudaGetErrorString(ce));
+    const int failed = (S.rc != 0 || ce != cudaSuccess) ? 1 : 0;
     for (int i = 0; i < S.n; ++i) {
       Slot& sl = slots[S.ids[(size_t)i]];
-      memcpy(sl.policy, S.h_out + (size_t)i * UG_NUM_MOVES, sizeof(sl.policy));
-      sl.value = S.h_out[(size_t)S.n * UG_NUM_MOVES + i];
+      if (!failed) {
+        memcpy(sl.policy, S.h_out + (size_t)i * UG_NUM_MOVES, sizeof(sl.policy));
+        sl.value = S.h_out[(size_t)S.n * UG_NUM_MOVES + i];
+      }
+      sl.failed = failed;
       sl.state.store(SLOT_READY, std::memory_order_release);
     }
     {
@@ -260,6 +268,12 @@ ug_queue* ug_queue_create(ug_eval* h, int max_batch, int timeout_us, int capacit
          cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming) == cudaSuccess &&
          // the completion thread sleeps on this one instead of spinning a core away (4 CPUs per GPU on 8-GPU boxes)
          cudaEventCreateWithFlags(&S.ev_out, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
+  }
+  for (int i = 0; i < 2 && ok; ++i) {
+    // batches are launched on sizes rounded up to 8: the rows past n must be defined data (an all-zero position, every
+    // move legal), not whatever cudaMalloc returned — a zero legal sum would put NaNs in rows nobody reads
+    ok = cudaMemset(q->st[i].d_pos, 0, (size_t)max_batch * sizeof(ug_packed_pos)) == cudaSuccess &&
+         cudaMemset(q->st[i].d_legal, 0xff, (size_t)max_batch * UG_MASK_WORDS * 4) == cudaSuccess;
   }
   if (!ok) {
     h->fail(-1, "queue: cannot allocate staging buffers");
@@ -334,11 +348,18 @@ static inline bool ready(const Slot& sl, int64_t ticket) {
          sl.ticket.load(std::memory_order_relaxed) == (uint64_t)ticket;
 }
 
-static inline void take(ug_queue* q, Slot& sl, int64_t ticket, float* policy, float* value) {
-  if (policy) memcpy(policy, sl.policy, sizeof(sl.policy));
-  if (value) *value = sl.value;
+// copies the result out (nothing on a failed batch: outputs stay untouched) and frees the slot; returns the slot's
+// failure flag.  The ticket is cleared so that waiting on it again reports "not outstanding" instead of spinning.
+static inline int take(ug_queue* q, Slot& sl, int64_t ticket, float* policy, float* value) {
+  const int failed = sl.failed;
+  if (!failed) {
+    if (policy) memcpy(policy, sl.policy, sizeof(sl.policy));
+    if (value) *value = sl.value;
+  }
+  sl.ticket.store(0, std::memory_order_relaxed);
   sl.state.store(SLOT_FREE, std::memory_order_release);
   q->free_ids.push((uint32_t)((uint64_t)ticket & ((1ull << kIdBits) - 1)));
+  return failed;
 }
 
 int ug_queue_wait(ug_queue* q, int64_t ticket, float* policy, float* value) {
@@ -353,8 +374,7 @@ int ug_queue_wait(ug_queue* q, int64_t ticket, float* policy, float* value) {
     std::unique_lock<std::mutex> lk(q->mu);
     q->cv_results.wait_for(lk, std::chrono::microseconds(200));
   }
-  take(q, *sl, ticket, policy, value);
-  return q->error.load() ? -1 : 0;
+  return (take(q, *sl, ticket, policy, value) || q->error.load()) ? -1 : 0;
 }
 
 int ug_queue_poll(ug_queue* q, int64_t ticket, float* policy, float* value) {
@@ -362,8 +382,7 @@ int ug_queue_poll(ug_queue* q, int64_t ticket, float* policy, float* value) {
   Slot* sl = slot_of(q, ticket);
   if (!sl) return -1;
   if (!ready(*sl, ticket)) return q->quit.load(std::memory_order_acquire) ? -1 : 0;
-  take(q, *sl, ticket, policy, value);
-  return q->error.load() ? -1 : 1;
+  return (take(q, *sl, ticket, policy, value) || q->error.load()) ? -1 : 1;
 }
 
 int ug_queue_stats(ug_queue* q, uint64_t* batches, uint64_t* leaves, uint64_t* flush_timeouts) {

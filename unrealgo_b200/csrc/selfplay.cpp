@@ -84,6 +84,7 @@ struct Game {
   std::vector<int16_t> moves;
   std::vector<float> visit_policy;  // [moves][362] root visit counts per move (only when records are written)
   int index = 0;                    // game number on this evaluator
+  int first_search_move = 0;        // moves already on the board when the first search starts (prelude_moves)
   std::mt19937_64 rng;
   float policy[UG_NUM_MOVES];
 };
@@ -341,7 +342,7 @@ void make_move(Game& g, Shared& sh) {
   int move = ugo::PASS;
   uint32_t chosen = 0;
   if (rn) {
-    if (g.root_board.move_number < sh.cfg.random_opening_moves) {
+    if (g.root_board.move_number - g.first_search_move < sh.cfg.random_opening_moves) {
       // harness option (not in the reference): diversify games with uniformly random legal opening moves
       std::uniform_int_distribution<uint32_t> d(0, rn > 1 ? rn - 2 : 0);  // PASS is last
       chosen = rbase + d(g.rng);
@@ -370,7 +371,8 @@ void make_move(Game& g, Shared& sh) {
   else new_root(g);
   g.playouts_this_move = 0;
   const int limit = sh.cfg.max_moves > 0 ? sh.cfg.max_moves : 2 * 19 * 19;
-  if (g.root_board.passes >= 2 || g.root_board.move_number >= limit) {
+  if (g.root_board.passes >= 2 || g.root_board.move_number - g.first_search_move >= limit ||
+      g.root_board.move_number >= 2 * 19 * 19) {
     g.finished = true;
     sh.games_done.fetch_add(1, std::memory_order_relaxed);
     if (sh.cfg.record_dir && !write_game_record(g, sh.cfg)) sh.record_errors.fetch_add(1, std::memory_order_relaxed);
@@ -438,6 +440,7 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
   if (cfg.puct <= 0) cfg.puct = 2.5f;  // puct_const, search/UctSearch.cpp:370
   if (cfg.max_batch <= 0) cfg.max_batch = 256;
   if (cfg.leaves_per_game > Game::kMaxLeaves) cfg.leaves_per_game = Game::kMaxLeaves;
+  if (cfg.prelude_moves < 0 || (cfg.prelude_moves > 0 && cfg.record_dir)) return -1;
   Shared sh;
   sh.cfg = cfg;
   sh.q = ug_queue_create(h, cfg.max_batch, cfg.timeout_us > 0 ? cfg.timeout_us : 200, 4 * cfg.games * (cfg.leaves_per_game > 1 ? cfg.leaves_per_game : 1) + 1024);
@@ -471,6 +474,19 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
             if (cfg.reuse_tree) { g.scratch.resize(cap / 2); g.scratch.clear(); }
           }
           new_root(g);
+          // mid-game sample: random legal moves before the first search (see ug_selfplay_config.prelude_moves)
+          for (int k = 0; k < cfg.prelude_moves && g.root_board.passes < 2; ++k) {
+            uint16_t mv[UG_NUM_MOVES];
+            uint32_t legal[UG_MASK_WORDS];
+            const int n = g.root_board.generate_moves(mv, legal);
+            if (n == 0) break;
+            // PASS is generated last: only when nothing else is left
+            std::uniform_int_distribution<int> d(0, n > 1 ? n - 2 : 0);
+            const uint16_t m = mv[d(g.rng)];
+            g.root_board.play(m);
+            g.moves.push_back((int16_t)m);
+          }
+          g.first_search_move = g.root_board.move_number;
         }
       });
     }
@@ -526,7 +542,7 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
   stats->mean_batch = batches ? (double)leaves / (double)batches : 0;
   stats->mean_tree_nodes = stats->moves ? (double)sh.nodes.load() / (double)stats->moves : 0;
   if (moves_out && n_moves_out) {
-    const int cap = cfg.max_moves > 0 ? cfg.max_moves : 2 * 19 * 19;
+    const int cap = (cfg.max_moves > 0 ? cfg.max_moves : 2 * 19 * 19) + cfg.prelude_moves;  // row length of moves_out
     for (int i = 0; i < cfg.games; ++i) {
       const int n = (int)std::min<size_t>(games[i].moves.size(), (size_t)cap);
       n_moves_out[i] = n;

@@ -407,14 +407,15 @@ def pack_planes(planes):
 
 def selfplay(evaluator, games, playouts_per_move, threads=4, max_moves=0, max_batch=256, timeout_us=200,
              reuse_tree=True, random_opening_moves=0, puct=0.0, seed=1, record_moves=False, record_dir=None,
-             komi=0.0, game_index_base=0, leaves_per_game=1):
+             komi=0.0, game_index_base=0, leaves_per_game=1, prelude_moves=0):
     """ug_selfplay_run: returns (stats dict, list of move lists or None)"""
     lib = _lib.load()
     cfg = _lib.SelfplayConfig(games, threads, playouts_per_move, max_moves, max_batch, timeout_us,
                               1 if reuse_tree else 0, random_opening_moves, puct, seed,
-                              record_dir.encode() if record_dir else None, komi, game_index_base, leaves_per_game)
+                              record_dir.encode() if record_dir else None, komi, game_index_base, leaves_per_game,
+                              prelude_moves)
     st = _lib.SelfplayStats()
-    cap = max_moves if max_moves > 0 else 722
+    cap = (max_moves if max_moves > 0 else 722) + prelude_moves
     moves = n_moves = None
     if record_moves:
         moves = np.zeros((games, cap), np.int16)

@@ -59,15 +59,21 @@ def pb_fixed32(num, v):
 _CRC_TABLE = None
 
 
+# bench.py's reference arm sets this to False: that process must not map the product library at all, and it writes its
+# checkpoint with tensor_crc=False so that only the few KB of index blocks go through the table loop below
+NATIVE_CRC = True
+
+
 def crc32c(data):
     """CRC-32C (Castagnoli).  Uses libugeval's exported implementation when built, else a table loop."""
-    try:
-        from . import _lib
-        lib = _lib.load()
-        buf = bytes(data)
-        return lib.ug_crc32c(buf, len(buf))
-    except (ImportError, OSError, AttributeError):
-        pass
+    if NATIVE_CRC:
+        try:
+            from . import _lib
+            lib = _lib.load()
+            buf = bytes(data)
+            return lib.ug_crc32c(buf, len(buf))
+        except (ImportError, OSError, AttributeError):
+            pass
     global _CRC_TABLE
     if _CRC_TABLE is None:
         tab = []
@@ -129,8 +135,9 @@ def _handle(off, size):
     return _varint(off) + _varint(size)
 
 
-def write_bundle(prefix, tensors, block_size=4096):
-    """tensors: dict name -> np.ndarray (float32).  Keys are stored sorted, as TensorFlow does."""
+def write_bundle(prefix, tensors, block_size=4096, tensor_crc=True):
+    """tensors: dict name -> np.ndarray (float32).  Keys are stored sorted, as TensorFlow does.  tensor_crc=False omits
+    BundleEntryProto.crc32c (an optional field: readers then skip the per-tensor check)."""
     names = sorted(tensors)
     entries = []
     with open(prefix + ".data-00000-of-00001", "wb") as df:
@@ -143,7 +150,9 @@ def write_bundle(prefix, tensors, block_size=4096):
             e = pb_varint(1, DT_FLOAT) + pb_bytes(2, shape)
             if off:
                 e += pb_varint(4, off)
-            e += pb_varint(5, len(raw)) + pb_fixed32(6, crc_mask(crc32c(raw)))
+            e += pb_varint(5, len(raw))
+            if tensor_crc:
+                e += pb_fixed32(6, crc_mask(crc32c(raw)))
             entries.append((name.encode(), e))
     # BundleHeaderProto{num_shards=1, endianness=LITTLE(0, omitted), version{producer=1}}
     header = pb_varint(1, 1) + pb_bytes(3, pb_varint(1, 1))
@@ -343,7 +352,8 @@ def random_weights(variables, seed):
     return out
 
 
-def write_synthetic_checkpoint(directory, blocks, filters, seed=20260119, name="bootstrap-ckpt", **graph_kw):
+def write_synthetic_checkpoint(directory, blocks, filters, seed=20260119, name="bootstrap-ckpt", tensor_crc=True,
+                               **graph_kw):
     """Writes <directory>/<name>.meta/.index/.data-00000-of-00001; returns (meta_path, ckpt_prefix)."""
     import os
     os.makedirs(directory, exist_ok=True)
@@ -351,5 +361,5 @@ def write_synthetic_checkpoint(directory, blocks, filters, seed=20260119, name="
     meta = os.path.join(directory, name + ".meta")
     prefix = os.path.join(directory, name)
     write_metagraph(meta, gd)
-    write_bundle(prefix, random_weights(g.variables, seed))
+    write_bundle(prefix, random_weights(g.variables, seed), tensor_crc=tensor_crc)
     return meta, prefix
