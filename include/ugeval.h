@@ -182,10 +182,11 @@ int ug_k_conv3x3_v2(int device, const void* d_in, const void* d_w, const float* 
                     const void* d_res_lo, void* d_out_hi, void* d_out_lo, int n, int n_alloc, int cin, int cout,
                     int relu, int f16, int desc_mode, int iters, float* ms_out, long long* d_prof);
 
-/* Raw entry of the small-batch conv kernel (same buffers as ug_k_conv3x3_v2; nt as ug_eval_set_small_batch). */
+/* Raw entry of the small-batch conv kernel (same buffers as ug_k_conv3x3_v2; nt as ug_eval_set_small_batch).
+ * d_prof (optional, device, [iters][148][16] int64): per-CTA time stamps of every timed launch (grids of <= 148 CTAs). */
 int ug_k_conv3x3_sb(int device, const void* d_in, const void* d_w, const float* d_bias, const void* d_res_hi,
                     const void* d_res_lo, void* d_out_hi, void* d_out_lo, int n, int n_alloc, int cin, int cout,
-                    int relu, int f16, int nt, int pdl, int iters, float* ms_out);
+                    int relu, int f16, int nt, int pdl, int iters, float* ms_out, long long* d_prof);
 
 /* planning probe: clusters of `cluster_size` CTAs of the tower kernel that fit on the device at once (a part that
  * strands SM pairs for clusters of 4 returns fewer than SMs/4) */

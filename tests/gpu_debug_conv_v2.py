@@ -15,7 +15,7 @@ lib = None
 
 
 def run(n, cin, cout, taps, desc_mode, residual, out_lo, f16=True, relu=True, seed=1, iters=0, n_alloc=None, prof=False, split_res=True,
-        impl="v2", nt=0, pdl=0):
+        impl="v2", nt=0, pdl=0, sb_prof=None):
     """impl "v2": conv3x3_v2 (ug_k_conv3x3_v2); "sb": the small-batch kernel (ug_k_conv3x3_sb, nt = tile width, 0 = auto)"""
     global lib
     if lib is None:
@@ -46,7 +46,7 @@ def run(n, cin, cout, taps, desc_mode, residual, out_lo, f16=True, relu=True, se
         rc = lib.ug_k_conv3x3_sb(0, dx.data_ptr(), dw.data_ptr(), db.data_ptr(), drh.data_ptr() if residual else None,
                                  drl.data_ptr() if drl is not None else None, doh.data_ptr(),
                                  dol.data_ptr() if out_lo else None, n, n_alloc, cin, cout, 1 if relu else 0,
-                                 1 if f16 else 0, nt, pdl, iters, C.byref(ms))
+                                 1 if f16 else 0, nt, pdl, iters, C.byref(ms), sb_prof.data_ptr() if sb_prof is not None else None)
     else:
         rc = lib.ug_k_conv3x3_v2(0, dx.data_ptr(), dw.data_ptr(), db.data_ptr(), drh.data_ptr() if residual else None,
                                  drl.data_ptr() if drl is not None else None, doh.data_ptr(), dol.data_ptr() if out_lo else None,
@@ -121,6 +121,29 @@ if __name__ == "__main__":
     if which == "probe":
         for dm in (0, 2, 4, 6):
             print(f"probe desc_mode={dm} conv1:", run(256, 256, 256, ALL, dm, False, False, iters=20, prof=True), flush=True)
+    if which == "sbprof":
+        # per-CTA time stamps of a chain of identical launches: where do the ~10 us per layer go at n = 1?
+        import numpy as np
+        for n, nt in ((1, 32), (1, 16), (16, 128)):
+            iters = 12
+            prof = torch.zeros(iters, 148, 16, dtype=torch.int64, device="cuda")
+            msg = run(n, 256, 256, ALL, 0, True, True, impl="sb", nt=nt, pdl=1, iters=iters, sb_prof=prof)
+            p = prof.cpu().numpy().astype(np.float64)
+            ctas = ((n * 361 + 127) // 128) * (256 // nt)
+            p = p[2:, :ctas]   # skip the first launches
+            clk = lambda a, b: (p[:, :, b] - p[:, :, a])
+            ghz = 1.9
+            names = [("prologue (start -> roles)", 0, 1), ("pdl_wait", 1, 2), ("wait -> first A chunk", 2, 3),
+                     ("first -> last A chunk", 3, 4), ("last A chunk -> MMAs issued", 4, 5), ("MMAs issued -> acc_full", 5, 6),
+                     ("acc_full -> epilogue done", 6, 7), ("epilogue done -> exit", 7, 10), ("whole CTA", 0, 10)]
+            print(f"n={n} nt={nt} ctas={ctas}: {msg.split('|')[-1].strip()}")
+            for nm, a, b in names:
+                d = clk(a, b) / ghz / 1e3
+                print(f"    {nm:<34s} mean {d.mean():6.2f} us  min {d.min():6.2f}  max {d.max():6.2f}")
+            g0, g1 = p[:, :, 8], p[:, :, 9]
+            print(f"    global timer: launch span (first start -> last end) {((g1.max(1) - g0.min(1))).mean() / 1e3:.2f} us, "
+                  f"launch-to-launch (start_i+1 - start_i) {np.diff(g0.min(1)).mean() / 1e3:.2f} us, "
+                  f"end_i -> first wait-return_i+1 n/a, overlap (end_i - start_i+1) {(g1.max(1)[:-1] - g0.min(1)[1:]).mean() / 1e3:.2f} us")
     if which == "sb":
         print("sb centre  n=3 64->64 nt32 :", run(3, 64, 64, [(1, 1)], 0, False, False, impl="sb", nt=32), flush=True)
         for tap in [(1, 0), (0, 1), (2, 2)]:

@@ -95,7 +95,7 @@ SIGNATURES = {
                                   C.POINTER(C.c_float), C.c_void_p]),
     "ug_k_conv3x3_sb": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                  C.c_int, C.POINTER(C.c_float)]),
+                                  C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     "ug_eval_set_small_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "ug_debug_max_active_clusters": (C.c_int, [C.c_int, C.c_int]),
     "ug_queue_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int]),

@@ -13,7 +13,8 @@
 //   A      the whole K extent of the tile resident: cin/64 TMA loads of 168 consecutive pixel rows (tile + 20-row halo
 //          either side), taps = the same slot read through a descriptor shifted by (20 + 19 dy + dx) rows, off-board
 //          rows switched off per tap with tcgen05.mma's disable-output-lane mask (exactly conv3x3_v2's scheme);
-//   B      [NT x 64] weight tile per (chunk, tap) through a ring of up to 36 stages (96 KB), 16 rows per TMA box;
+//   B      weights in stages of three filter taps ([3][NT x 64] per chunk and stage) through a ring of up to 12 stages
+//          (96 KB), 16 rows per TMA box: one mbarrier wait feeds twelve MMAs (see the MMA issuer);
 //   D      NT TMEM columns; one tile per CTA, so no double buffering;
 //   epilogue  all 8 warps (two per TMEM lane quarter, alternating 16-column steps): residual rows prefetched from
 //          global memory before the accumulator is ready, tcgen05.ld -> +bias (+residual hi/lo) -> ReLU -> 16-bit hi
@@ -43,7 +44,8 @@ constexpr int kTileM = 128;
 constexpr int kHalo = kBoard + 1;           // 20
 constexpr int kARows = kTileM + 2 * kHalo;  // 168
 constexpr int kThreads = 256;
-constexpr int kMaxStages = 36;              // one per (chunk, tap) of a 256-channel layer
+constexpr int kTapsPerStage = 3;            // filter taps per weight stage
+constexpr int kMaxStages = 12;              // 3 per 64-channel chunk of a 256-channel layer
 constexpr int kBRing = 96 * 1024;
 constexpr int kMaxEpiSteps = 4;             // 16-column steps per warp: NT = 128 -> 8 steps over two warp groups
 
@@ -77,6 +79,18 @@ __device__ __forceinline__ float2 unpack2_t(uint32_t w) {
   else return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
 
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// bring-up instrumentation: slot k of this CTA's 16 time stamps (SM clock; slots 8/9 hold the global timer in ns)
+#define UG_SB_STAMP(k)                                                                                   \
+  do {                                                                                                   \
+    if (args.prof != nullptr && lane == 0)                                                               \
+      args.prof[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (k)] = clock64();                   \
+  } while (0)
+
 template <int CK, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -103,8 +117,13 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int chunks = args.cin / CK;
   const int m0 = (int)blockIdx.x * kTileM;
   const int n0 = (int)blockIdx.y * nt;
-  const uint32_t stage_bytes = (uint32_t)nt * kRowBytes;
+  const uint32_t tap_bytes = (uint32_t)nt * kRowBytes;   // one filter tap's [NT x CK] weight tile
 
+  if (warp == 0) {
+    UG_SB_STAMP(0);
+    if (args.prof != nullptr && lane == 0)
+      args.prof[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + 8] = globaltimer_ns();
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
@@ -130,7 +149,9 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t elected = elect_one();
   if (warp == 0) {
     // ===================== A producer: the previous layer's output =====================
+    UG_SB_STAMP(1);
     pdl_wait();
+    UG_SB_STAMP(2);
     for (int j = 0; j < chunks; ++j) {
       if (elected) {
         mbar_expect_tx(&a_full[j], C::kASlot);
@@ -144,14 +165,17 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t phb = 0;
     for (int j = 0; j < chunks; ++j) {
 #pragma unroll 1
-      for (int t = 0; t < 9; ++t) {
-        const int tap = (t == 0) ? 4 : (t <= 4 ? t - 1 : t);  // centre first, then 0,1,2,3,5,6,7,8
+      for (int g = 0; g < 9 / kTapsPerStage; ++g) {
         mbar_wait(&b_empty[sb], phb ^ 1);
         if (elected) {
-          mbar_expect_tx(&b_full[sb], stage_bytes);
-          uint8_t* dst = smB + (size_t)sb * stage_bytes;
-          for (int i = 0; i < nt; i += 16)
-            tma_load_2d(dst + i * kRowBytes, &tmW, &b_full[sb], tap * args.cin + j * CK, n0 + i);
+          mbar_expect_tx(&b_full[sb], kTapsPerStage * tap_bytes);
+          uint8_t* dst = smB + (size_t)sb * (kTapsPerStage * tap_bytes);
+          for (int u = 0; u < kTapsPerStage; ++u) {
+            const int t = g * kTapsPerStage + u;
+            const int tap = (t == 0) ? 4 : (t <= 4 ? t - 1 : t);  // centre first, then 0,1,2,3,5,6,7,8
+            for (int i = 0; i < nt; i += 16)
+              tma_load_2d(dst + u * tap_bytes + i * kRowBytes, &tmW, &b_full[sb], tap * args.cin + j * CK, n0 + i);
+          }
         }
         __syncwarp();
         if (++sb == stages) { sb = 0; phb ^= 1; }
@@ -159,39 +183,54 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // One warp issues every MMA of the tile, and at these tile widths an MMA occupies the tensor pipe for only 8 .. 64
+    // cycles: the issue loop itself is the critical path of the kernel.  (First version: one mbarrier wait, one mask
+    // lookup and ~130 SASS instructions per filter tap — measured 0.2 us per tap, 7.2 of a layer's 10.4 us at n = 1.)
+    // Hence: the nine taps fully unrolled with their row shifts as immediates, the lane masks of all taps fetched
+    // once per CTA, and one barrier wait / one commit per stage of three taps (12 MMAs).
     const uint32_t idesc = make_idesc_16(kTileM, nt, F16 ? 1 : 0);
     // pixel-in-image index of the tile's first row; the lane mask of 32 consecutive rows depends only on
     // (tap, that index mod 361)
     const int q0 = m0 % kPix;
+    uint32_t msk[9][4];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        int q = q0 + 32 * w;
+        if (q >= kPix) q -= kPix;  // q0 < 361 and 32*w <= 96
+        msk[tap][w] = c_edge_mask_sb[tap][q];
+      }
+    const uint32_t tap_desc_step = tap_bytes >> 4;  // descriptor start-address units (16 B) between two taps of a stage
     int sb = 0;
     uint32_t phb = 0;
+#pragma unroll 1
     for (int j = 0; j < chunks; ++j) {
       mbar_wait(&a_full[j], 0);
-      const uint32_t a_slot = smem_u32(smA + j * C::kASlot);
-#pragma unroll 1
-      for (int t = 0; t < 9; ++t) {
-        const int tap = (t == 0) ? 4 : (t <= 4 ? t - 1 : t);
-        const int r = tap / 3, s = tap - 3 * r;
-        const int shift = kHalo + (r - 1) * kBoard + (s - 1);
-        uint32_t m[8];
+      if (j == 0) UG_SB_STAMP(3);
+      if (j == chunks - 1) UG_SB_STAMP(4);
+      const uint64_t adesc0 = make_kmajor_desc<kRowBytes>(smem_u32(smA + j * C::kASlot));
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          int q = q0 + 32 * w;
-          if (q >= kPix) q -= kPix;  // q0 < 361 and 32*w <= 96
-          m[w] = c_edge_mask_sb[tap][q];
-        }
-        m[4] = m[5] = m[6] = m[7] = 0u;
+      for (int g = 0; g < 9 / kTapsPerStage; ++g) {
         mbar_wait(&b_full[sb], phb);
         tc_fence_after();
-        const uint64_t adesc = make_kmajor_desc<kRowBytes>(a_slot + (uint32_t)shift * kRowBytes);
-        const uint64_t bdesc = make_kmajor_desc<kRowBytes>(smem_u32(smB + (size_t)sb * stage_bytes));
+        const uint64_t bdesc0 = make_kmajor_desc<kRowBytes>(smem_u32(smB + (size_t)sb * (kTapsPerStage * tap_bytes)));
         if (elected) {
 #pragma unroll
-          for (int k = 0; k < kMmaPerStep; ++k) {
-            if (tap == 4)  // the centre tap never needs a mask; it goes first and initialises the accumulator
-              umma_f16<1>(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (j | t | k) != 0);
-            else
-              umma_f16_1sm_masked(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u, m);
+          for (int u = 0; u < kTapsPerStage; ++u) {
+            constexpr int kOrder[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};
+            const int tap = kOrder[g * kTapsPerStage + u];
+            const int shift = kHalo + (tap / 3 - 1) * kBoard + (tap % 3 - 1);  // rows: a compile-time constant
+            const uint64_t adesc = adesc0 + (uint64_t)(shift * (kRowBytes / 16));
+            const uint64_t bdesc = bdesc0 + (uint64_t)(u * tap_desc_step);
+            const uint32_t m[8] = {msk[tap][0], msk[tap][1], msk[tap][2], msk[tap][3], 0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int k = 0; k < kMmaPerStep; ++k) {
+              if (tap == 4)  // the centre tap never needs a mask; it goes first and initialises the accumulator
+                umma_f16<1>(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((j | k) != 0));
+              else
+                umma_f16_1sm_masked(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u, m);
+            }
           }
           umma_commit(&b_empty[sb]);
         }
@@ -201,6 +240,7 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     if (elected) umma_commit(acc_full);
     __syncwarp();
+    UG_SB_STAMP(5);
   }
 
   // ===================== epilogue: every warp =====================
@@ -233,6 +273,7 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    if (warp == 4) UG_SB_STAMP(6);
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll
     for (int s = 0; s < kMaxEpiSteps; ++s) {
@@ -282,9 +323,15 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   }
 
+  if (warp == 4) UG_SB_STAMP(7);
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<1>(tmem_base, nt < 32 ? 32u : (uint32_t)nt);
+  if (warp == 0) {
+    UG_SB_STAMP(10);
+    if (args.prof != nullptr && lane == 0)
+      args.prof[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + 9] = globaltimer_ns();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -365,9 +412,9 @@ cudaError_t conv3x3_sb_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, Co
   if (a.cout % a.nt != 0 || a.M <= 0 || !a.out_hi || !a.bias) return cudaErrorInvalidValue;
   if (a.res_lo && !a.res_hi) return cudaErrorInvalidValue;
   if (!upload_masks(device)) return cudaErrorUnknown;  // no-op after conv3x3_sb_prepare()
-  const int ksteps = 9 * (a.cin / ck);
-  const int fit = kBRing / (a.nt * ck * 2);
-  a.stages = fit < ksteps ? fit : ksteps;
+  const int need = (9 / kTapsPerStage) * (a.cin / ck);          // stages a tile consumes
+  const int fit = kBRing / (kTapsPerStage * a.nt * ck * 2);      // stages the ring holds (>= 2: NT = 128 -> 48 KB each)
+  a.stages = fit < need ? fit : need;
   if (a.stages > kMaxStages) a.stages = kMaxStages;
   if (ck == 64) return a.f16 ? launch_sb<64, true>(tmA, tmW, a, stream) : launch_sb<64, false>(tmA, tmW, a, stream);
   return a.f16 ? launch_sb<32, true>(tmA, tmW, a, stream) : launch_sb<32, false>(tmA, tmW, a, stream);

@@ -22,6 +22,7 @@ struct ConvSbArgs {
   int nt;                 // output channels per CTA: 16, 32, 64 or 128 (0 = choose from the grid size)
   int pdl;                // launch with programmatic stream serialization
   int stages;             // filled by the launcher: depth of the weight ring
+  long long* prof;        // optional [ctas][16] time stamps of this launch (bring-up instrumentation), else null
 };
 
 // tmA: halo-tile map over the input [rows][cin] (box {ck, 168}, the same map conv3x3_v2 uses);

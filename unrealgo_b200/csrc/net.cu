@@ -96,8 +96,9 @@ bool load_conv(const TfBundle& ck, const ConvPlan& p, int ksize, HostConv* out, 
   }
   out->b.assign(cout, 0.f);
   if (p.has_bn) {
-    std::vector<float> g, be, mu, var;
-    if (!ck.read_float(p.gamma, &g, nullptr, err) || !ck.read_float(p.beta, &be, nullptr, err) ||
+    std::vector<float> g = p.gamma_const, be = p.beta_const, mu, var;  // Const scale / offset (scale=False / center=False)
+    if ((!p.gamma.empty() && !ck.read_float(p.gamma, &g, nullptr, err)) ||
+        (!p.beta.empty() && !ck.read_float(p.beta, &be, nullptr, err)) ||
         !ck.read_float(p.mean, &mu, nullptr, err) || !ck.read_float(p.var, &var, nullptr, err))
       return false;
     if ((int)g.size() != cout || (int)be.size() != cout || (int)mu.size() != cout || (int)var.size() != cout) {
@@ -1055,7 +1056,7 @@ int ug_k_conv3x3_bf16(int device, const void* d_in, const void* d_w, const float
 
 int ug_k_conv3x3_sb(int device, const void* d_in, const void* d_w, const float* d_bias, const void* d_res_hi,
                     const void* d_res_lo, void* d_out_hi, void* d_out_lo, int n, int n_alloc, int cin, int cout,
-                    int relu, int f16, int nt, int pdl, int iters, float* ms_out) {
+                    int relu, int f16, int nt, int pdl, int iters, float* ms_out, long long* d_prof) {
   cudaSetDevice(device);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
@@ -1089,7 +1090,11 @@ int ug_k_conv3x3_sb(int device, const void* d_in, const void* d_w, const float* 
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e == cudaSuccess && iters > 0) {
     cudaEventRecord(e0, s);
-    for (int i = 0; i < iters && e == cudaSuccess; ++i) e = conv3x3_sb_launch(ta, tw, a, ck, device, prop.multiProcessorCount, s);
+    for (int i = 0; i < iters && e == cudaSuccess; ++i) {
+      // time stamps: launch i writes its own [ctas][16] block (the caller sizes d_prof for iters x 148 CTAs)
+      if (d_prof) a.prof = d_prof + (size_t)i * 148 * 16;
+      e = conv3x3_sb_launch(ta, tw, a, ck, device, prop.multiProcessorCount, s);
+    }
     cudaEventRecord(e1, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     float ms = 0.f;

@@ -105,6 +105,48 @@ static void parse_list_value(const uint8_t* p, size_t n, TfAttr* a) {
   }
 }
 
+// TensorProto of a Const node (tensor.proto): dtype = 1, tensor_shape = 2, tensor_content = 4, float_val = 5
+static void parse_tensor_proto(const uint8_t* p, size_t n, TfAttr* a) {
+  PbReader r(p, n);
+  PbField f;
+  int64_t elems = 1;
+  bool have_shape = false;
+  std::vector<float> vals;
+  while (r.next(&f)) {
+    if (f.number == 1 && f.wire == 0) a->tensor_dtype = (int)f.value;
+    else if (f.number == 2 && f.wire == 2) {
+      have_shape = true;
+      PbReader s(f.data, f.size);
+      PbField sf;
+      while (s.next(&sf)) {
+        if (sf.number != 2 || sf.wire != 2) continue;
+        PbReader d(sf.data, sf.size);
+        PbField df;
+        int64_t size = 0;
+        while (d.next(&df)) if (df.number == 1) size = (int64_t)df.value;
+        elems *= size;
+      }
+    } else if (f.number == 4 && f.wire == 2) {
+      vals.resize(f.size / 4);
+      memcpy(vals.data(), f.data, vals.size() * 4);
+    } else if (f.number == 5) {
+      if (f.wire == 5) { uint32_t u = (uint32_t)f.value; float v; memcpy(&v, &u, 4); vals.push_back(v); }
+      else if (f.wire == 2) {
+        const size_t at = vals.size();
+        vals.resize(at + f.size / 4);
+        memcpy(vals.data() + at, f.data, (f.size / 4) * 4);
+      }
+    }
+  }
+  a->has_tensor = r.ok();
+  if (a->tensor_dtype != 1 || !a->has_tensor) return;  // only float constants are ever needed
+  if (!have_shape) elems = (int64_t)vals.size();
+  if (elems < 0 || elems > (1 << 24)) { a->has_tensor = false; return; }
+  if (vals.size() == 1 && elems > 1) vals.assign((size_t)elems, vals[0]);  // splat
+  if ((int64_t)vals.size() != elems) { a->has_tensor = false; return; }
+  a->tensor_f = std::move(vals);
+}
+
 static void parse_attr_value(const uint8_t* p, size_t n, TfAttr* a) {
   PbReader r(p, n);
   PbField f;
@@ -116,7 +158,8 @@ static void parse_attr_value(const uint8_t* p, size_t n, TfAttr* a) {
       case 4: { uint32_t u = (uint32_t)f.value; memcpy(&a->f, &u, 4); a->has_f = true; } break;
       case 5: a->b = f.value != 0; a->has_b = true; break;
       case 6: a->type = (int)f.value; a->has_type = true; break;
-      default: break;  // shape / tensor / func: not needed on the inference path
+      case 8: if (f.wire == 2) parse_tensor_proto(f.data, f.size, a); break;
+      default: break;  // shape / func: not needed on the inference path
     }
   }
 }
@@ -284,6 +327,22 @@ struct Walker {
     return fail("expected a variable, found '" + (v ? v->name + "' (" + v->op + ")" : std::string("?'")));
   }
 
+  // batch-norm scale / offset: a variable, or (scale=False / center=False) a float Const
+  bool var_or_const(const TfNode* n, std::string* key, std::vector<float>* values) {
+    const TfNode* v = n;
+    for (int guard = 0; v && guard < 16 && (v->op == "Identity" || v->op == "Switch"); ++guard) v = in(v, 0);
+    if (v && v->op == "Const") {
+      auto it = v->attrs.find("value");
+      if (it == v->attrs.end() || !it->second.has_tensor || it->second.tensor_dtype != 1 || it->second.tensor_f.empty())
+        return fail("constant '" + v->name + "' is not a float tensor the loader can read");
+      key->clear();
+      *values = it->second.tensor_f;
+      return true;
+    }
+    values->clear();
+    return var_of(n, key);
+  }
+
   bool conv_bn(const TfNode* n, ConvPlan* out, const TfNode** src) {
     if (!n) return false;
     if (is_bn(n->op)) {
@@ -297,8 +356,8 @@ struct Walker {
       out->eps = (ep != n->attrs.end() && ep->second.has_f) ? ep->second.f : 1e-4f;
       out->has_bn = true;
       const TfNode* p;
-      if (!(p = in(n, 1)) || !var_of(p, &out->gamma)) return false;
-      if (!(p = in(n, 2)) || !var_of(p, &out->beta)) return false;
+      if (!(p = in(n, 1)) || !var_or_const(p, &out->gamma, &out->gamma_const)) return false;
+      if (!(p = in(n, 2)) || !var_or_const(p, &out->beta, &out->beta_const)) return false;
       if (!(p = in(n, 3)) || !var_of(p, &out->mean)) return false;
       if (!(p = in(n, 4)) || !var_of(p, &out->var)) return false;
       n = rin(n, 0);

@@ -40,6 +40,11 @@ struct TfAttr {
   int type = 0;
   std::vector<int64_t> list_i;
   bool has_s = false, has_i = false, has_f = false, has_b = false, has_type = false;
+  // `tensor` (Const nodes): DT_FLOAT values only, expanded to the tensor's element count (a constant filled with one
+  // value is stored as a single float_val)
+  bool has_tensor = false;
+  int tensor_dtype = 0;
+  std::vector<float> tensor_f;
 };
 struct TfNode {
   std::string name, op;
@@ -60,7 +65,8 @@ struct ConvPlan {
   std::string kernel;            // variable holding HWIO weights
   std::string bias;              // optional BiasAdd variable
   bool has_bn = false;
-  std::string gamma, beta, mean, var;  // FusedBatchNorm inputs (gamma may be empty: scale=False -> Const ones)
+  std::string gamma, beta, mean, var;  // FusedBatchNorm inputs: checkpoint keys.  scale=False / center=False make gamma /
+  std::vector<float> gamma_const, beta_const;  // beta a Const node instead: key empty, values here ([cout])
   float eps = 1e-3f;
   int ksize = 3;
 };
