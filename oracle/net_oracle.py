@@ -4,7 +4,7 @@ The reference runs the graph inside tensorflow::Session::Run (funcapproximator/D
 TensorFlow (un-vendored third-party dependency, no version pinned: README.md:40) is not available here, so this
 module *interprets* the GraphDef node by node with torch fp32 CPU ops that restate the published semantics of
 each TensorFlow op (Conv2D NHWC/SAME, FusedBatchNorm inference: (x-mean)*rsqrt(var+eps)*gamma+beta, BiasAdd,
-Add, Relu, Reshape, MatMul, Softmax, Tanh, Cast, Identity).  It is independent of the product's C++ pattern
+Add, Relu, Reshape, MatMul, Softmax, Tanh, Cast, Identity, Switch/Merge with dead-branch semantics).  It is independent of the product's C++ pattern
 matcher: it evaluates whatever graph the .meta describes, starting from the two nn_outputs nodes.
 
 "restatement, not TensorFlow": parity against the real TF evaluator + bootstrap checkpoint is UNPINNED until
@@ -17,11 +17,20 @@ import torch.nn.functional as F
 from . import tf_reader
 
 
-def _strip(name):
+def _split(name):
+    """'node:1' -> ('node', 1); 'node' -> ('node', 0); control inputs ('^node') are filtered by the caller"""
     if name.startswith("^"):
         name = name[1:]
     head, sep, tail = name.rpartition(":")
-    return head if sep and tail.isdigit() else name
+    return (head, int(tail)) if sep and tail.isdigit() else (name, 0)
+
+
+def _strip(name):
+    return _split(name)[0]
+
+
+class _Dead(Exception):
+    """the untaken side of a Switch was asked for (TensorFlow's dead tensor): Merge catches it and takes the other input"""
 
 
 class GraphOracle:
@@ -36,7 +45,7 @@ class GraphOracle:
         return [i for i in node["inputs"] if not i.startswith("^")]
 
     def _eval(self, name, cache):
-        name = _strip(name)
+        name, idx = _split(name)
         if name in cache:
             return cache[name]
         node = self.nodes[name]
@@ -44,9 +53,24 @@ class GraphOracle:
         ins = self._data_inputs(node)
         a = node["attrs"]
         ev = lambda k: self._eval(ins[k], cache)
-        if op in ("VariableV2", "Variable"):
+        if op == "Switch":  # (data, pred) -> output 0 when pred is false, output 1 when true; never cached (two outputs)
+            taken = bool(torch.as_tensor(ev(1)).reshape(-1)[0])
+            if idx != int(taken):
+                raise _Dead(name)
+            return ev(0)
+        if op == "Merge":
+            out = None
+            for k in range(len(ins)):
+                try:
+                    out = ev(k)
+                    break
+                except _Dead:
+                    continue
+            if out is None:
+                raise _Dead(name)
+        elif op in ("VariableV2", "Variable", "VarHandleOp"):
             out = self.vars[name]
-        elif op in ("Identity", "StopGradient"):
+        elif op in ("Identity", "StopGradient", "ReadVariableOp", "PlaceholderWithDefault", "Snapshot"):
             out = ev(0)
         elif op == "Const":
             out = a["value"]["tensor"]
@@ -61,6 +85,7 @@ class GraphOracle:
             y = F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=kh // 2)
             out = y.permute(0, 2, 3, 1).contiguous()
         elif op in ("FusedBatchNorm", "FusedBatchNormV2", "FusedBatchNormV3"):
+            assert idx == 0, "only the normalised output is on the inference path"
             assert not a.get("is_training", {}).get("b", True), "inference graph expected"
             x, g, b, m, v = (ev(k) for k in range(5))
             eps = a.get("epsilon", {}).get("f", 1e-4)
@@ -85,11 +110,13 @@ class GraphOracle:
         return out
 
     @torch.no_grad()
-    def run(self, nhwc, fetch=None):
+    def run(self, nhwc, fetch=None, feeds=None):
         """nhwc: bool/int8/float array [n,19,19,17] (what TransformFeature hands to TF).
         Returns (policy float32 [n,362], value float32 [n])."""
         x = torch.from_numpy(np.ascontiguousarray(nhwc)).to(torch.float32)
         cache = {self.input_name: x}
+        for k, v in (feeds or {}).items():
+            cache[_strip(k)] = torch.as_tensor(v)
         pol = self._eval(self.outputs[0], cache)
         val = self._eval(self.outputs[1], cache)
         if fetch:

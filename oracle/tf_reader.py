@@ -51,7 +51,7 @@ def _signed(v, bits=64):
 
 
 def parse_tensor(buf):
-    dtype, dims, content, ints, floats, strs = 0, [], None, [], [], []
+    dtype, dims, content, ints, floats, strs, bools = 0, [], None, [], [], [], []
     for num, wire, v in fields(buf):
         if num == 1:
             dtype = v
@@ -77,6 +77,14 @@ def parse_tensor(buf):
                 ints.append(_signed(v))
         elif num == 8:
             strs.append(v)
+        elif num == 11:  # bool_val (packed or not)
+            bools += [bool(b) for b in v] if wire == 2 else [bool(v)]
+    if dtype == 10:
+        arr = np.frombuffer(content, np.bool_) if content is not None else np.asarray(bools, np.bool_)
+        count = int(np.prod(dims)) if dims else 1
+        if arr.size == 0 and count == 1:
+            arr = np.zeros(1, np.bool_)   # proto3 omits a false scalar
+        return arr.reshape(dims) if dims else arr.reshape(())
     if dtype == 3:
         arr = np.frombuffer(content, "<i4") if content is not None else np.asarray(ints, np.int32)
     elif dtype == 1:

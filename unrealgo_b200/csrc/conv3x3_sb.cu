@@ -271,53 +271,65 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
+    // bias of this warp's columns: fetched before the accumulator is ready, like the residual
+    float2 bs[kMaxEpiSteps][8];
+#pragma unroll
+    for (int s = 0; s < kMaxEpiSteps; ++s) {
+      const int step = 2 * s + grp;
+      if (step < total_steps) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bs[s][e] = __ldg(reinterpret_cast<const float2*>(args.bias + n0 + step * 16) + e);
+      }
+    }
     mbar_wait(acc_full, 0);
     tc_fence_after();
     if (warp == 4) UG_SB_STAMP(6);
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    // all of this warp's accumulator columns in one go: up to four tcgen05.ld in flight, one wait
+    uint32_t v[kMaxEpiSteps][16];
 #pragma unroll
     for (int s = 0; s < kMaxEpiSteps; ++s) {
       const int step = 2 * s + grp;
-      if (step < total_steps) {   // warp-uniform
-        const int c0 = step * 16;
-        uint32_t v[16];
-        tmem_ld_32x16(t_row + c0, v);
-        tmem_ld_wait();
-        if (row_ok) {
-          uint32_t ph[8], pl[8];
-          const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rh[s][0]);
-          const uint32_t* lw = reinterpret_cast<const uint32_t*>(&rl[s][0]);
+      if (step < total_steps) tmem_ld_32x16(t_row + step * 16, v[s]);   // warp-uniform condition
+    }
+    tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float2 b2 = __ldg(reinterpret_cast<const float2*>(args.bias + n0 + c0) + e);
-            float f0 = __uint_as_float(v[2 * e]) + b2.x;
-            float f1 = __uint_as_float(v[2 * e + 1]) + b2.y;
-            if (has_res) {
-              const float2 r2 = unpack2_t<F16>(rw[e]);
-              f0 += r2.x;
-              f1 += r2.y;
-              if (has_res_lo) {
-                const float2 l2 = unpack2_t<F16>(lw[e]);
-                f0 += l2.x;
-                f1 += l2.y;
-              }
-            }
-            f0 = fmaxf(f0, act_floor);
-            f1 = fmaxf(f1, act_floor);
-            ph[e] = pack2_sat<F16>(f0, f1);
-            if (has_out_lo) {
-              const float2 hi = unpack2_t<F16>(ph[e]);
-              pl[e] = pack2_sat<F16>(f0 - hi.x, f1 - hi.y);
+    for (int s = 0; s < kMaxEpiSteps; ++s) {
+      const int step = 2 * s + grp;
+      if (step < total_steps && row_ok) {
+        const int c0 = step * 16;
+        uint32_t ph[8], pl[8];
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(&rh[s][0]);
+        const uint32_t* lw = reinterpret_cast<const uint32_t*>(&rl[s][0]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float f0 = __uint_as_float(v[s][2 * e]) + bs[s][e].x;
+          float f1 = __uint_as_float(v[s][2 * e + 1]) + bs[s][e].y;
+          if (has_res) {
+            const float2 r2 = unpack2_t<F16>(rw[e]);
+            f0 += r2.x;
+            f1 += r2.y;
+            if (has_res_lo) {
+              const float2 l2 = unpack2_t<F16>(lw[e]);
+              f0 += l2.x;
+              f1 += l2.y;
             }
           }
-          uint4* o = reinterpret_cast<uint4*>(static_cast<uint16_t*>(args.out_hi) + row_off + c0);
-          o[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-          o[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+          f0 = fmaxf(f0, act_floor);
+          f1 = fmaxf(f1, act_floor);
+          ph[e] = pack2_sat<F16>(f0, f1);
           if (has_out_lo) {
-            uint4* ol = reinterpret_cast<uint4*>(static_cast<uint16_t*>(args.out_lo) + row_off + c0);
-            ol[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-            ol[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+            const float2 hi = unpack2_t<F16>(ph[e]);
+            pl[e] = pack2_sat<F16>(f0 - hi.x, f1 - hi.y);
           }
+        }
+        uint4* o = reinterpret_cast<uint4*>(static_cast<uint16_t*>(args.out_hi) + row_off + c0);
+        o[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        o[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+        if (has_out_lo) {
+          uint4* ol = reinterpret_cast<uint4*>(static_cast<uint16_t*>(args.out_lo) + row_off + c0);
+          ol[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          ol[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
         }
       }
     }

@@ -14,7 +14,8 @@ namespace {
 void json_conv(std::ostringstream& o, const ConvPlan& c) {
   o << "{\"kernel\":\"" << c.kernel << "\",\"bias\":\"" << c.bias << "\",\"bn\":" << (c.has_bn ? "true" : "false")
     << ",\"gamma\":\"" << c.gamma << "\",\"beta\":\"" << c.beta << "\",\"mean\":\"" << c.mean << "\",\"var\":\""
-    << c.var << "\",\"eps\":" << c.eps << "}";
+    << c.var << "\",\"gamma_const\":" << c.gamma_const.size() << ",\"beta_const\":" << c.beta_const.size()
+    << ",\"eps\":" << c.eps << "}";
 }
 int emit(const std::string& s, char* out, int cap) {
   if (!out || cap <= 0) return -1;
@@ -65,7 +66,12 @@ extern "C" int ug_inspect_model(const char* graph_path, const char* ckpt_prefix,
     auto add_conv = [&](const ConvPlan& c) {
       need.push_back(c.kernel);
       if (!c.bias.empty()) need.push_back(c.bias);
-      if (c.has_bn) { need.push_back(c.gamma); need.push_back(c.beta); need.push_back(c.mean); need.push_back(c.var); }
+      if (c.has_bn) {
+        if (!c.gamma.empty()) need.push_back(c.gamma);  // empty: a Const in the graph (scale=False)
+        if (!c.beta.empty()) need.push_back(c.beta);    // empty: a Const in the graph (center=False)
+        need.push_back(c.mean);
+        need.push_back(c.var);
+      }
     };
     add_conv(plan.stem);
     for (const ConvPlan& c : plan.tower) add_conv(c);
