@@ -66,6 +66,15 @@ typedef struct ug_net_info {
   int sm_count;
   int conv_impl;        /* 1 = TMA-im2col tower kernel, 2 = resident-tile kernel (see ug_eval_set_conv_impl) */
   int small_batch_max;  /* batches up to this size run the small-batch tower kernel (see ug_eval_set_small_batch) */
+  int precision;        /* UG_PREC_* in use: an fp16 evaluator falls back to bf16 for a checkpoint outside fp16's range */
+  /* range calibration of the loaded checkpoint (ug_eval_load_checkpoint runs a few built-in positions through the fp32
+   * validation tower): largest |layer output|, largest |batch-norm-folded weight|, and 65504 / max of the two */
+  float calib_max_activation;
+  float calib_max_weight;
+  float fp16_headroom;
+  /* fp16 mode: how often a tower epilogue had to clamp an output to +-65504 since the evaluator was created (counted
+   * per thread and tile, not per element); anything but 0 means results are not trustworthy */
+  uint64_t saturation_events;
 } ug_net_info;
 
 typedef struct ug_eval ug_eval;
@@ -109,6 +118,10 @@ int ug_efficient_batch_for_sms(int sm_count, int n);
 /* tower kernel generation: 1 = TMA-im2col operand staging (conv3x3_tc.cu), 2 = shared-memory-resident input tile
  * with shifted-descriptor taps and TMA-staged epilogue (conv3x3_v2.cu, default); testing/benchmark knob */
 int ug_eval_set_conv_impl(ug_eval* h, int impl);
+/* What an fp16 evaluator does with a checkpoint whose calibrated range leaves less than 8x headroom below 65504:
+ * 0 = evaluate it with bf16 operands instead (default; a warning goes to stderr, ug_net_info.precision tells),
+ * 1 = refuse it (ug_eval_load_checkpoint returns >0), 2 = load it anyway.  UGEVAL_FP16_RANGE=bf16|refuse|ignore. */
+int ug_eval_set_fp16_range_policy(ug_eval* h, int policy);
 /* Batches of at most max_batch positions run the tower on the small-batch kernel (conv3x3_sb.cu: 128-row x nt-column
  * tiles on many SMs) — the batch sizes the reference's engine issues (1 .. MAX_BATCHES = 16,
  * funcapproximator/DlTFNetworkEvaluator.h:15; search/UctSearch.cpp:183-186).  max_batch 0 disables; nt = output

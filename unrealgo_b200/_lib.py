@@ -34,6 +34,8 @@ class NetInfo(C.Structure):
         ("blocks", C.c_int), ("filters", C.c_int), ("policy_channels", C.c_int), ("value_channels", C.c_int),
         ("value_hidden", C.c_int), ("input_planes", C.c_int), ("flops_per_position", C.c_double),
         ("conv_ctas", C.c_int), ("sm_count", C.c_int), ("conv_impl", C.c_int), ("small_batch_max", C.c_int),
+        ("precision", C.c_int), ("calib_max_activation", C.c_float), ("calib_max_weight", C.c_float),
+        ("fp16_headroom", C.c_float), ("saturation_events", C.c_uint64),
     ]
 
 
@@ -97,6 +99,7 @@ SIGNATURES = {
                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     "ug_eval_set_small_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "ug_eval_set_fp16_range_policy": (C.c_int, [C.c_void_p, C.c_int]),
     "ug_debug_max_active_clusters": (C.c_int, [C.c_int, C.c_int]),
     "ug_queue_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "ug_queue_destroy": (None, [C.c_void_p]),

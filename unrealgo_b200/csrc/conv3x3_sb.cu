@@ -293,6 +293,7 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (step < total_steps) tmem_ld_32x16(t_row + step * 16, v[s]);   // warp-uniform condition
     }
     tmem_ld_wait();
+    float out_max = 0.f;  // fp16 range watch
 #pragma unroll
     for (int s = 0; s < kMaxEpiSteps; ++s) {
       const int step = 2 * s + grp;
@@ -317,6 +318,7 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           f0 = fmaxf(f0, act_floor);
           f1 = fmaxf(f1, act_floor);
+          if constexpr (F16) out_max = fmaxf(out_max, fmaxf(fabsf(f0), fabsf(f1)));
           ph[e] = pack2_sat<F16>(f0, f1);
           if (has_out_lo) {
             const float2 hi = unpack2_t<F16>(ph[e]);
@@ -333,8 +335,10 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
+    if constexpr (F16) {
+      if (out_max > 65504.f && args.sat_count != nullptr) atomicAdd(args.sat_count, 1ull);
+    }
   }
-
   if (warp == 4) UG_SB_STAMP(7);
   tc_fence_before();
   __syncthreads();

@@ -22,6 +22,7 @@ struct ConvSbArgs {
   int nt;                 // output channels per CTA: 16, 32, 64 or 128 (0 = choose from the grid size)
   int pdl;                // launch with programmatic stream serialization
   int stages;             // filled by the launcher: depth of the weight ring
+  unsigned long long* sat_count;  // fp16 mode: += 1 per thread that had to clamp an output to +-65504 (or null)
   long long* prof;        // optional [ctas][16] time stamps of this launch (bring-up instrumentation), else null
 };
 

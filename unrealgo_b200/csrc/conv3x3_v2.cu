@@ -373,6 +373,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float hacc[HEADS > 0 ? HEADS : 1];
 #pragma unroll
       for (int h = 0; h < (HEADS > 0 ? HEADS : 1); ++h) hacc[h] = 0.f;
+      float out_max = 0.f;  // fp16 range watch: the largest |output| this thread converts in this tile
       for (int c0 = grp * kEpiCols; c0 < cout; c0 += 2 * kEpiCols) {
         uint32_t v[32];
         tmem_ld_32x32(t_row + c0, v);
@@ -423,6 +424,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             f0 = fmaxf(f0, act_floor);
             f1 = fmaxf(f1, act_floor);
+            if constexpr (F16 && HEADS == 0) out_max = fmaxf(out_max, fmaxf(fabsf(f0), fabsf(f1)));
             if constexpr (HEADS > 0) {
               // head weights [HEADS][cout] fp32: the same address in every lane (one L1 wavefront per load)
 #pragma unroll
@@ -466,6 +468,10 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             bulk_commit_group();
           }
         }
+      }
+      if constexpr (F16 && HEADS == 0) {
+        // cvt.satfinite clamped something: the evaluator is outside fp16's range (ug_net_info.saturation_events)
+        if (out_max > 65504.f && args.sat_count != nullptr) atomicAdd(args.sat_count, 1ull);
       }
       if constexpr (HEADS == 0) {
         // tile-granular mode: publish "this warp's share of the tile is in memory" (16 counts complete a tile)

@@ -35,6 +35,7 @@ struct ConvV2Args {
   int pdl;                // launch with programmatic stream serialization (overlap the prologue and the weight
                           // prefetch with the previous kernel's tail)
   int num_tiles;          // filled by the launcher
+  unsigned long long* sat_count;  // fp16 mode: += 1 per (thread, tile) that had to clamp an output to +-65504 (or null)
   long long* prof;        // optional [clusters][64] cycle counters, zeroed by the caller (bring-up instrumentation), else null
 };
 

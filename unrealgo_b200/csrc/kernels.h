@@ -47,6 +47,8 @@ void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* leg
 // fp32 validation tower (SIMT, direct convolution): in/out fp32 NHWC, weights HWIO [3][3][cin][cout]
 void launch_conv3x3_f32(const float* in, const float* w_hwio, const float* bias, const float* res, float* out,
                         int n, int cin, int cout, int relu, cudaStream_t s);
+// *slot = max(*slot, max |p[i]|) (slot zero-initialised by the caller; fp32 values, non-negative result)
+void launch_max_abs_f32(const float* p, size_t count, float* slot, cudaStream_t s);
 // bf16 <-> fp32 images for debug readback
 // out64[i] = (double)in[i] for the policy; value: widened, then value_transform applied in double exactly as the
 // reference does on the host (DlTensorUtil::GetValue + DlTFNetworkEvaluator.cc:300-310)

@@ -119,6 +119,12 @@ bool load_conv(const TfBundle& ck, const ConvPlan& p, int ksize, HostConv* out, 
   return true;
 }
 
+float max_abs(const std::vector<float>& v) {
+  float m = 0.f;
+  for (float x : v) { const float a = std::fabs(x); if (a > m || a != a) m = a; }
+  return m;
+}
+
 bool make_conv_layer(const HostConv& hc, int cin_pad, bool f16, ConvLayer* L, std::string* err) {
   L->cin = hc.cin;
   L->cin_pad = cin_pad;
@@ -171,14 +177,19 @@ Weights* build_weights(const NetPlan& plan, const TfBundle& ck, bool f16, std::s
     return nullptr;
   }
   W->C = C;
+  W->f16 = f16;
   W->blocks = (int)plan.tower.size() / 2;
   W->convs.resize(1 + plan.tower.size());
   if (!make_conv_layer(stem, kCinPad, f16, &W->convs[0], err)) return nullptr;
+  W->max_weight = max_abs(stem.w);
+  W->max_weight_layer = 0;
   for (size_t i = 0; i < plan.tower.size(); ++i) {
     HostConv hc;
     if (!load_conv(ck, plan.tower[i], 3, &hc, err)) return nullptr;
     if (hc.cin != C || hc.cout != C) { *err = "tower conv '" + plan.tower[i].kernel + "' is not C x C"; return nullptr; }
     if (!make_conv_layer(hc, C, f16, &W->convs[1 + i], err)) return nullptr;
+    const float mw = max_abs(hc.w);
+    if (mw > W->max_weight || mw != mw) { W->max_weight = mw; W->max_weight_layer = 1 + (int)i; }
   }
   HostConv pcv, vcv;
   if (!load_conv(ck, plan.policy_conv, 1, &pcv, err) || !load_conv(ck, plan.value_conv, 1, &vcv, err)) return nullptr;
@@ -211,6 +222,77 @@ Weights* build_weights(const NetPlan& plan, const TfBundle& ck, bool f16, std::s
   W->policy_softmax = plan.policy_softmax;
   W->value_tanh = plan.value_tanh;
   return W.release();
+}
+
+// Range calibration.  fp16 operands saturate at 65504 and the tower clamps instead of producing inf, so a checkpoint
+// whose activations (or folded weights w * gamma / sqrt(var + eps): a small variance makes them large) come near that
+// limit would evaluate *wrongly but plausibly*.  A few built-in positions (empty board to a full one, both colours to
+// move) run through the fp32 validation tower on the loaded weights; the largest |output| of every layer — exactly the
+// quantity the 16-bit epilogues convert — is recorded.  ~50 ms for 20x256, once per checkpoint load.
+constexpr int kCalibPositions = 4;
+
+void calibration_positions(ug_packed_pos* pos) {
+  memset(pos, 0, sizeof(ug_packed_pos) * kCalibPositions);
+  uint64_t rng = 0x9E3779B97F4A7C15ull;
+  auto next = [&rng] { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+  for (int p = 0; p < kCalibPositions; ++p) {
+    const int stones = p * 110;  // 0, 110, 220, 330 of 361 points
+    int order[UG_NUM_POINTS];
+    for (int i = 0; i < UG_NUM_POINTS; ++i) order[i] = i;
+    for (int i = UG_NUM_POINTS - 1; i > 0; --i) { const int j = (int)(next() % (uint64_t)(i + 1)); std::swap(order[i], order[j]); }
+    for (int k = 0; k < UG_HISTORY; ++k) {        // history step k: the last k stones not yet played
+      const int keep = stones - k > 0 ? stones - k : 0;
+      for (int i = 0; i < keep; ++i) {
+        uint32_t* m = (i & 1) ? pos[p].white[k] : pos[p].black[k];
+        m[order[i] >> 5] |= 1u << (order[i] & 31);
+      }
+    }
+    pos[p].to_play = (uint32_t)(stones & 1);
+  }
+}
+
+bool calibrate_range(ug_eval* h, Weights* W, std::string* err) {
+  const int n = kCalibPositions, C = W->C, layers = 1 + 2 * W->blocks;
+  const size_t act = (size_t)n * UG_NUM_POINTS * C;
+  DevBuf d_pos, d_in16, f_in, f_a, f_b, f_t, d_max;
+  if (!d_pos.alloc(n * sizeof(ug_packed_pos)) || !d_in16.alloc((size_t)n * UG_NUM_POINTS * kCinPad * 2) ||
+      !f_in.alloc((size_t)n * UG_NUM_POINTS * UG_NUM_PLANES * 4) || !f_a.alloc(act * 4) || !f_b.alloc(act * 4) ||
+      !f_t.alloc(act * 4) || !d_max.alloc((size_t)layers * 4)) {
+    *err = "out of device memory calibrating the activation range";
+    return false;
+  }
+  ug_packed_pos pos[kCalibPositions];
+  calibration_positions(pos);
+  cudaStream_t s = h->stream;
+  cudaMemcpyAsync(d_pos.p, pos, sizeof(pos), cudaMemcpyHostToDevice, s);
+  cudaMemsetAsync(d_max.p, 0, d_max.bytes, s);
+  launch_encode_packed_nhwc(d_pos.as<ug_packed_pos>(), d_in16.as<__nv_bfloat16>(), n, 0, s);
+  launch_nhwc_to_f32(d_in16.as<__nv_bfloat16>(), f_in.as<float>(), n, 0, s);
+  float* S[2] = {f_a.as<float>(), f_b.as<float>()};
+  float* mx = d_max.as<float>();
+  const ConvLayer& st = W->convs[0];
+  launch_conv3x3_f32(f_in.as<float>(), st.w_f32.as<float>(), st.bias.as<float>(), nullptr, S[0], n, UG_NUM_PLANES, C, 1, s);
+  launch_max_abs_f32(S[0], act, mx + 0, s);
+  for (int b = 0; b < W->blocks; ++b) {
+    const int x = b & 1, y = x ^ 1;
+    const ConvLayer& c1 = W->convs[1 + 2 * b];
+    const ConvLayer& c2 = W->convs[2 + 2 * b];
+    launch_conv3x3_f32(S[x], c1.w_f32.as<float>(), c1.bias.as<float>(), nullptr, f_t.as<float>(), n, C, C, 1, s);
+    launch_max_abs_f32(f_t.as<float>(), act, mx + 1 + 2 * b, s);
+    launch_conv3x3_f32(f_t.as<float>(), c2.w_f32.as<float>(), c2.bias.as<float>(), S[x], S[y], n, C, C, 1, s);
+    launch_max_abs_f32(S[y], act, mx + 2 + 2 * b, s);
+  }
+  std::vector<float> host((size_t)layers);
+  cudaMemcpyAsync(host.data(), d_max.p, (size_t)layers * 4, cudaMemcpyDeviceToHost, s);
+  const cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { *err = std::string("range calibration failed: ") + cudaGetErrorString(e); return false; }
+  W->max_activation = 0.f;
+  for (int l = 0; l < layers; ++l)
+    if (host[(size_t)l] > W->max_activation || host[(size_t)l] != host[(size_t)l]) {
+      W->max_activation = host[(size_t)l];
+      W->max_activation_layer = l;
+    }
+  return true;
 }
 
 bool ends_with(const std::string& s, const char* suf) {
@@ -259,7 +341,7 @@ bool ug_eval::ensure_workspace(int C) {
             d_in.alloc(nb * UG_NUM_POINTS * kCinPad * 2) && d_feat.alloc(nb * UG_NUM_POINTS * 8 * 4) &&
             d_policy.alloc(nb * UG_NUM_MOVES * 4) && d_value.alloc(nb * 4) &&
             d_policy64.alloc(nb * UG_NUM_MOVES * 8) && d_value64.alloc(nb * 8) &&
-            d_flags.alloc(2 * ((nb * UG_NUM_POINTS + 255) / 256) * sizeof(uint32_t));
+            d_flags.alloc(2 * ((nb * UG_NUM_POINTS + 255) / 256) * sizeof(uint32_t)) && d_sat.alloc(16);
   for (int i = 0; i < 2 && ok; ++i) ok = d_s_hi[i].alloc(act_elems * 2) && d_s_lo[i].alloc(act_elems * 2);
   ok = ok && d_t.alloc(act_elems * 2);
   if (ok && precision == UG_PREC_FP32) {
@@ -267,6 +349,7 @@ bool ug_eval::ensure_workspace(int C) {
     for (int i = 0; i < 2 && ok; ++i) ok = f_s[i].alloc(act_elems * 4);
   }
   if (!ok) { last_error = "out of device memory allocating the workspace"; return false; }
+  cudaMemset(d_sat.p, 0, d_sat.bytes);
   // zero once so that rows past n (read by the tail tile) are finite
   cudaMemset(d_in.p, 0, d_in.bytes);
   for (int i = 0; i < 2; ++i) { cudaMemset(d_s_hi[i].p, 0, d_s_hi[i].bytes); cudaMemset(d_s_lo[i].p, 0, d_s_lo[i].bytes); }
@@ -406,6 +489,7 @@ int ug_eval::enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, con
   a.f16 = precision == UG_PREC_FP16;
   a.cout = C;
   a.pdl = use_pdl ? 1 : 0;
+  a.sat_count = d_sat.as<unsigned long long>();
   // Tile-granular dependencies need the overlap that programmatic launch provides; counters restart every pass.
   const bool deps = tile_deps && use_pdl;
   const size_t tiles_alloc = ((size_t)max_batch * UG_NUM_POINTS + 255) / 256;
@@ -488,6 +572,7 @@ int ug_eval::enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, con
   a.f16 = precision == UG_PREC_FP16;
   a.cout = C;
   a.pdl = use_pdl ? 1 : 0;
+  a.sat_count = d_sat.as<unsigned long long>();
   a.nt = sb_nt;
   a.cin = kCinPad;
   a.bias = W.convs[0].bias.as<float>();
@@ -522,6 +607,7 @@ int ug_eval::enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, con
       v.f16 = a.f16;
       v.cin = v.cout = C;
       v.pdl = a.pdl;
+      v.sat_count = a.sat_count;
       v.bias = c2.bias.as<float>();
       v.has_res = 1;
       v.has_res_lo = v.has_out_lo = split;
@@ -631,7 +717,9 @@ ug_eval* ug_eval_create(int device, int precision, int max_batch) {
   }
   ug_eval* h = new ug_eval();
   h->device = device;
-  h->precision = precision;
+  h->precision = h->precision_requested = precision;
+  if (const char* fr = getenv("UGEVAL_FP16_RANGE"))
+    h->fp16_policy = !strcmp(fr, "refuse") ? 1 : (!strcmp(fr, "ignore") ? 2 : 0);
   h->max_batch = max_batch;
   h->sms = prop.multiProcessorCount;
   const char* ng = getenv("UGEVAL_NO_GRAPH");
@@ -716,8 +804,35 @@ int ug_eval_load_checkpoint(ug_eval* h, const char* prefix) {
   std::string err;
   TfBundle ck;
   if (!ck.open(h->ckpt_prefix, &err)) return h->fail(1, err);
-  Weights* W = build_weights(h->plan, ck, h->precision == UG_PREC_FP16, &err);
+  int precision = h->precision_requested;
+  Weights* W = build_weights(h->plan, ck, precision == UG_PREC_FP16, &err);
   if (!W) return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err);
+  if (!calibrate_range(h, W, &err)) { delete W; return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err); }
+  {
+    const float worst = W->max_activation > W->max_weight ? W->max_activation : W->max_weight;
+    const bool nan = worst != worst;
+    if (nan) { delete W; return h->fail(1, "checkpoint " + h->ckpt_prefix + ": weights or calibration activations are NaN"); }
+    if (precision == UG_PREC_FP16 && worst > 65504.f / 8 && h->fp16_policy != 2) {
+      char msg[512];
+      snprintf(msg, sizeof(msg), "checkpoint %s leaves fp16 less than 8x headroom (largest |activation| %.4g after layer %d, "
+               "largest |folded weight| %.4g in layer %d, fp16 saturates at 65504)", h->ckpt_prefix.c_str(),
+               (double)W->max_activation, W->max_activation_layer, (double)W->max_weight, W->max_weight_layer);
+      if (h->fp16_policy == 1) { delete W; return h->fail(1, std::string(msg) + ": refused (UGEVAL_FP16_RANGE=refuse)"); }
+      fprintf(stderr, "ugeval: %s: evaluating with bf16 operands instead\n", msg);
+      const float ma = W->max_activation, mw = W->max_weight;
+      const int la = W->max_activation_layer, lw = W->max_weight_layer;
+      delete W;
+      precision = UG_PREC_BF16;
+      W = build_weights(h->plan, ck, false, &err);
+      if (!W) return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err);
+      W->max_activation = ma; W->max_weight = mw; W->max_activation_layer = la; W->max_weight_layer = lw;
+    }
+  }
+  if (precision != h->precision) {  // 16-bit formats share every buffer; the format is a run-time flag of the kernels
+    cudaStreamSynchronize(h->stream);
+    h->drop_graphs();
+    h->precision = precision;
+  }
   if (!h->ensure_workspace(W->C)) {
     delete W;
     if (h->weights && h->weights->C != h->ws_C) {  // the old network's workspace did not survive the attempt
@@ -780,6 +895,12 @@ int ug_eval_set_residual_split(ug_eval* h, int on) {
   return 0;
 }
 
+int ug_eval_set_fp16_range_policy(ug_eval* h, int policy) {
+  if (!h || policy < 0 || policy > 2) return -1;
+  h->fp16_policy = policy;
+  return 0;
+}
+
 int ug_eval_set_small_batch(ug_eval* h, int max_batch, int nt) {
   if (!h || max_batch < 0 || (nt != 0 && nt != 16 && nt != 32 && nt != 64 && nt != 128)) return -1;
   h->sb_max_batch = max_batch;
@@ -803,6 +924,18 @@ int ug_eval_info(const ug_eval* h, ug_net_info* out) {
   out->sm_count = h->sms;
   out->conv_impl = (h->conv_impl == 2 && W.C % 64 == 0) ? 2 : 1;
   out->small_batch_max = out->conv_impl == 2 ? h->sb_max_batch : 0;
+  out->precision = h->precision;
+  out->calib_max_activation = W.max_activation;
+  out->calib_max_weight = W.max_weight;
+  const float worst = W.max_activation > W.max_weight ? W.max_activation : W.max_weight;
+  out->fp16_headroom = worst > 0 ? 65504.f / worst : 0.f;
+  out->saturation_events = 0;
+  if (h->d_sat.p) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    unsigned long long v = 0;
+    if (cudaMemcpy(&v, h->d_sat.p, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) out->saturation_events = v;
+  }
   return 0;
 }
 

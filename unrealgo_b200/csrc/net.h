@@ -45,6 +45,11 @@ struct ConvLayer {
 
 struct Weights {
   int blocks = 0, C = 0, pc = 0, vc = 0, H = 0;
+  bool f16 = false;              // operand format the conv weights were packed in
+  // range calibration (ug_eval_load_checkpoint): the largest |folded weight| of any tower layer, and the largest
+  // |layer output| seen when a few calibration positions run through the fp32 validation tower
+  float max_weight = 0.f, max_activation = 0.f;
+  int max_activation_layer = -1, max_weight_layer = -1;
   bool policy_softmax = true, value_tanh = true;
   std::vector<ConvLayer> convs;  // [0] stem, then 2 per block
   DevBuf head_conv_w, head_conv_b, pfc_w, pfc_b, v1_w, v1_b, v2_w, v2_b;
@@ -55,7 +60,13 @@ struct Weights {
 
 struct ug_eval {
   int device = 0;
-  int precision = UG_PREC_BF16;
+  int precision = UG_PREC_BF16;            // arithmetic in use
+  int precision_requested = UG_PREC_BF16;  // what ug_eval_create asked for (a checkpoint outside fp16's range can
+                                           // move an fp16 evaluator to bf16: fp16_policy)
+  // fp16 operands saturate at 65504.  0 = fall back to bf16 when a checkpoint's calibrated range leaves less than 8x
+  // headroom (default), 1 = refuse the checkpoint, 2 = load anyway (ug_net_info.saturation_events then tells).
+  // UGEVAL_FP16_RANGE=bf16|refuse|ignore
+  int fp16_policy = 0;
   int max_batch = 0;
   int sms = 148;
   int conv_ctas = 2;
@@ -91,6 +102,7 @@ struct ug_eval {
   // workspace (allocated once the architecture is known)
   int ws_C = 0;
   ug::DevBuf d_pos, d_legal, d_planes, d_in, d_feat, d_policy, d_value, d_bytes;
+  ug::DevBuf d_sat;    // one 64-bit counter: outputs clamped to fp16's range by the tower epilogues
   ug::DevBuf d_flags;  // [2][tiles] per-tile completion counters of the tower layers (tile-granular dependencies)
   ug::DevBuf d_policy64, d_value64;  // double images of the outputs for registered (pinned) caller buffers
   std::vector<std::pair<uintptr_t, size_t>> host_regs;  // caller buffers registered with ug_eval_register_host

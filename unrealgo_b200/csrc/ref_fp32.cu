@@ -37,7 +37,29 @@ __global__ void __launch_bounds__(256) conv3x3_f32_kernel(const float* __restric
   out[idx] = acc;
 }
 
+// range calibration: the largest magnitude in a tensor (non-negative floats order like their bit patterns)
+__global__ void __launch_bounds__(256) max_abs_f32_kernel(const float* __restrict__ p, size_t count, float* slot) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(p[i]);
+    m = (v > m || v != v) ? v : m;   // a NaN wins, so that it is seen
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = (t > m || t != t) ? t : m;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(m));
+}
+
 }  // namespace
+
+void launch_max_abs_f32(const float* p, size_t count, float* slot, cudaStream_t s) {
+  if (count == 0) return;
+  unsigned grid = (unsigned)((count + 255) / 256);
+  if (grid > 1184) grid = 1184;
+  max_abs_f32_kernel<<<grid, 256, 0, s>>>(p, count, slot);
+}
 
 void launch_conv3x3_f32(const float* in, const float* w_hwio, const float* bias, const float* res, float* out,
                         int n, int cin, int cout, int relu, cudaStream_t s) {

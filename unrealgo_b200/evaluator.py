@@ -147,6 +147,11 @@ class DlTFNetworkEvaluator:
         if self._lib.ug_eval_set_conv_impl(self._h, impl) != 0:
             raise ValueError("impl must be 1 or 2")
 
+    def set_fp16_range_policy(self, policy):
+        """0 = fall back to bf16 for a checkpoint outside fp16's range (default), 1 = refuse it, 2 = load it anyway"""
+        if self._lib.ug_eval_set_fp16_range_policy(self._h, {"bf16": 0, "refuse": 1, "ignore": 2}.get(policy, policy)) != 0:
+            raise ValueError("policy: 0/'bf16', 1/'refuse', 2/'ignore'")
+
     def set_small_batch(self, max_batch, nt=0):
         """batches <= max_batch run the small-batch tower kernel (0 disables); nt = output channels per CTA (0 = auto)"""
         if self._lib.ug_eval_set_small_batch(self._h, max_batch, nt) != 0:
