@@ -21,9 +21,10 @@ struct ConvV2Args {
   int relu;
   int f16;                // operands/outputs are fp16 (else bf16)
   int has_res, has_res_lo, has_out_lo;
-  int desc_mode;          // bring-up knobs: bit 0 set the descriptor's matrix-base-offset field for shifted A tiles;
-                          // bit 1 unmasked MMA form, bit 2 no tap shift, bit 4 no weight reloads after the first lap
-                          // (all three give wrong results: timing probes)
+  int desc_mode;          // bring-up knob: bit 4 = no weight reloads after the first lap of the ring (wrong results: a
+                          // timing probe for the weight traffic).  Bits 0-2 (descriptor base offset / unmasked MMAs /
+                          // no tap shift) were probes of the first bring-up and are ignored since the issue loop was
+                          // unrolled.
   // Tile-granular dependencies between consecutive layers (all null/0: whole-grid dependency through
   // griddepcontrol.wait).  Counters are per 256-row tile, +16 when a layer has stored the tile (one count per epilogue
   // warp of the CTA pair), zeroed by the caller at the start of every pass through the tower.
