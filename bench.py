@@ -242,6 +242,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # one process per GPU: give every rank its own slice of the host CPUs (search threads, gather and completion
+    # threads inherit it) so that ranks do not migrate over each other's caches
+    affinity = None
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cpus) >= world:
+            per = len(cpus) // world
+            affinity = cpus[local * per:(local + 1) * per]
+            os.sched_setaffinity(0, affinity)
+    except (AttributeError, OSError):
+        affinity = None
     if world > 1:
         import datetime
         # a rank that dies must not leave the others in a 10-minute collective timeout
@@ -506,7 +517,8 @@ def main():
     # round-1 sample; 200: late middle game): host cost per playout and tree shape depend on the stage of the game.
     sp = None
     if not args.no_selfplay:
-        threads = args.sp_threads or max(2, min(12, (os.cpu_count() or 8) // max(world, 1)))
+        ncpu = len(affinity) if affinity else (os.cpu_count() or 8) // max(world, 1)
+        threads = args.sp_threads or max(2, min(12, ncpu))
         legs = {}
         for k in [int(x) for x in args.sp_preludes.split(",") if x.strip() != ""]:
             if world > 1:
@@ -520,13 +532,19 @@ def main():
             evals, _ = shard.reduce_throughput(st["evaluations"], st["seconds"], device="cuda")
             legs[str(k)] = {"playouts_per_s": playouts / sp_secs, "evaluations_per_s": evals / sp_secs,
                             "seconds": sp_secs, "moves_per_game_sampled": moves, "mean_batch_rank0": st["mean_batch"],
-                            "flush_timeouts_rank0": st["flush_timeouts"], "mean_tree_nodes_rank0": st["mean_tree_nodes"]}
+                            "flush_timeouts_rank0": st["flush_timeouts"], "mean_tree_nodes_rank0": st["mean_tree_nodes"],
+                            "search_busy_fraction_rank0": st["search_busy_fraction"],
+                            "host_us_per_playout_rank0": st["host_us_per_playout"],
+                            "batches_rank0": st["batches"], "full_batches_rank0": st["full_batches"],
+                            "wave_cut_batches_rank0": st["wave_cut_batches"],
+                            "max_queue_depth_rank0": st["max_queue_depth"], "gather_sleeps_rank0": st["gather_sleeps"]}
         head = legs[str(int(args.sp_preludes.split(",")[0]))]
         sp = dict(head)
         sp.update({"unit": "playouts/s", "sample": f"headline: games started after {args.sp_preludes.split(',')[0]} random "
                                                   "legal moves (middle game); by_random_prelude_moves lists every sample",
                    "by_random_prelude_moves": legs,
                    "games_per_gpu": args.sp_games, "search_threads_per_gpu": threads, "host_cpus": os.cpu_count(),
+                   "cpu_affinity_rank0": affinity,
                    "leaf_batch_cap": SP_BATCH, "playouts_per_move": args.sp_playouts, "reuse_searchtree": True,
                    "sharding": "independent games per GPU, weights replicated, no collective"})
         # one game alone (GTP-style use): one leaf in flight vs the reference's virtual-loss multi-thread search

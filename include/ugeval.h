@@ -219,6 +219,14 @@ int ug_queue_wait(ug_queue* q, int64_t ticket, float* policy, float* value);
 int ug_queue_poll(ug_queue* q, int64_t ticket, float* policy, float* value);
 /* counters: batches run, leaves evaluated, flushes caused by the timeout */
 int ug_queue_stats(ug_queue* q, uint64_t* batches, uint64_t* leaves, uint64_t* flush_timeouts);
+/* Compact priors (UctSearch::UpdatePrior search/UctSearch.cpp:1257-1270): with on != 0 a leaf that
+ * was submitted with a legal mask gets back only its #legal renormalised priors, in ascending move-index order (the
+ * order GenerateLegalMoves emits children, pass last), in policy[0 .. #legal): the head kernel packs them and the
+ * device-to-host copy shrinks from 362 floats per leaf to the widest row of the batch.  Set before submitting. */
+int ug_queue_set_compact_priors(ug_queue* q, int on);
+/* out[0..count): batches, leaves, timeout flushes, full batches, batches cut back to whole kernel waves, failed batches,
+ * deepest submission queue seen at a batch start, times the gather thread went to sleep */
+int ug_queue_stats_ex(ug_queue* q, uint64_t* out, int count);
 /* pause the consumer, swap the checkpoint, resume (hot swap between searches, search/UctSearch.cpp:178-182) */
 int ug_queue_swap_checkpoint(ug_queue* q, const char* prefix);
 
@@ -261,6 +269,10 @@ typedef struct ug_selfplay_config {
 typedef struct ug_selfplay_stats {
   uint64_t playouts, evaluations, batches, flush_timeouts, moves, games_finished, terminal_leaves;
   double seconds, playouts_per_s, mean_batch, mean_tree_nodes;
+  /* where the host side stands: share of the search threads' time spent searching (the rest: asleep, waiting for
+   * evaluations), search-thread microseconds per playout, and the leaf queue's batch bookkeeping */
+  double search_busy_fraction, host_us_per_playout;
+  uint64_t full_batches, wave_cut_batches, max_queue_depth, gather_sleeps;
 } ug_selfplay_stats;
 /* moves_out (optional): [games][(max_moves or 722) + prelude_moves] policy indices (361 = pass), the prelude's moves
  * first; n_moves_out: [games] */

@@ -13,7 +13,7 @@
 #include "stub_eval.h"
 
 struct StubSlot { ug_packed_pos pos; uint32_t legal[UG_MASK_WORDS]; };
-struct ug_queue { std::mutex mu; std::vector<StubSlot*> slots; std::vector<int64_t> free_ids; };
+struct ug_queue { std::mutex mu; std::vector<StubSlot*> slots; std::vector<int64_t> free_ids; bool compact = false; };
 
 extern "C" {
 ug_queue* ug_queue_create(ug_eval*, int, int, int) { return new ug_queue(); }
@@ -55,10 +55,17 @@ int ug_queue_poll(ug_queue* q, int64_t ticket, float* policy, float* value) {
     sum += policy[i];
   }
   for (int i = 0; i < UG_NUM_MOVES; ++i) policy[i] /= sum;
+  if (q->compact) {  // only the legal priors, ascending move order (ug_queue_set_compact_priors)
+    int k = 0;
+    for (int i = 0; i < UG_NUM_MOVES; ++i)
+      if ((s.legal[i >> 5] >> (i & 31)) & 1u) policy[k++] = policy[i];
+  }
   return 1;
 }
 int ug_queue_wait(ug_queue* q, int64_t t, float* p, float* v) { return ug_queue_poll(q, t, p, v) == 1 ? 0 : -1; }
 int ug_queue_stats(ug_queue*, uint64_t* a, uint64_t* b, uint64_t* c) { *a = *b = *c = 0; return 0; }
 int ug_queue_swap_checkpoint(ug_queue*, const char*) { return 0; }
+int ug_queue_set_compact_priors(ug_queue* q, int on) { q->compact = on != 0; return 0; }
+int ug_queue_stats_ex(ug_queue*, uint64_t* out, int n) { for (int i = 0; i < n; ++i) out[i] = 0; return 0; }
 }
 #endif

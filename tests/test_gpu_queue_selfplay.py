@@ -199,3 +199,50 @@ def test_selfplay_virtual_loss_leaves_fill_batches_from_few_games(small_ckpt):
         for mv in g:
             assert b.is_legal(mv), (g, mv)
             b.play(mv)
+
+
+def test_compact_priors_are_the_legal_entries_in_move_order(small_ckpt):
+    """SURVEY 8(f) row 1, second half: the queue ships #legal priors per leaf instead of 362 floats.  Same numbers as the
+    dense rows at the legal indices, in ascending move order (pass last); a leaf without a mask still gets 362."""
+    import oracle
+    from unrealgo_b200 import LeafQueue
+    packed, _ = oracle.synthetic_positions(48, seed=8)
+    rng = np.random.default_rng(3)
+    legal = np.zeros((48, 12), np.uint32)
+    idx = []
+    for i in range(48):
+        k = int(rng.integers(1, 362))
+        moves = np.sort(rng.permutation(362)[:k])
+        idx.append(moves)
+        np.bitwise_or.at(legal[i], moves >> 5, (np.uint32(1) << (moves & 31).astype(np.uint32)))
+    ev = _ev(small_ckpt)
+    dense_p, dense_v = ev.evaluate_packed(packed, legal)
+    plain_p, _ = ev.evaluate_packed(packed[:1])
+    q = LeafQueue(ev, max_batch=32, timeout_us=300)
+    q.set_compact_priors(True)
+    tickets = [q.submit(packed[i], legal[i]) for i in range(48)] + [q.submit(packed[0])]
+    for i in range(48):
+        pol, val = q.wait(tickets[i])
+        k = len(idx[i])
+        assert np.array_equal(pol[:k], dense_p[i][idx[i]]) and val == dense_v[i], i
+        assert abs(float(pol[:k].sum()) - 1) < 1e-5
+    pol, _ = q.wait(tickets[48])                       # no mask: the dense softmax row
+    assert np.array_equal(pol, plain_p[0])
+    st = q.stats_ex()
+    assert st["leaves"] == 49 and st["failed_batches"] == 0
+    q.close()
+    ev.close()
+
+
+def test_waiting_on_a_consumed_ticket_returns_instead_of_hanging(small_ckpt):
+    import oracle
+    from unrealgo_b200 import LeafQueue
+    packed, _ = oracle.synthetic_positions(2, seed=8)
+    ev = _ev(small_ckpt)
+    q = LeafQueue(ev, max_batch=8, timeout_us=100)
+    t = q.submit(packed[0])
+    q.wait(t)
+    with pytest.raises(RuntimeError):
+        q.wait(t)                                      # consumed: reported, not waited for
+    q.close()
+    ev.close()

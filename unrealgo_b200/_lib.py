@@ -51,7 +51,10 @@ class SelfplayStats(C.Structure):
     _fields_ = [("playouts", C.c_uint64), ("evaluations", C.c_uint64), ("batches", C.c_uint64),
                 ("flush_timeouts", C.c_uint64), ("moves", C.c_uint64), ("games_finished", C.c_uint64),
                 ("terminal_leaves", C.c_uint64), ("seconds", C.c_double), ("playouts_per_s", C.c_double),
-                ("mean_batch", C.c_double), ("mean_tree_nodes", C.c_double)]
+                ("mean_batch", C.c_double), ("mean_tree_nodes", C.c_double),
+                ("search_busy_fraction", C.c_double), ("host_us_per_playout", C.c_double),
+                ("full_batches", C.c_uint64), ("wave_cut_batches", C.c_uint64), ("max_queue_depth", C.c_uint64),
+                ("gather_sleeps", C.c_uint64)]
 
 
 class BenchResult(C.Structure):
@@ -119,6 +122,8 @@ SIGNATURES = {
     "ug_pack_planes": (None, [C.c_void_p, C.c_void_p]),
     "ug_queue_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ug_queue_swap_checkpoint": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "ug_queue_set_compact_priors": (C.c_int, [C.c_void_p, C.c_int]),
+    "ug_queue_stats_ex": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
     "ug_tfrecord_open": (C.c_void_p, [C.c_char_p]),
     "ug_tfrecord_write_example": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_float]),
     "ug_tfrecord_write_example_named": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_char_p, C.c_void_p,

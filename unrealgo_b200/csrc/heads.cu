@@ -30,6 +30,13 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// compact priors: position of move j among the set bits of the legal mask (ascending move order)
+__device__ __forceinline__ int legal_rank(const uint32_t* __restrict__ lm, int j) {
+  int r = 0;
+  const int w = j >> 5;
+  for (int i = 0; i < w; ++i) r += __popc(__ldg(lm + i));
+  return r + __popc(__ldg(lm + w) & ((1u << (j & 31)) - 1u));
+}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -181,7 +188,7 @@ __device__ __forceinline__ void fc_column(const float* __restrict__ wcol, int st
 __global__ void __launch_bounds__(kFcThreads) head_fc_kernel(const float* __restrict__ feat, HeadWeights hw,
                                                              const uint32_t* __restrict__ legal, int vt,
                                                              float* __restrict__ policy,
-                                                             float* __restrict__ value, int n) {
+                                                             float* __restrict__ value, int n, int compact) {
   extern __shared__ float sm[];
   const int pc = hw.pc, vc = hw.vc, hc = pc + vc, H = hw.H;
   const int pin = kPoints * pc, vin = kPoints * vc;
@@ -257,6 +264,10 @@ __global__ void __launch_bounds__(kFcThreads) head_fc_kernel(const float* __rest
       const bool ok = pol && ((__ldg(lm + (j >> 5)) >> (j & 31)) & 1u);
       const float lsum = block_reduce(ok ? prob : 0.f, false, scratch);
       prob = ok ? prob / lsum : 0.f;
+      if (compact) {  // only the legal priors, packed in ascending move order
+        if (ok) policy[(size_t)(p0 + p) * kMoves + legal_rank(lm, j)] = prob;
+        continue;
+      }
     }
     if (pol) policy[(size_t)(p0 + p) * kMoves + j] = prob;
   }
@@ -341,7 +352,7 @@ __device__ __forceinline__ void fc_column8(const float* __restrict__ wcol, int s
 
 __global__ void __cluster_dims__(kClu, 1, 1) __launch_bounds__(kCluThreads)
 head_fc_cluster_kernel(const float* __restrict__ feat, HeadWeights hw, const uint32_t* __restrict__ legal, int vt,
-                       float* __restrict__ policy, float* __restrict__ value, int n) {
+                       float* __restrict__ policy, float* __restrict__ value, int n, int compact) {
   extern __shared__ float sm[];
   const int pc = hw.pc, vc = hw.vc, hc = pc + vc, H = hw.H;
   const int pin = kPoints * pc, vin = kPoints * vc;
@@ -521,7 +532,12 @@ head_fc_cluster_kernel(const float* __restrict__ feat, HeadWeights hw, const uin
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const int c = lane + 32 * k;
-        if (c < ncol) policy[(size_t)(p0 + p) * kMoves + c0 + c] = e_keep[k] / lt;
+        if (c < ncol) {
+          if (!compact) policy[(size_t)(p0 + p) * kMoves + c0 + c] = e_keep[k] / lt;
+          else if (e_keep[k] != 0.f || ((__ldg(legal + (size_t)(p0 + p) * UG_MASK_WORDS + ((c0 + c) >> 5)) >> ((c0 + c) & 31)) & 1u))
+            // legal moves only (an exponential can underflow to 0: ask the mask, not the value), packed in ascending order
+            policy[(size_t)(p0 + p) * kMoves + legal_rank(legal + (size_t)(p0 + p) * UG_MASK_WORDS, c0 + c)] = e_keep[k] / lt;
+        }
       }
     }
   }
@@ -568,8 +584,9 @@ static bool use_cluster_fc() {
 }
 
 void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* legal, int vt, float* policy,
-                    float* value, int n, cudaStream_t s) {
+                    float* value, int n, cudaStream_t s, int compact) {
   if (n <= 0) return;
+  if (legal == nullptr) compact = 0;
   const int hper = (w.H + kClu - 1) / kClu;
   if (use_cluster_fc() && hper <= 96 && w.pc + w.vc <= kMaxHeadCh) {
     const int pstr = (kPoints * w.pc + 3) & ~3, vstr = (kPoints * w.vc + 3) & ~3;
@@ -584,7 +601,7 @@ void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* leg
       set_c[dev & 63] = smem;
     }
     const int clusters = (n + kCluPos - 1) / kCluPos;
-    head_fc_cluster_kernel<<<clusters * kClu, kCluThreads, smem, s>>>(feat, w, legal, vt, policy, value, n);
+    head_fc_cluster_kernel<<<clusters * kClu, kCluThreads, smem, s>>>(feat, w, legal, vt, policy, value, n, compact);
     return;
   }
   const size_t smem =
@@ -598,7 +615,7 @@ void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* leg
     set = smem;
   }
   const int grid = (n + kPosPerCta - 1) / kPosPerCta;
-  head_fc_kernel<<<grid, kFcThreads, smem, s>>>(feat, w, legal, vt, policy, value, n);
+  head_fc_kernel<<<grid, kFcThreads, smem, s>>>(feat, w, legal, vt, policy, value, n, compact);
 }
 
 }  // namespace ug

@@ -41,8 +41,9 @@ struct HeadWeights {
 // NHWC [n][361][C]
 void launch_head_conv(const void* act, const void* act_lo, int act_fmt /*0 bf16, 1 fp32, 2 fp16*/, const HeadWeights& w, float* feat, int n, cudaStream_t s);
 // K5-K7 stage 2: FC + softmax (optionally renormalised over a legal mask) and FC-ReLU-FC-tanh-value_transform
+// compact (with a legal mask only): row p holds just its legal priors, packed in ascending move order
 void launch_head_fc(const float* feat, const HeadWeights& w, const uint32_t* legal, int vt, float* policy,
-                    float* value, int n, cudaStream_t s);
+                    float* value, int n, cudaStream_t s, int compact = 0);
 
 // fp32 validation tower (SIMT, direct convolution): in/out fp32 NHWC, weights HWIO [3][3][cin][cout]
 void launch_conv3x3_f32(const float* in, const float* w_hwio, const float* bias, const float* res, float* out,

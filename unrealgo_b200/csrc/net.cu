@@ -638,41 +638,41 @@ int ug_eval::enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, con
 }
 
 int ug_eval::enqueue_heads(const void* act, const void* act_lo, int n, const uint32_t* d_leg, int vt, float* d_pol,
-                           float* d_val, cudaStream_t s) {
+                           float* d_val, cudaStream_t s, bool compact) {
   const HeadWeights hw = weights->head();
   if (act != nullptr)  // null: the tower's last layer already produced d_feat (fused head convolutions)
     launch_head_conv(act, act_lo, precision == UG_PREC_FP32 ? 1 : (precision == UG_PREC_FP16 ? 2 : 0), hw,
                      d_feat.as<float>(), n, s);
-  launch_head_fc(d_feat.as<float>(), hw, d_leg, vt, d_pol, d_val, n, s);
+  launch_head_fc(d_feat.as<float>(), hw, d_leg, vt, d_pol, d_val, n, s, compact ? 1 : 0);
   return cudaGetLastError() == cudaSuccess ? 0 : fail(-1, "head kernel launch failed");
 }
 
 int ug_eval::enqueue_raw(Src kind, const void* d_src, int n, const uint32_t* d_leg, int vt, float* d_pol,
-                         float* d_val, cudaStream_t s) {
+                         float* d_val, cudaStream_t s, bool compact) {
   int rc = enqueue_encoder(kind, d_src, n, s);
   if (rc) return rc;
   const void* act = nullptr;
   const void* act_lo = nullptr;
   rc = enqueue_tower(n, s, &act, &act_lo);
   if (rc) return rc;
-  return enqueue_heads(act, act_lo, n, d_leg, vt, d_pol, d_val, s);
+  return enqueue_heads(act, act_lo, n, d_leg, vt, d_pol, d_val, s, compact);
 }
 
 int ug_eval::enqueue(Src kind, const void* d_src, int n, const uint32_t* d_leg, int vt, float* d_pol,
-                     float* d_val, cudaStream_t s) {
+                     float* d_val, cudaStream_t s, bool compact) {
   if (!weights) return fail(-1, "no network loaded (LoadGraph + UpdateCheckPoint first)");
   if (n <= 0 || n > max_batch) return fail(-1, "batch size " + std::to_string(n) + " outside [1, max_batch]");
-  if (!use_graphs) return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
+  if (!use_graphs) return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s, compact);
   const GraphKey key((int)kind, n, d_src, (const void*)d_leg, (const void*)d_pol, (const void*)d_val, vt,
                      conv_ctas * 4 + precision + (resid_split ? 8192 : 0) + conv_impl * 16384 + (use_pdl ? 65536 : 0) + (fuse_heads ? 131072 : 0) + (tile_deps ? 262144 : 0) + (debug_stop + 1) * 16 +
-                         (use_small_batch(n) ? (1 << 19) + (sb_nt << 20) : 0));
+                         (use_small_batch(n) ? (1 << 19) + (sb_nt << 20) : 0) + (compact ? (1 << 28) : 0));
   auto it = graphs.find(key);
   if (it == graphs.end()) {
     if (graphs.size() > 1024) drop_graphs();
     cudaGraph_t g = nullptr;
     if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
-      return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
-    const int rc = enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s);
+      return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s, compact);
+    const int rc = enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s, compact);
     const cudaError_t ee = cudaStreamEndCapture(s, &g);
     if (rc != 0 || ee != cudaSuccess || !g) {
       if (g) cudaGraphDestroy(g);

@@ -128,14 +128,15 @@ struct ug_eval {
   // source kinds for enqueue()
   enum Src { SRC_PACKED = 0, SRC_CHW = 1, SRC_HWC = 2 };
   // enqueue encoder + tower + heads on `s`; all pointers are device pointers
+  // compact: with a legal mask, policy rows hold only the legal priors packed in ascending move order (leaf queue)
   int enqueue(Src kind, const void* d_src, int n, const uint32_t* d_legal, int vt, float* d_policy,
-              float* d_value, cudaStream_t s);
+              float* d_value, cudaStream_t s, bool compact = false);
   int enqueue_raw(Src kind, const void* d_src, int n, const uint32_t* d_legal, int vt, float* d_policy,
-                  float* d_value, cudaStream_t s);
+                  float* d_value, cudaStream_t s, bool compact = false);
   int enqueue_encoder(Src kind, const void* d_src, int n, cudaStream_t s);
   int enqueue_tower(int n, cudaStream_t s, const void** final_act, const void** final_lo);
   int enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, const void** final_lo);
   int enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, const void** final_lo);
   int enqueue_heads(const void* act, const void* act_lo, int n, const uint32_t* d_legal, int vt, float* d_policy, float* d_value,
-                    cudaStream_t s);
+                    cudaStream_t s, bool compact = false);
 };

@@ -40,6 +40,7 @@ struct Slot {
   ug_packed_pos pos;
   uint32_t legal[UG_MASK_WORDS];
   uint32_t has_legal;
+  uint32_t n_out;                   // floats of `policy` that carry the result: #legal in compact mode, else 362
   float policy[UG_NUM_MOVES];
   float value;
   int failed;                       // the batch this leaf rode in did not run: policy/value are not results
@@ -60,6 +61,7 @@ struct Staging {
   int n = 0;
   bool any_legal = false;
   bool busy = false;
+  int max_out = UG_NUM_MOVES;        // widest result row of the batch (compact priors: max #legal)
   int rc = 0;                        // evaluator return code of this batch (failures belong to a batch, not the queue)
 };
 
@@ -87,6 +89,22 @@ struct ug_queue {
   std::deque<int> inflight;         // staging indices in submission order
   std::atomic<bool> quit{false};
   bool pause_req = false, paused = false;
+  // compact priors: a leaf submitted with a legal mask gets back its #legal priors in ascending
+  // move order instead of a 362-float row with zeros — the head kernel packs them, the D2H copy and the two host copies
+  // shrink to the widest row of the batch
+  std::atomic<bool> compact{false};
+  // the gather thread sleeps instead of spinning while it waits for leaves (4 CPUs per GPU on the 8-GPU boxes): a
+  // producer wakes it when the queue holds what it is waiting for
+  std::mutex mu_g;
+  std::condition_variable cv_g;
+  std::atomic<bool> sleeping{false};
+  std::atomic<uint64_t> wake_at{0};
+  std::atomic<uint64_t> n_full{0}, n_wave_cut{0}, n_sleeps{0}, max_depth{0};
+  uint64_t depth() const {
+    const uint64_t e = submitted.enq.load(std::memory_order_acquire), d = submitted.deq.load(std::memory_order_acquire);
+    return e > d ? e - d : 0;
+  }
+  void wait_for_leaves(uint64_t want, std::chrono::steady_clock::time_point deadline);
   std::atomic<uint64_t> n_batches{0}, n_leaves{0}, n_timeouts{0}, n_failed{0};
   std::atomic<int> error{0};        // set only by a CUDA (context-wide) error: closes the queue
 
@@ -94,9 +112,25 @@ struct ug_queue {
   void complete_loop();
 };
 
+void ug_queue::wait_for_leaves(uint64_t want, std::chrono::steady_clock::time_point deadline) {
+  for (int i = 0; i < 128; ++i) {  // leaves arrive in bursts: a short spin first
+    if (depth() >= want) return;
+    cpu_relax();
+  }
+  std::unique_lock<std::mutex> lk(mu_g);
+  wake_at.store(want, std::memory_order_relaxed);
+  sleeping.store(true, std::memory_order_seq_cst);
+  if (depth() < want && !quit.load(std::memory_order_acquire)) {
+    n_sleeps.fetch_add(1, std::memory_order_relaxed);
+    cv_g.wait_until(lk, deadline);  // a missed wake-up costs at most the time to the deadline
+  }
+  sleeping.store(false, std::memory_order_relaxed);
+}
+
 void ug_queue::gather_loop() {
   cudaSetDevice(eval->device);
   int which = 0;
+  using clock = std::chrono::steady_clock;
   while (!quit.load(std::memory_order_acquire)) {
     {
       std::unique_lock<std::mutex> lk(mu);
@@ -109,13 +143,11 @@ void ug_queue::gather_loop() {
         continue;
       }
     }
-    // wait for the first published leaf
+    // wait for the first published leaf (re-checking pause/quit every millisecond)
     if (carry.empty()) {
       uint32_t id;
-      bool got = submitted.pop(&id);
-      for (int i = 0; i < 64 && !got; ++i) { cpu_relax(); got = submitted.pop(&id); }
-      if (!got) {
-        std::this_thread::sleep_for(std::chrono::microseconds(5));
+      if (!submitted.pop(&id)) {
+        wait_for_leaves(1, clock::now() + std::chrono::milliseconds(1));
         continue;
       }
       carry.push_back(id);
@@ -128,7 +160,12 @@ void ug_queue::gather_loop() {
       if (quit.load()) break;
       S.busy = true;
     }
-    const auto t0 = std::chrono::steady_clock::now();
+    const auto deadline = clock::now() + std::chrono::microseconds(timeout_us);
+    {
+      const uint64_t d = depth() + carry.size();
+      uint64_t m = max_depth.load(std::memory_order_relaxed);
+      while (d > m && !max_depth.compare_exchange_weak(m, d, std::memory_order_relaxed)) {}
+    }
     int n = 0;
     bool timed_out = false;
     S.any_legal = false;
@@ -138,9 +175,8 @@ void ug_queue::gather_loop() {
       uint32_t id;
       if (from_carry < carry.size()) id = carry[from_carry++];
       else if (!submitted.pop(&id)) {
-        const auto dt = std::chrono::steady_clock::now() - t0;
-        if (std::chrono::duration_cast<std::chrono::microseconds>(dt).count() >= timeout_us) { timed_out = true; break; }
-        cpu_relax();
+        if (clock::now() >= deadline) { timed_out = true; break; }
+        wait_for_leaves((uint64_t)(max_batch - n), deadline);  // sleeps until the rest of the batch is there
         continue;
       }
       S.ids.push_back(id);
@@ -151,10 +187,15 @@ void ug_queue::gather_loop() {
       n_timeouts.fetch_add(1, std::memory_order_relaxed);
       // a partial batch is cut back to whole waves of the tower kernel; the leaves beyond open the next batch
       const int keep = ug_eval_efficient_batch(eval, n);
+      if (keep < n) n_wave_cut.fetch_add(1, std::memory_order_relaxed);
       carry.insert(carry.begin(), S.ids.begin() + keep, S.ids.end());
       S.ids.resize((size_t)keep);
       n = keep;
+    } else {
+      n_full.fetch_add(1, std::memory_order_relaxed);
     }
+    const bool cmp = compact.load(std::memory_order_relaxed);
+    int max_out = cmp ? 1 : UG_NUM_MOVES;
     for (int i = 0; i < n; ++i) {
       const Slot& sl = slots[S.ids[(size_t)i]];
       memcpy(&S.h_pos[i], &sl.pos, sizeof(ug_packed_pos));
@@ -164,8 +205,10 @@ void ug_queue::gather_loop() {
       } else {
         memset(&S.h_legal[(size_t)i * UG_MASK_WORDS], 0xff, sizeof(sl.legal));
       }
+      if ((int)sl.n_out > max_out) max_out = (int)sl.n_out;
     }
     S.n = n;
+    S.max_out = max_out;
     // H2D on the copy-in stream, tower on the evaluator stream, D2H on the copy-out stream
     cudaMemcpyAsync(S.d_pos, S.h_pos, (size_t)n * sizeof(ug_packed_pos), cudaMemcpyHostToDevice, s_in);
     if (S.any_legal)
@@ -177,15 +220,19 @@ void ug_queue::gather_loop() {
     // staging buffer instead of 256.
     int n_run = (n + 7) & ~7;
     if (n_run > max_batch) n_run = max_batch;
-    const int rc = ug_eval_run_packed_device(eval, S.d_pos, n_run, S.any_legal ? S.d_legal : nullptr, S.d_policy,
-                                             S.d_value, eval->stream);
+    int rc;
+    if (!eval->weights) rc = eval->fail(-1, "no network loaded");
+    else rc = eval->enqueue(ug_eval::SRC_PACKED, S.d_pos, n_run, S.any_legal ? S.d_legal : nullptr, eval->value_transform,
+                            S.d_policy, S.d_value, eval->stream, cmp && S.any_legal);
     S.rc = rc;
     if (rc != 0 && n_failed.fetch_add(1, std::memory_order_relaxed) == 0)
       fprintf(stderr, "ugeval queue: evaluator failure %d on a batch of %d: %s\n", rc, n_run, ug_last_error(eval));
     cudaEventRecord(S.ev_done, eval->stream);
     cudaStreamWaitEvent(s_out, S.ev_done, 0);
-    cudaMemcpyAsync(S.h_out, S.d_policy, (size_t)n * UG_NUM_MOVES * 4, cudaMemcpyDeviceToHost, s_out);
-    cudaMemcpyAsync(S.h_out + (size_t)n * UG_NUM_MOVES, S.d_value, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out);
+    // policy rows: only the first max_out floats of each (all 362 unless the priors are compact)
+    cudaMemcpy2DAsync(S.h_out, (size_t)UG_NUM_MOVES * 4, S.d_policy, (size_t)UG_NUM_MOVES * 4, (size_t)max_out * 4, (size_t)n,
+                      cudaMemcpyDeviceToHost, s_out);
+    cudaMemcpyAsync(S.h_out + (size_t)max_batch * UG_NUM_MOVES, S.d_value, (size_t)n * 4, cudaMemcpyDeviceToHost, s_out);
     cudaEventRecord(S.ev_out, s_out);
     {
       std::lock_guard<std::mutex> lk(mu);
@@ -217,8 +264,8 @@ void ug_queue::complete_loop() {
     for (int i = 0; i < S.n; ++i) {
       Slot& sl = slots[S.ids[(size_t)i]];
       if (!failed) {
-        memcpy(sl.policy, S.h_out + (size_t)i * UG_NUM_MOVES, sizeof(sl.policy));
-        sl.value = S.h_out[(size_t)S.n * UG_NUM_MOVES + i];
+        memcpy(sl.policy, S.h_out + (size_t)i * UG_NUM_MOVES, (size_t)sl.n_out * 4);
+        sl.value = S.h_out[(size_t)max_batch * UG_NUM_MOVES + i];
       }
       sl.failed = failed;
       sl.state.store(SLOT_READY, std::memory_order_release);
@@ -294,6 +341,7 @@ void ug_queue_destroy(ug_queue* q) {
   }
   q->cv_free.notify_all();
   q->cv_pause.notify_all();
+  { std::lock_guard<std::mutex> lk(q->mu_g); q->cv_g.notify_all(); }
   if (q->gather_thread.joinable()) q->gather_thread.join();
   q->cv_inflight.notify_all();
   if (q->complete_thread.joinable()) q->complete_thread.join();
@@ -329,11 +377,23 @@ int64_t ug_queue_submit(ug_queue* q, const ug_packed_pos* pos, const uint32_t* l
   Slot& sl = q->slots[id];
   memcpy(&sl.pos, pos, sizeof(ug_packed_pos));
   sl.has_legal = legal ? 1u : 0u;
-  if (legal) memcpy(sl.legal, legal, sizeof(sl.legal));
+  sl.n_out = UG_NUM_MOVES;
+  if (legal) {
+    memcpy(sl.legal, legal, sizeof(sl.legal));
+    if (q->compact.load(std::memory_order_relaxed)) {
+      uint32_t c = 0;
+      for (int w = 0; w < UG_MASK_WORDS; ++w) c += (uint32_t)__builtin_popcount(w == UG_MASK_WORDS - 1 ? legal[w] & 0x3ffu : legal[w]);
+      sl.n_out = c;   // bits 0..361 only: word 11 holds moves 352..361
+    }
+  }
   const uint64_t ticket = (++sl.allocs << kIdBits) | id;
   sl.ticket.store(ticket, std::memory_order_relaxed);
   sl.state.store(SLOT_QUEUED, std::memory_order_release);
   q->submitted.push(id);  // cannot be full: at most `capacity` ids exist
+  if (q->sleeping.load(std::memory_order_seq_cst) && q->depth() >= q->wake_at.load(std::memory_order_relaxed)) {
+    std::lock_guard<std::mutex> lk(q->mu_g);
+    q->cv_g.notify_one();
+  }
   return (int64_t)ticket;
 }
 
@@ -353,7 +413,7 @@ static inline bool ready(const Slot& sl, int64_t ticket) {
 static inline int take(ug_queue* q, Slot& sl, int64_t ticket, float* policy, float* value) {
   const int failed = sl.failed;
   if (!failed) {
-    if (policy) memcpy(policy, sl.policy, sizeof(sl.policy));
+    if (policy) memcpy(policy, sl.policy, (size_t)sl.n_out * 4);
     if (value) *value = sl.value;
   }
   sl.ticket.store(0, std::memory_order_relaxed);
@@ -390,6 +450,20 @@ int ug_queue_stats(ug_queue* q, uint64_t* batches, uint64_t* leaves, uint64_t* f
   if (batches) *batches = q->n_batches.load();
   if (leaves) *leaves = q->n_leaves.load();
   if (flush_timeouts) *flush_timeouts = q->n_timeouts.load();
+  return 0;
+}
+
+int ug_queue_set_compact_priors(ug_queue* q, int on) {
+  if (!q) return -1;
+  q->compact.store(on != 0, std::memory_order_relaxed);
+  return 0;
+}
+
+int ug_queue_stats_ex(ug_queue* q, uint64_t* out, int count) {
+  if (!q || !out) return -1;
+  const uint64_t v[8] = {q->n_batches.load(), q->n_leaves.load(), q->n_timeouts.load(), q->n_full.load(),
+                         q->n_wave_cut.load(), q->n_failed.load(), q->max_depth.load(), q->n_sleeps.load()};
+  for (int i = 0; i < count && i < 8; ++i) out[i] = v[i];
   return 0;
 }
 

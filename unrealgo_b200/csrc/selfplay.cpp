@@ -94,6 +94,7 @@ struct Shared {
   ug_selfplay_config cfg;
   std::atomic<uint64_t> playouts{0}, moves{0}, games_done{0}, nodes{0}, terminal_leaves{0};
   std::atomic<uint64_t> record_errors{0};
+  std::atomic<uint64_t> idle_ns{0};   // search threads: time asleep because no evaluation had come back
   std::atomic<bool> stop{false};
 };
 
@@ -321,8 +322,9 @@ bool start_playout(Game& g, Shared& sh) {
 void finish_playout(Game& g, uint32_t leaf, float value) {
   Tree& t = g.tree;
   const uint32_t base = t.first_child[leaf], nc = t.n_children[leaf];
-  for (uint32_t i = 0; i < nc; ++i)
-    t.prior[base + i] = g.policy[t.move[base + i]];  // already renormalised over the legal children on the GPU
+  // compact priors: the queue returns exactly the children's priors, renormalised over the legal set on the GPU, in
+  // ascending move order with pass last — the order generate_moves created the children in
+  memcpy(&t.prior[base], g.policy, (size_t)nc * sizeof(float));
   uint32_t cur = leaf;
   float v = value;
   for (;;) {  // BackupTree, search/UctSearch.cpp:1282-1295
@@ -424,7 +426,12 @@ void worker(std::vector<Game>& games, size_t lo, size_t hi, Shared& sh) {
       if (g.finished) --live;
       progressed = true;
     }
-    if (!progressed) std::this_thread::sleep_for(std::chrono::microseconds(20));
+    if (!progressed) {
+      const auto t0 = std::chrono::steady_clock::now();
+      std::this_thread::sleep_for(std::chrono::microseconds(20));
+      sh.idle_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                               std::chrono::steady_clock::now() - t0).count(), std::memory_order_relaxed);
+    }
   }
 }
 
@@ -445,6 +452,7 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
   sh.cfg = cfg;
   sh.q = ug_queue_create(h, cfg.max_batch, cfg.timeout_us > 0 ? cfg.timeout_us : 200, 4 * cfg.games * (cfg.leaves_per_game > 1 ? cfg.leaves_per_game : 1) + 1024);
   if (!sh.q) return -2;
+  ug_queue_set_compact_priors(sh.q, 1);
   std::vector<Game> games((size_t)cfg.games);
   {
     // Tree storage: one expansion per playout, up to 362 children each, plus the subtree carried over by tree
@@ -529,6 +537,8 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   uint64_t batches = 0, leaves = 0, timeouts = 0;
   ug_queue_stats(sh.q, &batches, &leaves, &timeouts);
+  uint64_t qx[8] = {0};
+  ug_queue_stats_ex(sh.q, qx, 8);
   ug_queue_destroy(sh.q);
   stats->playouts = sh.playouts.load();
   stats->evaluations = leaves;
@@ -541,6 +551,16 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
   stats->playouts_per_s = secs > 0 ? (double)stats->playouts / secs : 0;
   stats->mean_batch = batches ? (double)leaves / (double)batches : 0;
   stats->mean_tree_nodes = stats->moves ? (double)sh.nodes.load() / (double)stats->moves : 0;
+  {
+    const double thread_secs = secs * (double)threads.size();
+    const double idle = (double)sh.idle_ns.load() * 1e-9;
+    stats->search_busy_fraction = thread_secs > 0 ? 1.0 - idle / thread_secs : 0;
+    stats->host_us_per_playout = stats->playouts ? (thread_secs - idle) * 1e6 / (double)stats->playouts : 0;
+    stats->full_batches = qx[3];
+    stats->wave_cut_batches = qx[4];
+    stats->max_queue_depth = qx[6];
+    stats->gather_sleeps = qx[7];
+  }
   if (moves_out && n_moves_out) {
     const int cap = (cfg.max_moves > 0 ? cfg.max_moves : 2 * 19 * 19) + cfg.prelude_moves;  // row length of moves_out
     for (int i = 0; i < cfg.games; ++i) {

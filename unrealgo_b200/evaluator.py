@@ -357,6 +357,17 @@ class LeafQueue:
     def swap_checkpoint(self, prefix):
         return self._lib.ug_queue_swap_checkpoint(self._q, prefix.encode()) == 0
 
+    def set_compact_priors(self, on=True):
+        """leaves submitted with a legal mask get back only their #legal priors, packed in ascending move order"""
+        self._lib.ug_queue_set_compact_priors(self._q, 1 if on else 0)
+
+    def stats_ex(self):
+        out = (C.c_uint64 * 8)()
+        self._lib.ug_queue_stats_ex(self._q, out, 8)
+        names = ("batches", "leaves", "flush_timeouts", "full_batches", "wave_cut_batches", "failed_batches",
+                 "max_queue_depth", "gather_sleeps")
+        return dict(zip(names, (int(v) for v in out)))
+
 
 class ProductBoard:
     """test hook over the self-play driver's incremental board (csrc/goboard.h)"""
