@@ -572,10 +572,14 @@ cudaError_t dispatch_v2(const ConvV2Maps& m, const ConvV2Args& a, int sms, cudaS
   const int res = a.has_res ? (a.has_res_lo ? 2 : 1) : 0;
   const bool lo = a.has_out_lo != 0;
   if (a.head_out != nullptr) {
-    // fused heads: only the shapes the tower's last layer takes (64-channel chunks, 3 head channels)
+    // fused heads: only the shapes the tower's last layer takes (64-channel chunks, 3 or 4 head channels: the exchange
+    // buffer between the two epilogue warp groups holds 4 floats per row)
     if constexpr (CK == 64) {
       if (a.head_channels == 3 && res == 2 && lo) return launch_v2<CK, F16, 2, true, 3>(m, a, sms, stream);
       if (a.head_channels == 3 && res == 1 && !lo) return launch_v2<CK, F16, 1, false, 3>(m, a, sms, stream);
+      // 2 policy + 2 value channels (a two-channel value head)
+      if (a.head_channels == 4 && res == 2 && lo) return launch_v2<CK, F16, 2, true, 4>(m, a, sms, stream);
+      if (a.head_channels == 4 && res == 1 && !lo) return launch_v2<CK, F16, 1, false, 4>(m, a, sms, stream);
     }
     return cudaErrorInvalidValue;
   }
@@ -614,7 +618,7 @@ int conv3x3_v2_max_active_clusters(int cluster_size) {
 }
 
 bool conv3x3_v2_can_fuse_heads(int ck, int has_res, int has_res_lo, int has_out_lo, int head_channels) {
-  if (ck != 64 || head_channels != 3 || !has_res) return false;
+  if (ck != 64 || (head_channels != 3 && head_channels != 4) || !has_res) return false;
   return (has_res_lo && has_out_lo) || (!has_res_lo && !has_out_lo);
 }
 
