@@ -395,7 +395,7 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6500.0)
     traffic = None
     try:  # DRAM bytes per launch from the committed ncu capture (mean of the two tower-conv variants)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["tower_conv_mean"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["tower_conv_mean"]
     except Exception:
         pass
 
@@ -408,7 +408,7 @@ def main():
                 "flops_per_launch": conv_flops, "ms_per_launch": br["ms_conv"], "launches_per_step": conv_launches,
                 "ms_tower_conv_per_step": br["ms_conv"] * conv_launches, "traffic": traffic,
                 "traffic_note": "DRAM read+write bytes per launch, mean of the two tower-conv variants, from "
-                                "profiles/r01_traffic.json (ncu --set full, cold L2); tensor-bound kernel"}
+                                "profiles/r02_traffic.json (ncu --set full, cold L2); tensor-bound kernel"}
 
     def hbm_line(kernel, batch, ms, bytes_per_pos, note):
         gbs = batch * bytes_per_pos / (ms * 1e-3) / 1e9

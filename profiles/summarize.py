@@ -3,11 +3,14 @@
 under profiles/, and an ncu launch list (--metrics gpu__time_duration.sum --csv) into a per-kernel share table.
 
   python profiles/summarize.py rep  gpurun_out/prof.ncu-rep        profiles/rNN_name_ncu_full_subset.csv
-  python profiles/summarize.py list gpurun_out/launches.csv        profiles/rNN_name_launch_shares.csv
+  python profiles/summarize.py list gpurun_out/launches.csv        profiles/rNN_name_launch_shares.csv [exclude-regex]
+(exclude-regex: kernels that are not part of a step — the load-time range calibration, torch's own fill/compare
+kernels — are listed with their times but left out of the share column)
 """
 import collections
 import csv
 import io
+import re
 import subprocess
 import sys
 
@@ -42,22 +45,23 @@ def rep(path, out):
     print(f"{out}: {len(data)} launches x {len(idx)} metrics")
 
 
-def launch_list(path, out):
+def launch_list(path, out, exclude=None):
     rows = [r for r in csv.reader(open(path)) if len(r) > 5]
     hdr = rows[0]
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
     agg = collections.OrderedDict()
     for r in rows[1:]:
         agg.setdefault(r[ki].split("(")[0], []).append(float(r[vi].replace(",", "")))
-    tot = sum(sum(v) for v in agg.values())
+    skip = re.compile(exclude) if exclude else None
+    tot = sum(sum(v) for k, v in agg.items() if not (skip and skip.search(k)))
     with open(out, "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["kernel", "launches", "mean_us", "min_us", "max_us", "share_of_listed_time_pct"])
         for k, v in agg.items():
-            w.writerow([k, len(v), f"{sum(v) / len(v) / 1e3:.2f}", f"{min(v) / 1e3:.2f}", f"{max(v) / 1e3:.2f}",
-                        f"{100 * sum(v) / tot:.2f}"])
+            share = "excluded" if (skip and skip.search(k)) else f"{100 * sum(v) / tot:.2f}"
+            w.writerow([k, len(v), f"{sum(v) / len(v) / 1e3:.2f}", f"{min(v) / 1e3:.2f}", f"{max(v) / 1e3:.2f}", share])
     print(f"{out}: {len(agg)} kernels, {sum(len(v) for v in agg.values())} launches")
 
 
 if __name__ == "__main__":
-    {"rep": rep, "list": launch_list}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"rep": rep, "list": launch_list}[sys.argv[1]](*sys.argv[2:])
