@@ -114,6 +114,7 @@ def test_leaf_queue_patch_applies_to_the_reference_tree(tmp_path):
     header = open(os.path.join(ROOT, "include", "ugeval.h")).read()
     added = [ln[1:] for ln in open(patch).read().splitlines() if ln.startswith("+") and not ln.startswith("+++")]
     used = set(re.findall(r"\b(ug_[a-z_]+)\s*\(", "\n".join(added)))
-    assert used == {"ug_pack_planes", "ug_queue_submit", "ug_queue_wait", "ug_queue_create", "ug_queue_swap_checkpoint"}
+    assert used == {"ug_pack_planes", "ug_queue_submit", "ug_queue_wait", "ug_queue_create", "ug_queue_swap_checkpoint",
+                    "ug_eval_set_value_transform"}   # dlcfg value_transform: Evaluate() read it per call, the queue bypasses it
     for s in used:
         assert re.search(r"\b%s\s*\(" % s, header), s
