@@ -534,6 +534,7 @@ def main():
                             "seconds": sp_secs, "moves_per_game_sampled": moves, "mean_batch_rank0": st["mean_batch"],
                             "flush_timeouts_rank0": st["flush_timeouts"], "mean_tree_nodes_rank0": st["mean_tree_nodes"],
                             "search_busy_fraction_rank0": st["search_busy_fraction"],
+                            "gpu_busy_fraction_rank0": st["gpu_busy_fraction"],
                             "host_us_per_playout_rank0": st["host_us_per_playout"],
                             "batches_rank0": st["batches"], "full_batches_rank0": st["full_batches"],
                             "wave_cut_batches_rank0": st["wave_cut_batches"],

@@ -225,7 +225,8 @@ int ug_queue_stats(ug_queue* q, uint64_t* batches, uint64_t* leaves, uint64_t* f
  * device-to-host copy shrinks from 362 floats per leaf to the widest row of the batch.  Set before submitting. */
 int ug_queue_set_compact_priors(ug_queue* q, int on);
 /* out[0..count): batches, leaves, timeout flushes, full batches, batches cut back to whole kernel waves, failed batches,
- * deepest submission queue seen at a batch start, times the gather thread went to sleep */
+ * deepest submission queue seen at a batch start, times the gather thread went to sleep, microseconds the evaluator
+ * stream spent on batches (CUDA events around every batch: device busy time) */
 int ug_queue_stats_ex(ug_queue* q, uint64_t* out, int count);
 /* pause the consumer, swap the checkpoint, resume (hot swap between searches, search/UctSearch.cpp:178-182) */
 int ug_queue_swap_checkpoint(ug_queue* q, const char* prefix);
@@ -273,6 +274,7 @@ typedef struct ug_selfplay_stats {
    * evaluations), search-thread microseconds per playout, and the leaf queue's batch bookkeeping */
   double search_busy_fraction, host_us_per_playout;
   uint64_t full_batches, wave_cut_batches, max_queue_depth, gather_sleeps;
+  double gpu_busy_fraction;   /* share of the run the evaluator stream was working on a batch */
 } ug_selfplay_stats;
 /* moves_out (optional): [games][(max_moves or 722) + prelude_moves] policy indices (361 = pass), the prelude's moves
  * first; n_moves_out: [games] */

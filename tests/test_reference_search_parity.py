@@ -86,7 +86,7 @@ def test_product_search_matches_the_reference_engine(tools, playouts, moves, reu
     (UctTreeUtil::ExtractSubtree, as UctDeepPlayer::FindInitTree does), the product with reuse_tree=1"""
     _write_cfg(tools, reuse)
     got_moves, got_visits = _product(tools, playouts, moves, reuse)
-    for attempt in range(4):  # the stub's wait-for-settled-inputs is a heuristic (see ugeval_stub.c): retry under load
+    for attempt in range(6):  # the stub's wait-for-settled-inputs is a heuristic (see ugeval_stub.c): retry under load
         ref_moves, ref_root, _ = _reference(tools, playouts, moves, UGSTUB_SYNC="1",
                                             UGSTUB_SETTLE_US=str(250 * (attempt + 1)))
         if ref_moves == got_moves:
@@ -109,7 +109,7 @@ def test_a_whole_game_through_the_endgame(tools):
     _write_cfg(tools, True)
     got_moves, _ = _product(tools, 40, 700, True)
     assert got_moves[-2:] == [361, 361] and len(got_moves) > 300
-    for attempt in range(4):
+    for attempt in range(6):
         cwd, stub, _ = tools
         e = dict(os.environ, LD_PRELOAD=stub, UGSTUB_SYNC="1", UGSTUB_SETTLE_US=str(250 * (attempt + 1)))
         r = subprocess.run([REF_SEARCH, "40", "700"], cwd=cwd, env=e, capture_output=True, text=True, timeout=600)
@@ -221,7 +221,7 @@ def test_live_reference_player_writes_the_same_records(tools, recorder):
     cwd, stub, _ = tools
     _write_cfg(tools, True)
     got = _product_game(recorder, 4)
-    for attempt in range(4):
+    for attempt in range(6):
         out = os.path.join(cwd, f"ref_game_{attempt}.tfrecords")
         e = dict(os.environ, LD_PRELOAD=stub, UGSTUB_SYNC="1", UGSTUB_SETTLE_US=str(150 * (attempt + 1)))
         r = subprocess.run([REF_SELFPLAY, "4", out], cwd=cwd, env=e, capture_output=True, text=True, timeout=300)

@@ -57,6 +57,7 @@ struct Staging {
   float* d_policy = nullptr;
   float* d_value = nullptr;
   cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+  cudaEvent_t ev_t0 = nullptr;       // timing pair with ev_done: how long the evaluator stream worked on this batch
   std::vector<uint32_t> ids;         // slot id of every leaf in the batch
   int n = 0;
   bool any_legal = false;
@@ -99,7 +100,7 @@ struct ug_queue {
   std::condition_variable cv_g;
   std::atomic<bool> sleeping{false};
   std::atomic<uint64_t> wake_at{0};
-  std::atomic<uint64_t> n_full{0}, n_wave_cut{0}, n_sleeps{0}, max_depth{0};
+  std::atomic<uint64_t> n_full{0}, n_wave_cut{0}, n_sleeps{0}, max_depth{0}, gpu_busy_us{0};
   uint64_t depth() const {
     const uint64_t e = submitted.enq.load(std::memory_order_acquire), d = submitted.deq.load(std::memory_order_acquire);
     return e > d ? e - d : 0;
@@ -221,6 +222,7 @@ void ug_queue::gather_loop() {
     int n_run = (n + 7) & ~7;
     if (n_run > max_batch) n_run = max_batch;
     int rc;
+    cudaEventRecord(S.ev_t0, eval->stream);
     if (!eval->weights) rc = eval->fail(-1, "no network loaded");
     else rc = eval->enqueue(ug_eval::SRC_PACKED, S.d_pos, n_run, S.any_legal ? S.d_legal : nullptr, eval->value_transform,
                             S.d_policy, S.d_value, eval->stream, cmp && S.any_legal);
@@ -261,6 +263,10 @@ void ug_queue::complete_loop() {
     if (ce != cudaSuccess && error.exchange(-1) == 0)
       fprintf(stderr, "ugeval queue: CUDA error while waiting for a batch: %s\n", cudaGetErrorString(ce));
     const int failed = (S.rc != 0 || ce != cudaSuccess) ? 1 : 0;
+    if (!failed) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, S.ev_t0, S.ev_done) == cudaSuccess) gpu_busy_us.fetch_add((uint64_t)(ms * 1e3f));
+    }
     for (int i = 0; i < S.n; ++i) {
       Slot& sl = slots[S.ids[(size_t)i]];
       if (!failed) {
@@ -312,7 +318,7 @@ ug_queue* ug_queue_create(ug_eval* h, int max_batch, int timeout_us, int capacit
          cudaMalloc((void**)&S.d_policy, nb * UG_NUM_MOVES * 4) == cudaSuccess &&
          cudaMalloc((void**)&S.d_value, nb * 4) == cudaSuccess &&
          cudaEventCreateWithFlags(&S.ev_in, cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreate(&S.ev_done) == cudaSuccess && cudaEventCreate(&S.ev_t0) == cudaSuccess &&
          // the completion thread sleeps on this one instead of spinning a core away (4 CPUs per GPU on 8-GPU boxes)
          cudaEventCreateWithFlags(&S.ev_out, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
   }
@@ -358,6 +364,7 @@ void ug_queue_destroy(ug_queue* q) {
     if (S.d_value) cudaFree(S.d_value);
     if (S.ev_in) cudaEventDestroy(S.ev_in);
     if (S.ev_done) cudaEventDestroy(S.ev_done);
+    if (S.ev_t0) cudaEventDestroy(S.ev_t0);
     if (S.ev_out) cudaEventDestroy(S.ev_out);
   }
   if (q->s_in) cudaStreamDestroy(q->s_in);
@@ -461,9 +468,10 @@ int ug_queue_set_compact_priors(ug_queue* q, int on) {
 
 int ug_queue_stats_ex(ug_queue* q, uint64_t* out, int count) {
   if (!q || !out) return -1;
-  const uint64_t v[8] = {q->n_batches.load(), q->n_leaves.load(), q->n_timeouts.load(), q->n_full.load(),
-                         q->n_wave_cut.load(), q->n_failed.load(), q->max_depth.load(), q->n_sleeps.load()};
-  for (int i = 0; i < count && i < 8; ++i) out[i] = v[i];
+  const uint64_t v[9] = {q->n_batches.load(), q->n_leaves.load(), q->n_timeouts.load(), q->n_full.load(),
+                         q->n_wave_cut.load(), q->n_failed.load(), q->max_depth.load(), q->n_sleeps.load(),
+                         q->gpu_busy_us.load()};
+  for (int i = 0; i < count && i < 9; ++i) out[i] = v[i];
   return 0;
 }
 

@@ -61,6 +61,13 @@ struct Tree {
     n_children.swap(o.n_children); move.swap(o.move);
     vloss.swap(o.vloss);
   }
+  void assign_from(const Tree& o) {
+    prior.assign(o.prior.begin(), o.prior.end()); w.assign(o.w.begin(), o.w.end());
+    visits.assign(o.visits.begin(), o.visits.end()); first_child.assign(o.first_child.begin(), o.first_child.end());
+    parent.assign(o.parent.begin(), o.parent.end()); n_children.assign(o.n_children.begin(), o.n_children.end());
+    move.assign(o.move.begin(), o.move.end());
+    if (use_vloss) vloss.assign(o.vloss.begin(), o.vloss.end());
+  }
   void copy_node(size_t dst, const Tree& src, size_t s) {
     prior[dst] = src.prior[s]; w[dst] = src.w[s]; visits[dst] = src.visits[s]; first_child[dst] = src.first_child[s];
     parent[dst] = src.parent[s]; n_children[dst] = src.n_children[s]; move[dst] = src.move[s];
@@ -288,7 +295,10 @@ void reuse_subtree(Game& g, uint32_t child) {
       map_src.push_back(sbase + i);
     }
   }
-  src.swap(dst);
+  // Copy the kept subtree back into the game's big arrays instead of swapping the vectors: the tree keeps the storage
+  // that was sized and prefaulted for a full move (a swap would leave it in the half-sized scratch arrays, which then
+  // regrow — a fresh 17 MB mapping and its page faults — in the middle of the next search, for every game and move).
+  src.assign_from(dst);
 }
 
 // RemoveVirtualLoss on every node of a finished descent (:847-850): from the leaf up to the root
@@ -562,8 +572,8 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   uint64_t batches = 0, leaves = 0, timeouts = 0;
   ug_queue_stats(sh.q, &batches, &leaves, &timeouts);
-  uint64_t qx[8] = {0};
-  ug_queue_stats_ex(sh.q, qx, 8);
+  uint64_t qx[9] = {0};
+  ug_queue_stats_ex(sh.q, qx, 9);
   ug_queue_destroy(sh.q);
   stats->playouts = sh.playouts.load();
   stats->evaluations = leaves;
@@ -585,6 +595,7 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
     stats->wave_cut_batches = qx[4];
     stats->max_queue_depth = qx[6];
     stats->gather_sleeps = qx[7];
+    stats->gpu_busy_fraction = secs > 0 ? (double)qx[8] * 1e-6 / secs : 0;
   }
   if (moves_out && n_moves_out) {
     const int cap = (cfg.max_moves > 0 ? cfg.max_moves : 2 * 19 * 19) + cfg.prelude_moves;  // row length of moves_out

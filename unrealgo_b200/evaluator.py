@@ -362,10 +362,10 @@ class LeafQueue:
         self._lib.ug_queue_set_compact_priors(self._q, 1 if on else 0)
 
     def stats_ex(self):
-        out = (C.c_uint64 * 8)()
-        self._lib.ug_queue_stats_ex(self._q, out, 8)
+        out = (C.c_uint64 * 9)()
+        self._lib.ug_queue_stats_ex(self._q, out, 9)
         names = ("batches", "leaves", "flush_timeouts", "full_batches", "wave_cut_batches", "failed_batches",
-                 "max_queue_depth", "gather_sleeps")
+                 "max_queue_depth", "gather_sleeps", "gpu_busy_us")
         return dict(zip(names, (int(v) for v in out)))
 
 
