@@ -123,7 +123,9 @@ def test_config5_40x256_batch512(agz40):
     want_p, want_v = GraphOracle(*agz40).evaluate_reference(planes[sub])
     dp, dv = np.abs(p[sub] - want_p).max(), np.abs(v[sub] - want_v).max()
     print(f"40x256 batch 512 (fp16): max|dpolicy|={dp:.3e} max|dvalue|={dv:.3e}")
-    assert dp <= 2e-3 and dv <= 1e-2  # twice the 20-block budget: twice the depth
+    # north_star's tolerance is stated for the 20-block bootstrap net; this one is twice as deep: value budget doubled
+    # (measured 3e-6 / 7e-3)
+    assert dp <= 1e-3 and dv <= 1e-2
     ev.close()
 
 
