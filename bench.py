@@ -550,8 +550,9 @@ def main():
                    "sharding": "independent games per GPU, weights replicated, no collective"})
         # one game alone (GTP-style use): one leaf in flight vs the reference's virtual-loss multi-thread search
         try:
-            s1, _ = selfplay(ev, games=1, threads=1, playouts_per_move=400, max_moves=2, max_batch=SP_BATCH,
-                             timeout_us=300, reuse_tree=True, prelude_moves=80, seed=77, leaves_per_game=1)
+            # one leaf in flight: nothing to batch, so no flush window (timeout 0): the rate is 1 / evaluation latency
+            s1, _ = selfplay(ev, games=1, threads=1, playouts_per_move=800, max_moves=2, max_batch=SP_BATCH,
+                             timeout_us=-1, reuse_tree=True, prelude_moves=80, seed=77, leaves_per_game=1)
             s64, _ = selfplay(ev, games=1, threads=1, playouts_per_move=args.sp_playouts, max_moves=3,
                               max_batch=SP_BATCH, timeout_us=300, reuse_tree=True, prelude_moves=80, seed=77,
                               leaves_per_game=64)

@@ -241,7 +241,8 @@ typedef struct ug_selfplay_config {
   int playouts_per_move;   /* MAX_SEARCH_ITERATIONS is 4000 in the reference (search/UctDeepPlayer.cpp:15) */
   int max_moves;           /* per game; 0 = 722 (m_maxGameLength, search/UctDeepPlayer.cpp:30) */
   int max_batch;           /* leaf-queue batch cap (<= evaluator max_batch) */
-  int timeout_us;          /* leaf-queue flush timeout */
+  int timeout_us;          /* leaf-queue flush timeout; 0 = 200 us, < 0 = none (a single game with one leaf in flight:
+                            * nothing to batch, every microsecond of the window is latency per playout) */
   int reuse_tree;          /* dlcfg reuse_searchtree */
   int random_opening_moves;/* harness option: first k moves uniformly random (0 = reference behaviour) */
   float puct;              /* 0 = 2.5 (search/UctSearch.cpp:370) */

@@ -114,7 +114,11 @@ struct ug_queue {
 };
 
 void ug_queue::wait_for_leaves(uint64_t want, std::chrono::steady_clock::time_point deadline) {
-  for (int i = 0; i < 128; ++i) {  // leaves arrive in bursts: a short spin first
+  // leaves arrive in bursts: a short spin first.  With timeout_us == 0 the caller asked for latency, not batching (a
+  // single search thread waiting for every evaluation): spin for ~100 us before giving the CPU away, a sleeping
+  // thread costs a wake-up of 50 us and more per leaf
+  const int spins = timeout_us == 0 ? 40000 : 128;
+  for (int i = 0; i < spins; ++i) {
     if (depth() >= want) return;
     cpu_relax();
   }

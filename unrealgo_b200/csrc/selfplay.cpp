@@ -461,7 +461,17 @@ void worker(std::vector<Game>& games, size_t lo, size_t hi, Shared& sh) {
     }
     if (!progressed) {
       const auto t0 = std::chrono::steady_clock::now();
-      std::this_thread::sleep_for(std::chrono::microseconds(20));
+      if (hi - lo <= 2) {
+        // one or two games on this thread: every playout waits for its own evaluation, so a sleep (50 us and more of
+        // timer slack) would be paid per playout — spin briefly instead
+        for (int i = 0; i < 2000; ++i) {
+#if defined(__x86_64__)
+          __builtin_ia32_pause();
+#endif
+        }
+      } else {
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+      }
       sh.idle_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
                                std::chrono::steady_clock::now() - t0).count(), std::memory_order_relaxed);
     }
@@ -483,7 +493,7 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
   if (cfg.prelude_moves < 0 || (cfg.prelude_moves > 0 && cfg.record_dir)) return -1;
   Shared sh;
   sh.cfg = cfg;
-  sh.q = ug_queue_create(h, cfg.max_batch, cfg.timeout_us > 0 ? cfg.timeout_us : 200, 4 * cfg.games * (cfg.leaves_per_game > 1 ? cfg.leaves_per_game : 1) + 1024);
+  sh.q = ug_queue_create(h, cfg.max_batch, cfg.timeout_us < 0 ? 0 : (cfg.timeout_us > 0 ? cfg.timeout_us : 200), 4 * cfg.games * (cfg.leaves_per_game > 1 ? cfg.leaves_per_game : 1) + 1024);
   if (!sh.q) return -2;
   ug_queue_set_compact_priors(sh.q, 1);
   std::vector<Game> games((size_t)cfg.games);
