@@ -208,7 +208,10 @@ int ug_debug_max_active_clusters(int device, int cluster_size);
 /* ------------------------------------------------------------------ leaf-batching queue (Q1) */
 /* Replaces EvalBuffer/EvalMsg + NetworkEvalThread's spin loop (search/UctSearch.h:59-72,126-130;
  * search/UctSearch.cpp:164-205): lock-free multi-producer ring, the consumer thread gathers up to max_batch
- * leaves (or flushes after timeout_us), double-buffered pinned staging on two CUDA streams. */
+ * leaves, double-buffered pinned staging on two CUDA streams.  A partial batch is flushed timeout_us after its first
+ * leaf when the GPU is idle; while a batch is still running the consumer keeps collecting until just before the GPU is
+ * expected to run out of work (from the measured time per kernel wave).  timeout_us = 0: flush at once (one producer
+ * that waits for every evaluation: latency mode, the consumer polls instead of sleeping). */
 ug_queue* ug_queue_create(ug_eval* h, int max_batch, int timeout_us, int capacity);
 void ug_queue_destroy(ug_queue* q);
 /* called by search threads; copies *pos (and legal, optional 12 words); returns ticket >= 0, or <0 */

@@ -16,6 +16,7 @@
 // another producer's submit (an earlier ring-of-slots version deadlocked when the ring lapped a parked result).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -62,6 +63,7 @@ struct Staging {
   int n = 0;
   bool any_legal = false;
   bool busy = false;
+  int n_run = 0;                     // positions the batch was launched with (n rounded up to 8)
   int max_out = UG_NUM_MOVES;        // widest result row of the batch (compact priors: max #legal)
   int rc = 0;                        // evaluator return code of this batch (failures belong to a batch, not the queue)
 };
@@ -101,6 +103,21 @@ struct ug_queue {
   std::atomic<bool> sleeping{false};
   std::atomic<uint64_t> wake_at{0};
   std::atomic<uint64_t> n_full{0}, n_wave_cut{0}, n_sleeps{0}, max_depth{0}, gpu_busy_us{0};
+  // Just-in-time flush.  A partial batch only has to leave when the GPU would otherwise run dry: while a batch is still
+  // running there is nothing to gain from flushing 300 us after the first leaf — the partial batch would just sit in
+  // the stream behind it, and partial batches cost more per position (fixed per-launch work, unfilled waves).  The
+  // gather thread therefore waits for a full batch until shortly before the evaluator stream is expected to run out of
+  // work: gpu_free_at_ns is that estimate (steady clock), kept from the measured device time per kernel wave.
+  std::atomic<int64_t> gpu_free_at_ns{0};
+  std::atomic<uint64_t> ema_wave_ns{0};
+  static int64_t now_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
+  int waves_of(int n) const {
+    const long per = (long)(eval->sms / 2) * 256;
+    return (int)(((long)n * UG_NUM_POINTS + per - 1) / per);
+  }
+  int64_t estimate_ns(int n) const { return (int64_t)waves_of(n) * (int64_t)ema_wave_ns.load(std::memory_order_relaxed) + 60000; }
   uint64_t depth() const {
     const uint64_t e = submitted.enq.load(std::memory_order_acquire), d = submitted.deq.load(std::memory_order_acquire);
     return e > d ? e - d : 0;
@@ -165,7 +182,15 @@ void ug_queue::gather_loop() {
       if (quit.load()) break;
       S.busy = true;
     }
-    const auto deadline = clock::now() + std::chrono::microseconds(timeout_us);
+    auto deadline = clock::now() + std::chrono::microseconds(timeout_us);
+    if (timeout_us > 0 && ema_wave_ns.load(std::memory_order_relaxed) > 0) {
+      // just-in-time: keep collecting until 300 us (staging copy, H2D, launch) before the stream runs out of work
+      const int64_t now = now_ns();
+      int64_t jit = gpu_free_at_ns.load(std::memory_order_relaxed) - 300000;
+      if (jit > now + 20000000) jit = now + 20000000;  // an estimate gone wrong must not park the queue
+      const auto jit_tp = clock::time_point(std::chrono::duration_cast<clock::duration>(std::chrono::nanoseconds(jit)));
+      if (jit_tp > deadline) deadline = jit_tp;
+    }
     {
       const uint64_t d = depth() + carry.size();
       uint64_t m = max_depth.load(std::memory_order_relaxed);
@@ -231,6 +256,12 @@ void ug_queue::gather_loop() {
     else rc = eval->enqueue(ug_eval::SRC_PACKED, S.d_pos, n_run, S.any_legal ? S.d_legal : nullptr, eval->value_transform,
                             S.d_policy, S.d_value, eval->stream, cmp && S.any_legal);
     S.rc = rc;
+    S.n_run = n_run;
+    {
+      const int64_t now = now_ns();
+      const int64_t base = std::max(gpu_free_at_ns.load(std::memory_order_relaxed), now);
+      gpu_free_at_ns.store(base + estimate_ns(n_run), std::memory_order_relaxed);
+    }
     if (rc != 0 && n_failed.fetch_add(1, std::memory_order_relaxed) == 0)
       fprintf(stderr, "ugeval queue: evaluator failure %d on a batch of %d: %s\n", rc, n_run, ug_last_error(eval));
     cudaEventRecord(S.ev_done, eval->stream);
@@ -262,6 +293,11 @@ void ug_queue::complete_loop() {
       which = inflight.front();
     }
     Staging& S = st[which];
+    if (timeout_us == 0) {
+      // latency mode (one leaf in flight): poll the event for up to ~1 ms before blocking — the blocking wait's wake-up
+      // costs 50 us and more per evaluation
+      for (int i = 0; i < 200000 && cudaEventQuery(S.ev_out) == cudaErrorNotReady; ++i) cpu_relax();
+    }
     const cudaError_t ce = cudaEventSynchronize(S.ev_out);
     // a CUDA error is sticky for the whole context: every later batch fails too, so it closes the queue
     if (ce != cudaSuccess && error.exchange(-1) == 0)
@@ -269,7 +305,12 @@ void ug_queue::complete_loop() {
     const int failed = (S.rc != 0 || ce != cudaSuccess) ? 1 : 0;
     if (!failed) {
       float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, S.ev_t0, S.ev_done) == cudaSuccess) gpu_busy_us.fetch_add((uint64_t)(ms * 1e3f));
+      if (cudaEventElapsedTime(&ms, S.ev_t0, S.ev_done) == cudaSuccess) {
+        gpu_busy_us.fetch_add((uint64_t)(ms * 1e3f));
+        const uint64_t per_wave = (uint64_t)(ms * 1e6f) / (uint64_t)std::max(waves_of(S.n_run), 1);
+        const uint64_t old = ema_wave_ns.load(std::memory_order_relaxed);
+        ema_wave_ns.store(old ? (3 * old + per_wave) / 4 : per_wave, std::memory_order_relaxed);
+      }
     }
     for (int i = 0; i < S.n; ++i) {
       Slot& sl = slots[S.ids[(size_t)i]];
@@ -284,6 +325,9 @@ void ug_queue::complete_loop() {
       std::lock_guard<std::mutex> lk(mu);
       inflight.pop_front();
       S.busy = false;
+      // re-anchor the estimate: the stream is idle now, or has just started on the other staging buffer's batch
+      const int64_t now = now_ns();
+      gpu_free_at_ns.store(inflight.empty() ? now : now + estimate_ns(st[inflight.front()].n_run), std::memory_order_relaxed);
     }
     cv_free.notify_all();
     cv_results.notify_all();
