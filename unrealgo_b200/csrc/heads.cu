@@ -315,23 +315,32 @@ __device__ __forceinline__ void dsmem_store(float* local, uint32_t cta, float v)
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
 
-// acc[p] += sum_{i<len} f[p*fstride + i] * w[i*stride], 8 positions.  Software-pipelined: the 16 weight loads of
-// the next step are in flight while the current 16 are consumed; features are 16-byte broadcast reads.
+// acc[p] += sum_{i<len} f[p*fstride + i] * w[i*stride], 8 positions.  Software-pipelined: the kFcDepth weight loads of
+// the next step are in flight while the current ones are consumed; features are 16-byte broadcast reads.  A thread walks
+// ~181 weight rows and every step is one L2 round trip, so the number of steps sets the kernel's latency: the remainder
+// (len % kFcDepth rows) is one more batched step with predicated loads, not a row-at-a-time loop (round 1: 11 pipelined
+// steps + 5 single rows = 16 round trips; now 7 + 1).  The remainder step reads features up to 3 floats past `len`
+// (multiplied by zero weights): the caller keeps those finite (rows are padded with zeros).
+constexpr int kFcDepth = 24;
 __device__ __forceinline__ void fc_column8(const float* __restrict__ wcol, int stride, const float* f, int fstride,
                                            int len, float (&acc)[kCluPos]) {
-  const int full = len & ~15;
-  float cur[16], nxt[16];
+  const int full = len - len % kFcDepth;
+  float cur[kFcDepth], nxt[kFcDepth];
   if (full > 0) {
 #pragma unroll
-    for (int u = 0; u < 16; ++u) cur[u] = __ldg(wcol + (size_t)u * stride);
+    for (int u = 0; u < kFcDepth; ++u) cur[u] = __ldg(wcol + (size_t)u * stride);
   }
-  for (int i = 0; i < full; i += 16) {
-    if (i + 16 < full) {
+  const int rem = len - full;
+  for (int i = 0; i < full; i += kFcDepth) {
+    if (i + kFcDepth < full) {
 #pragma unroll
-      for (int u = 0; u < 16; ++u) nxt[u] = __ldg(wcol + (size_t)(i + 16 + u) * stride);
+      for (int u = 0; u < kFcDepth; ++u) nxt[u] = __ldg(wcol + (size_t)(i + kFcDepth + u) * stride);
+    } else {
+#pragma unroll
+      for (int u = 0; u < kFcDepth; ++u) nxt[u] = u < rem ? __ldg(wcol + (size_t)(full + u) * stride) : 0.f;
     }
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
+    for (int g = 0; g < kFcDepth / 4; ++g)
 #pragma unroll
       for (int p = 0; p < kCluPos; ++p) {
         const float4 x = *reinterpret_cast<const float4*>(f + p * fstride + i + 4 * g);
@@ -341,12 +350,26 @@ __device__ __forceinline__ void fc_column8(const float* __restrict__ wcol, int s
         acc[p] = fmaf(x.w, cur[4 * g + 3], acc[p]);
       }
 #pragma unroll
-    for (int u = 0; u < 16; ++u) cur[u] = nxt[u];
+    for (int u = 0; u < kFcDepth; ++u) cur[u] = nxt[u];
   }
-  for (int i = full; i < len; ++i) {
-    const float wv = __ldg(wcol + (size_t)i * stride);
+  if (full == 0) {
 #pragma unroll
-    for (int p = 0; p < kCluPos; ++p) acc[p] = fmaf(f[p * fstride + i], wv, acc[p]);
+    for (int u = 0; u < kFcDepth; ++u) cur[u] = u < rem ? __ldg(wcol + (size_t)u * stride) : 0.f;
+  }
+  if (rem > 0) {
+#pragma unroll
+    for (int g = 0; g < kFcDepth / 4; ++g) {
+      if (4 * g < rem) {
+#pragma unroll
+        for (int p = 0; p < kCluPos; ++p) {
+          const float4 x = *reinterpret_cast<const float4*>(f + p * fstride + full + 4 * g);
+          acc[p] = fmaf(x.x, cur[4 * g], acc[p]);
+          acc[p] = fmaf(x.y, cur[4 * g + 1], acc[p]);
+          acc[p] = fmaf(x.z, cur[4 * g + 2], acc[p]);
+          acc[p] = fmaf(x.w, cur[4 * g + 3], acc[p]);
+        }
+      }
+    }
   }
 }
 
@@ -374,6 +397,11 @@ head_fc_cluster_kernel(const float* __restrict__ feat, HeadWeights hw, const uin
   const int h0 = (int)rank * hper;
   const int nh = max(0, min(hper, H - h0));
 
+  // row padding [pin, pstr) / [vin, vstr): read (times zero weights) by fc_column8's remainder step, must be finite
+  if (tid < kCluPos) {
+    for (int i = pin; i < pstr; ++i) fp[tid * pstr + i] = 0.f;
+    for (int i = vin; i < vstr; ++i) fv[tid * vstr + i] = 0.f;
+  }
   {  // features of the cluster's 8 positions -> shared memory, 4 independent loads in flight per thread
     const int total = kCluPos * kPoints * hc;
     for (int base = 0; base < total; base += 4 * (int)blockDim.x) {
