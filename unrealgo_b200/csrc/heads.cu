@@ -401,6 +401,7 @@ head_fc_cluster_kernel(const float* __restrict__ feat, HeadWeights hw, const uin
   if (tid < kCluPos) {
     for (int i = pin; i < pstr; ++i) fp[tid * pstr + i] = 0.f;
     for (int i = vin; i < vstr; ++i) fv[tid * vstr + i] = 0.f;
+    if (tid < 4) part[tid] = 0.f;  // the last value row's remainder step may look up to 2 floats past fv
   }
   {  // features of the cluster's 8 positions -> shared memory, 4 independent loads in flight per thread
     const int total = kCluPos * kPoints * hc;
