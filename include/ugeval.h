@@ -72,6 +72,10 @@ typedef struct ug_net_info {
   float calib_max_activation;
   float calib_max_weight;
   float fp16_headroom;
+  /* fp16 auto-ranging: tensors stored times 2^-shift (0 = not rescaled); the residual stream's shift and the largest
+   * shift of a block-internal tensor */
+  int fp16_stream_shift;
+  int fp16_max_block_shift;
   /* fp16 mode: how often a tower epilogue had to clamp an output to +-65504 since the evaluator was created (counted
    * per thread and tile, not per element); anything but 0 means results are not trustworthy */
   uint64_t saturation_events;
@@ -119,8 +123,10 @@ int ug_efficient_batch_for_sms(int sm_count, int n);
  * with shifted-descriptor taps and TMA-staged epilogue (conv3x3_v2.cu, default); testing/benchmark knob */
 int ug_eval_set_conv_impl(ug_eval* h, int impl);
 /* What an fp16 evaluator does with a checkpoint whose calibrated range leaves less than 8x headroom below 65504:
- * 0 = evaluate it with bf16 operands instead (default; a warning goes to stderr, ug_net_info.precision tells),
- * 1 = refuse it (ug_eval_load_checkpoint returns >0), 2 = load it anyway.  UGEVAL_FP16_RANGE=bf16|refuse|ignore. */
+ * 0 = auto (default): store the hot tensors times 2^-k (exact; folded into the packed weights and biases, accuracy
+ *     unchanged) and, only if a folded weight itself is out of range, evaluate with bf16 operands instead (a note goes
+ *     to stderr; ug_net_info.precision / fp16_stream_shift tell); 1 = refuse it (ug_eval_load_checkpoint returns >0);
+ * 2 = load it anyway; 3 = bf16 operands without rescaling.  UGEVAL_FP16_RANGE=auto|refuse|ignore|bf16. */
 int ug_eval_set_fp16_range_policy(ug_eval* h, int policy);
 /* Batches of at most max_batch positions run the tower on the small-batch kernel (conv3x3_sb.cu: 128-row x nt-column
  * tiles on many SMs) — the batch sizes the reference's engine issues (1 .. MAX_BATCHES = 16,

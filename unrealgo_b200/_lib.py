@@ -35,7 +35,8 @@ class NetInfo(C.Structure):
         ("value_hidden", C.c_int), ("input_planes", C.c_int), ("flops_per_position", C.c_double),
         ("conv_ctas", C.c_int), ("sm_count", C.c_int), ("conv_impl", C.c_int), ("small_batch_max", C.c_int),
         ("precision", C.c_int), ("calib_max_activation", C.c_float), ("calib_max_weight", C.c_float),
-        ("fp16_headroom", C.c_float), ("saturation_events", C.c_uint64),
+        ("fp16_headroom", C.c_float), ("fp16_stream_shift", C.c_int), ("fp16_max_block_shift", C.c_int),
+        ("saturation_events", C.c_uint64),
     ]
 
 

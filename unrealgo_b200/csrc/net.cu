@@ -125,19 +125,26 @@ float max_abs(const std::vector<float>& v) {
   return m;
 }
 
-bool make_conv_layer(const HostConv& hc, int cin_pad, bool f16, ConvLayer* L, std::string* err) {
+// in_shift / out_shift (fp16 auto-ranging): the layer's input is stored times 2^-in_shift and its output times
+// 2^-out_shift, so the packed weights carry 2^(in_shift - out_shift) and the tensor-core bias 2^-out_shift — exact
+// scalings; the fp32 copies (validation tower, calibration) stay as loaded.
+bool make_conv_layer(const HostConv& hc, int cin_pad, bool f16, int in_shift, int out_shift, ConvLayer* L,
+                     std::string* err) {
   L->cin = hc.cin;
   L->cin_pad = cin_pad;
   L->cout = hc.cout;
   const int ktot = 9 * cin_pad;
+  const float wscale = std::ldexp(1.f, in_shift - out_shift);
   std::vector<uint16_t> packed((size_t)hc.cout * ktot, 0);
   for (int tap = 0; tap < 9; ++tap)
     for (int ci = 0; ci < hc.cin; ++ci)
-      for (int co = 0; co < hc.cout; ++co)
-        packed[(size_t)co * ktot + tap * cin_pad + ci] =
-            f16 ? f32_to_f16_rn(hc.w[((size_t)tap * hc.cin + ci) * hc.cout + co])
-                : f32_to_bf16_rn(hc.w[((size_t)tap * hc.cin + ci) * hc.cout + co]);
-  if (!upload(&L->w_bf16, packed.data(), packed.size() * 2) ||
+      for (int co = 0; co < hc.cout; ++co) {
+        const float w = hc.w[((size_t)tap * hc.cin + ci) * hc.cout + co] * wscale;
+        packed[(size_t)co * ktot + tap * cin_pad + ci] = f16 ? f32_to_f16_rn(w) : f32_to_bf16_rn(w);
+      }
+  std::vector<float> btc(hc.b);
+  for (float& b : btc) b = std::ldexp(b, -out_shift);
+  if (!upload(&L->w_bf16, packed.data(), packed.size() * 2) || !upload(&L->bias_tc, btc.data(), btc.size() * 4) ||
       !upload(&L->w_f32, hc.w.data(), hc.w.size() * 4) || !upload(&L->bias, hc.b.data(), hc.b.size() * 4)) {
     *err = "out of device memory uploading weights";
     return false;
@@ -166,8 +173,16 @@ bool load_dense(const TfBundle& ck, const DensePlan& p, int in, std::vector<floa
   return true;
 }
 
-Weights* build_weights(const NetPlan& plan, const TfBundle& ck, bool f16, std::string* err) {
+// shifts (optional): {stream_shift, block_shift[0], block_shift[1], ...} from the range calibration
+Weights* build_weights(const NetPlan& plan, const TfBundle& ck, bool f16, const std::vector<int>* shifts,
+                       std::string* err) {
   std::unique_ptr<Weights> W(new Weights());
+  const int n_blocks = (int)plan.tower.size() / 2;
+  W->block_shift.assign((size_t)n_blocks, 0);
+  if (shifts && (int)shifts->size() == 1 + n_blocks) {
+    W->stream_shift = (*shifts)[0];
+    for (int b = 0; b < n_blocks; ++b) W->block_shift[(size_t)b] = (*shifts)[1 + (size_t)b];
+  }
   HostConv stem;
   if (!load_conv(ck, plan.stem, 3, &stem, err)) return nullptr;
   if (stem.cin != UG_NUM_PLANES) { *err = "stem conv expects " + std::to_string(stem.cin) + " input planes, the engine provides 17"; return nullptr; }
@@ -180,15 +195,18 @@ Weights* build_weights(const NetPlan& plan, const TfBundle& ck, bool f16, std::s
   W->f16 = f16;
   W->blocks = (int)plan.tower.size() / 2;
   W->convs.resize(1 + plan.tower.size());
-  if (!make_conv_layer(stem, kCinPad, f16, &W->convs[0], err)) return nullptr;
-  W->max_weight = max_abs(stem.w);
+  if (!make_conv_layer(stem, kCinPad, f16, 0, W->stream_shift, &W->convs[0], err)) return nullptr;
+  W->max_weight = std::ldexp(max_abs(stem.w), -W->stream_shift);  // of the weights as packed
   W->max_weight_layer = 0;
   for (size_t i = 0; i < plan.tower.size(); ++i) {
     HostConv hc;
     if (!load_conv(ck, plan.tower[i], 3, &hc, err)) return nullptr;
     if (hc.cin != C || hc.cout != C) { *err = "tower conv '" + plan.tower[i].kernel + "' is not C x C"; return nullptr; }
-    if (!make_conv_layer(hc, C, f16, &W->convs[1 + i], err)) return nullptr;
-    const float mw = max_abs(hc.w);
+    // conv1 of block b: stream -> T_b; conv2: T_b -> stream
+    const int bs = W->block_shift[i / 2];
+    const int in_shift = (i % 2 == 0) ? W->stream_shift : bs, out_shift = (i % 2 == 0) ? bs : W->stream_shift;
+    if (!make_conv_layer(hc, C, f16, in_shift, out_shift, &W->convs[1 + i], err)) return nullptr;
+    const float mw = std::ldexp(max_abs(hc.w), in_shift - out_shift);
     if (mw > W->max_weight || mw != mw) { W->max_weight = mw; W->max_weight_layer = 1 + (int)i; }
   }
   HostConv pcv, vcv;
@@ -210,7 +228,10 @@ Weights* build_weights(const NetPlan& plan, const TfBundle& ck, bool f16, std::s
   int od = 0;
   if (!load_dense(ck, plan.policy_fc, UG_NUM_POINTS * W->pc, &w, &b, &od, err)) return nullptr;
   if (od != UG_NUM_MOVES) { *err = "policy dense layer has " + std::to_string(od) + " outputs, expected 362"; return nullptr; }
+  std::vector<float> hw_tc(hw);  // the heads read the stream: stored times 2^-stream_shift
+  for (float& x : hw_tc) x = std::ldexp(x, W->stream_shift);
   bool ok = upload(&W->head_conv_w, hw.data(), hw.size() * 4) && upload(&W->head_conv_b, hb.data(), hb.size() * 4) &&
+            upload(&W->head_conv_w_tc, hw_tc.data(), hw_tc.size() * 4) &&
             upload(&W->pfc_w, w.data(), w.size() * 4) && upload(&W->pfc_b, b.data(), b.size() * 4);
   if (!load_dense(ck, plan.value_fc1, UG_NUM_POINTS * W->vc, &w, &b, &od, err)) return nullptr;
   W->H = od;
@@ -287,6 +308,7 @@ bool calibrate_range(ug_eval* h, Weights* W, std::string* err) {
   const cudaError_t e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) { *err = std::string("range calibration failed: ") + cudaGetErrorString(e); return false; }
   W->max_activation = 0.f;
+  W->layer_max = host;
   for (int l = 0; l < layers; ++l)
     if (host[(size_t)l] > W->max_activation || host[(size_t)l] != host[(size_t)l]) {
       W->max_activation = host[(size_t)l];
@@ -442,7 +464,7 @@ int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act, const 
   a.cout = C;
   // stem: 32 stored input channels (17 planes + zeros), SWIZZLE_64B tiles; its output opens the residual stream
   a.cin = kCinPad;
-  a.bias = W.convs[0].bias.as<float>();
+  a.bias = W.convs[0].bias_tc.as<float>();
   a.out = d_s_hi[0].as<__nv_bfloat16>();
   const bool split = resid_split;
   a.out_lo = split ? d_s_lo[0].as<__nv_bfloat16>() : nullptr;
@@ -455,7 +477,7 @@ int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act, const 
     const int x = b & 1, y = x ^ 1;
     const ConvLayer& c1 = W.convs[1 + 2 * b];
     const ConvLayer& c2 = W.convs[2 + 2 * b];
-    a.bias = c1.bias.as<float>();
+    a.bias = c1.bias_tc.as<float>();
     a.residual = nullptr;
     a.residual_lo = nullptr;
     a.out = d_t.as<__nv_bfloat16>();
@@ -465,7 +487,7 @@ int ug_eval::enqueue_tower(int n, cudaStream_t s, const void** final_act, const 
     *final_act = d_t.p;
     *final_lo = nullptr;
     if (debug_stop == 2 * b + 1) break;
-    a.bias = c2.bias.as<float>();
+    a.bias = c2.bias_tc.as<float>();
     a.residual = d_s_hi[x].as<__nv_bfloat16>();
     a.residual_lo = split ? d_s_lo[x].as<__nv_bfloat16>() : nullptr;
     a.out = d_s_hi[y].as<__nv_bfloat16>();
@@ -507,7 +529,7 @@ int ug_eval::enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, con
   };
   // stem: writes S[0] (hi [+ lo])
   a.cin = kCinPad;
-  a.bias = W.convs[0].bias.as<float>();
+  a.bias = W.convs[0].bias_tc.as<float>();
   a.has_out_lo = split;
   ConvV2Maps m{&v2_a_in, &W.convs[0].tm_w[1], nullptr, nullptr, &v2_out_hi[0], split ? &v2_out_lo[0] : nullptr};
   set_deps(false);
@@ -520,7 +542,7 @@ int ug_eval::enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, con
     const int x = b & 1, y = x ^ 1;
     const ConvLayer& c1 = W.convs[1 + 2 * b];
     const ConvLayer& c2 = W.convs[2 + 2 * b];
-    a.bias = c1.bias.as<float>();
+    a.bias = c1.bias_tc.as<float>();
     a.has_res = a.has_res_lo = a.has_out_lo = 0;
     m = ConvV2Maps{&v2_a_s[x], &c1.tm_w[1], nullptr, nullptr, &v2_out_t, nullptr};
     layer = 2 * b + 1;
@@ -530,14 +552,14 @@ int ug_eval::enqueue_tower_v2(int n, cudaStream_t s, const void** final_act, con
     *final_act = d_t.p;
     *final_lo = nullptr;
     if (debug_stop == 2 * b + 1) break;
-    a.bias = c2.bias.as<float>();
+    a.bias = c2.bias_tc.as<float>();
     a.has_res = 1;
     a.has_res_lo = a.has_out_lo = split;
     // last layer: the head 1x1 convolutions ride in its epilogue and the activation itself is never stored
     const bool fuse = fuse_heads && debug_stop < 0 && b == W.blocks - 1 &&
                       conv3x3_v2_can_fuse_heads(64, 1, split, split, W.pc + W.vc);
     if (fuse) {
-      a.head_w = W.head_conv_w.as<float>();
+      a.head_w = W.head_conv_w_tc.as<float>();
       a.head_b = W.head_conv_b.as<float>();
       a.head_out = d_feat.as<float>();
       a.head_channels = W.pc + W.vc;
@@ -575,7 +597,7 @@ int ug_eval::enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, con
   a.sat_count = d_sat.as<unsigned long long>();
   a.nt = sb_nt;
   a.cin = kCinPad;
-  a.bias = W.convs[0].bias.as<float>();
+  a.bias = W.convs[0].bias_tc.as<float>();
   a.out_hi = d_s_hi[0].p;
   a.out_lo = split ? d_s_lo[0].p : nullptr;
   cudaError_t e = conv3x3_sb_launch(v2_a_in, W.convs[0].tm_w_sb, a, 32, device, sms, s);
@@ -587,7 +609,7 @@ int ug_eval::enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, con
     const int x = b & 1, y = x ^ 1;
     const ConvLayer& c1 = W.convs[1 + 2 * b];
     const ConvLayer& c2 = W.convs[2 + 2 * b];
-    a.bias = c1.bias.as<float>();
+    a.bias = c1.bias_tc.as<float>();
     a.res_hi = a.res_lo = nullptr;
     a.out_hi = d_t.p;
     a.out_lo = nullptr;
@@ -608,10 +630,10 @@ int ug_eval::enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, con
       v.cin = v.cout = C;
       v.pdl = a.pdl;
       v.sat_count = a.sat_count;
-      v.bias = c2.bias.as<float>();
+      v.bias = c2.bias_tc.as<float>();
       v.has_res = 1;
       v.has_res_lo = v.has_out_lo = split;
-      v.head_w = W.head_conv_w.as<float>();
+      v.head_w = W.head_conv_w_tc.as<float>();
       v.head_b = W.head_conv_b.as<float>();
       v.head_out = d_feat.as<float>();
       v.head_channels = W.pc + W.vc;
@@ -623,7 +645,7 @@ int ug_eval::enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, con
       *final_lo = nullptr;
       break;
     }
-    a.bias = c2.bias.as<float>();
+    a.bias = c2.bias_tc.as<float>();
     a.res_hi = d_s_hi[x].p;
     a.res_lo = split ? d_s_lo[x].p : nullptr;
     a.out_hi = d_s_hi[y].p;
@@ -639,7 +661,7 @@ int ug_eval::enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, con
 
 int ug_eval::enqueue_heads(const void* act, const void* act_lo, int n, const uint32_t* d_leg, int vt, float* d_pol,
                            float* d_val, cudaStream_t s, bool compact) {
-  const HeadWeights hw = weights->head();
+  const HeadWeights hw = precision == UG_PREC_FP32 ? weights->head() : weights->head_tc();
   if (act != nullptr)  // null: the tower's last layer already produced d_feat (fused head convolutions)
     launch_head_conv(act, act_lo, precision == UG_PREC_FP32 ? 1 : (precision == UG_PREC_FP16 ? 2 : 0), hw,
                      d_feat.as<float>(), n, s);
@@ -719,7 +741,7 @@ ug_eval* ug_eval_create(int device, int precision, int max_batch) {
   h->device = device;
   h->precision = h->precision_requested = precision;
   if (const char* fr = getenv("UGEVAL_FP16_RANGE"))
-    h->fp16_policy = !strcmp(fr, "refuse") ? 1 : (!strcmp(fr, "ignore") ? 2 : 0);
+    h->fp16_policy = !strcmp(fr, "refuse") ? 1 : (!strcmp(fr, "ignore") ? 2 : (!strcmp(fr, "bf16") ? 3 : 0));
   h->max_batch = max_batch;
   h->sms = prop.multiProcessorCount;
   const char* ng = getenv("UGEVAL_NO_GRAPH");
@@ -805,27 +827,52 @@ int ug_eval_load_checkpoint(ug_eval* h, const char* prefix) {
   TfBundle ck;
   if (!ck.open(h->ckpt_prefix, &err)) return h->fail(1, err);
   int precision = h->precision_requested;
-  Weights* W = build_weights(h->plan, ck, precision == UG_PREC_FP16, &err);
+  Weights* W = build_weights(h->plan, ck, precision == UG_PREC_FP16, nullptr, &err);
   if (!W) return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err);
   if (!calibrate_range(h, W, &err)) { delete W; return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err); }
   {
     const float worst = W->max_activation > W->max_weight ? W->max_activation : W->max_weight;
-    const bool nan = worst != worst;
-    if (nan) { delete W; return h->fail(1, "checkpoint " + h->ckpt_prefix + ": weights or calibration activations are NaN"); }
+    if (worst != worst) { delete W; return h->fail(1, "checkpoint " + h->ckpt_prefix + ": weights or calibration activations are NaN"); }
     if (precision == UG_PREC_FP16 && worst > 65504.f / 8 && h->fp16_policy != 2) {
       char msg[512];
       snprintf(msg, sizeof(msg), "checkpoint %s leaves fp16 less than 8x headroom (largest |activation| %.4g after layer %d, "
                "largest |folded weight| %.4g in layer %d, fp16 saturates at 65504)", h->ckpt_prefix.c_str(),
                (double)W->max_activation, W->max_activation_layer, (double)W->max_weight, W->max_weight_layer);
       if (h->fp16_policy == 1) { delete W; return h->fail(1, std::string(msg) + ": refused (UGEVAL_FP16_RANGE=refuse)"); }
-      fprintf(stderr, "ugeval: %s: evaluating with bf16 operands instead\n", msg);
+      // auto-ranging: store every hot tensor times 2^-shift so that its calibrated maximum sits near 2^11 (32x headroom)
+      const int blocks = W->blocks;
+      std::vector<int> shifts((size_t)(1 + blocks), 0);
+      auto shift_for = [](float mx) { int k = 0; while (std::ldexp(mx, -k) > 2048.f && k < 60) ++k; return k; };
+      float stream_max = W->layer_max.empty() ? 0.f : W->layer_max[0];
+      for (int b = 0; b < blocks; ++b) stream_max = std::max(stream_max, W->layer_max[(size_t)(2 * b + 2)]);
+      shifts[0] = shift_for(stream_max);
+      for (int b = 0; b < blocks; ++b) shifts[(size_t)(1 + b)] = shift_for(W->layer_max[(size_t)(2 * b + 1)]);
+      const std::vector<float> lm = W->layer_max;
       const float ma = W->max_activation, mw = W->max_weight;
       const int la = W->max_activation_layer, lw = W->max_weight_layer;
       delete W;
-      precision = UG_PREC_BF16;
-      W = build_weights(h->plan, ck, false, &err);
-      if (!W) return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err);
-      W->max_activation = ma; W->max_weight = mw; W->max_activation_layer = la; W->max_weight_layer = lw;
+      W = nullptr;
+      if (h->fp16_policy == 0) {
+        W = build_weights(h->plan, ck, true, &shifts, &err);
+        if (!W) return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err);
+        if (W->max_weight > 65504.f / 2 || !(W->max_weight == W->max_weight)) {  // rescaling cannot help the weights
+          delete W;
+          W = nullptr;
+        } else {
+          int bmax = 0;
+          for (int v : W->block_shift) bmax = std::max(bmax, v);
+          fprintf(stderr, "ugeval: %s: activations rescaled by powers of two (stream 2^-%d, blocks up to 2^-%d)\n", msg,
+                  W->stream_shift, bmax);
+        }
+      }
+      if (!W) {
+        fprintf(stderr, "ugeval: %s: evaluating with bf16 operands instead\n", msg);
+        precision = UG_PREC_BF16;
+        W = build_weights(h->plan, ck, false, nullptr, &err);
+        if (!W) return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err);
+      }
+      if (W->stream_shift == 0) W->max_weight = mw;  // (rescaled weights keep the maximum of what was packed)
+      W->layer_max = lm; W->max_activation = ma; W->max_activation_layer = la; W->max_weight_layer = lw;
     }
   }
   if (precision != h->precision) {  // 16-bit formats share every buffer; the format is a run-time flag of the kernels
@@ -896,7 +943,7 @@ int ug_eval_set_residual_split(ug_eval* h, int on) {
 }
 
 int ug_eval_set_fp16_range_policy(ug_eval* h, int policy) {
-  if (!h || policy < 0 || policy > 2) return -1;
+  if (!h || policy < 0 || policy > 3) return -1;
   h->fp16_policy = policy;
   return 0;
 }
@@ -927,8 +974,17 @@ int ug_eval_info(const ug_eval* h, ug_net_info* out) {
   out->precision = h->precision;
   out->calib_max_activation = W.max_activation;
   out->calib_max_weight = W.max_weight;
-  const float worst = W.max_activation > W.max_weight ? W.max_activation : W.max_weight;
-  out->fp16_headroom = worst > 0 ? 65504.f / worst : 0.f;
+  {  // headroom of what is actually stored: calibrated maxima after the power-of-two shifts, and the packed weights
+    float worst = W.max_weight;
+    for (size_t l = 0; l < W.layer_max.size(); ++l) {
+      const int sh = (l == 0 || l % 2 == 0) ? W.stream_shift : W.block_shift[(l - 1) / 2];
+      worst = std::max(worst, std::ldexp(W.layer_max[l], -sh));
+    }
+    out->fp16_headroom = worst > 0 ? 65504.f / worst : 0.f;
+  }
+  out->fp16_stream_shift = W.stream_shift;
+  out->fp16_max_block_shift = 0;
+  for (int v : W.block_shift) out->fp16_max_block_shift = std::max(out->fp16_max_block_shift, v);
   out->saturation_events = 0;
   if (h->d_sat.p) {
     cudaSetDevice(h->device);

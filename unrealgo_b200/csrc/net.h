@@ -38,7 +38,8 @@ struct ConvLayer {
   int cin = 0, cin_pad = 0, cout = 0;
   DevBuf w_bf16;   // [cout][9*cin_pad] K-major, batch-norm folded
   DevBuf w_f32;    // [3][3][cin][cout] folded (fp32 validation path)
-  DevBuf bias;     // [cout] fp32
+  DevBuf bias;     // [cout] fp32 (fp32 validation tower, range calibration)
+  DevBuf bias_tc;  // [cout] fp32 for the 16-bit tensor-core tower: bias * 2^-out_shift (fp16 auto-ranging), else == bias
   CUtensorMap tm_w[2];  // index = ctas-1 (box rows differ)
   CUtensorMap tm_w_sb;  // box {ck, 16}: the small-batch kernel loads its NT weight rows 16 at a time
 };
@@ -50,6 +51,14 @@ struct Weights {
   // |layer output| seen when a few calibration positions run through the fp32 validation tower
   float max_weight = 0.f, max_activation = 0.f;
   int max_activation_layer = -1, max_weight_layer = -1;
+  std::vector<float> layer_max;  // calibration: largest |output| per layer (0 = stem, 2b+1 / 2b+2 = convs of block b)
+  // fp16 auto-ranging: activations are stored times 2^-shift (exact: powers of two), folded into the packed weights and
+  // biases — stream_shift for the residual stream (one value: the skip connection adds without rescaling), block_shift[b]
+  // for block b's internal tensor.  All zero unless the calibration found fp16 short of headroom.
+  int stream_shift = 0;
+  std::vector<int> block_shift;
+  DevBuf head_conv_w_tc;         // head 1x1 weights * 2^stream_shift for the tensor-core tower (else a copy)
+  HeadWeights head_tc() const { HeadWeights h = head(); h.conv_w = head_conv_w_tc.as<float>(); return h; }
   bool policy_softmax = true, value_tanh = true;
   std::vector<ConvLayer> convs;  // [0] stem, then 2 per block
   DevBuf head_conv_w, head_conv_b, pfc_w, pfc_b, v1_w, v1_b, v2_w, v2_b;
@@ -63,9 +72,11 @@ struct ug_eval {
   int precision = UG_PREC_BF16;            // arithmetic in use
   int precision_requested = UG_PREC_BF16;  // what ug_eval_create asked for (a checkpoint outside fp16's range can
                                            // move an fp16 evaluator to bf16: fp16_policy)
-  // fp16 operands saturate at 65504.  0 = fall back to bf16 when a checkpoint's calibrated range leaves less than 8x
-  // headroom (default), 1 = refuse the checkpoint, 2 = load anyway (ug_net_info.saturation_events then tells).
-  // UGEVAL_FP16_RANGE=bf16|refuse|ignore
+  // fp16 operands saturate at 65504.  When a checkpoint's calibrated range leaves less than 8x headroom:
+  // 0 = auto (default): rescale the layers by powers of two (exact; folded into weights and biases), and only if that
+  //     cannot help (a folded weight out of range) evaluate with bf16 operands; 1 = refuse the checkpoint;
+  // 2 = load anyway (ug_net_info.saturation_events then tells); 3 = bf16 operands without trying to rescale.
+  // UGEVAL_FP16_RANGE=auto|refuse|ignore|bf16
   int fp16_policy = 0;
   int max_batch = 0;
   int sms = 148;

@@ -148,9 +148,10 @@ class DlTFNetworkEvaluator:
             raise ValueError("impl must be 1 or 2")
 
     def set_fp16_range_policy(self, policy):
-        """0 = fall back to bf16 for a checkpoint outside fp16's range (default), 1 = refuse it, 2 = load it anyway"""
-        if self._lib.ug_eval_set_fp16_range_policy(self._h, {"bf16": 0, "refuse": 1, "ignore": 2}.get(policy, policy)) != 0:
-            raise ValueError("policy: 0/'bf16', 1/'refuse', 2/'ignore'")
+        """a checkpoint outside fp16's range: 0/'auto' = rescale by powers of two, else bf16 (default); 1/'refuse';
+        2/'ignore' = load anyway; 3/'bf16' = bf16 operands without rescaling"""
+        if self._lib.ug_eval_set_fp16_range_policy(self._h, {"auto": 0, "refuse": 1, "ignore": 2, "bf16": 3}.get(policy, policy)) != 0:
+            raise ValueError("policy: 0/'auto', 1/'refuse', 2/'ignore', 3/'bf16'")
 
     def set_small_batch(self, max_batch, nt=0):
         """batches <= max_batch run the small-batch tower kernel (0 disables); nt = output channels per CTA (0 = auto)"""
