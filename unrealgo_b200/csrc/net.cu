@@ -1024,7 +1024,10 @@ static int run_planes_common(ug_eval* h, const int8_t* planes, int hwc, int n, d
   int rc = h->enqueue(hwc ? ug_eval::SRC_HWC : ug_eval::SRC_CHW, h->d_planes.p, n, nullptr, UG_TR_IDENTITY,
                       h->d_policy.as<float>(), h->d_value.as<float>(), s);
   if (rc) return rc;
-  const bool direct_out = h->is_registered(policy, pol_count * 8) && h->is_registered(value, (size_t)n * 8);
+  // Registered outputs are worth it for large batches only (the widening kernel and two DMA writes of doubles replace
+  // a host loop over n * 362 floats); at the reference engine's own batch sizes the extra launch costs more than the
+  // loop: measured 0.41 ms against 0.35 ms per call at n = 1.
+  const bool direct_out = n > 32 && h->is_registered(policy, pol_count * 8) && h->is_registered(value, (size_t)n * 8);
   if (direct_out) {
     // Outputs must stay untouched on failure (.cc:315-317): a faulting kernel poisons the stream, so the copies
     // queued behind it never run.
