@@ -110,6 +110,8 @@ int ug_eval_ready(const ug_eval* h);
 int ug_eval_has_weights(const ug_eval* h);
 /* value_transform applied by run calls (the reference reads it from the DlConfig singleton, .cc:300) */
 int ug_eval_set_value_transform(ug_eval* h, int vt);
+/* description of the loaded network and its range calibration; waits for the evaluator's own stream (it reads the
+ * device-side saturation counter): not for a hot loop */
 int ug_eval_info(const ug_eval* h, ug_net_info* out);
 /* use cta_group::1 or ::2 tower kernels (default 2); testing/benchmark knob */
 int ug_eval_set_conv_ctas(ug_eval* h, int ctas);

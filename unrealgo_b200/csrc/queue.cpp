@@ -108,6 +108,7 @@ struct ug_queue {
   // the stream behind it, and partial batches cost more per position (fixed per-launch work, unfilled waves).  The
   // gather thread therefore waits for a full batch until shortly before the evaluator stream is expected to run out of
   // work: gpu_free_at_ns is that estimate (steady clock), kept from the measured device time per kernel wave.
+  std::atomic<int64_t> last_leaf_ns{0};   // when the gather thread last saw a leaf (latency mode spins only while hot)
   std::atomic<int64_t> gpu_free_at_ns{0};
   std::atomic<uint64_t> ema_wave_ns{0};
   static int64_t now_ns() {
@@ -134,7 +135,9 @@ void ug_queue::wait_for_leaves(uint64_t want, std::chrono::steady_clock::time_po
   // leaves arrive in bursts: a short spin first.  With timeout_us == 0 the caller asked for latency, not batching (a
   // single search thread waiting for every evaluation): spin for ~100 us before giving the CPU away, a sleeping
   // thread costs a wake-up of 50 us and more per leaf
-  const int spins = timeout_us == 0 ? 40000 : 128;
+  // (only while leaves keep coming: an engine that is idle between searches must not keep a core spinning)
+  const bool hot = timeout_us == 0 && now_ns() - last_leaf_ns.load(std::memory_order_relaxed) < 5000000;
+  const int spins = hot ? 40000 : 128;
   for (int i = 0; i < spins; ++i) {
     if (depth() >= want) return;
     cpu_relax();
@@ -212,6 +215,7 @@ void ug_queue::gather_loop() {
       S.ids.push_back(id);
       ++n;
     }
+    last_leaf_ns.store(now_ns(), std::memory_order_relaxed);
     carry.erase(carry.begin(), carry.begin() + (long)from_carry);
     if (timed_out) {
       n_timeouts.fetch_add(1, std::memory_order_relaxed);
