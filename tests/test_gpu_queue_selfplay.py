@@ -246,3 +246,24 @@ def test_waiting_on_a_consumed_ticket_returns_instead_of_hanging(small_ckpt):
         q.wait(t)                                      # consumed: reported, not waited for
     q.close()
     ev.close()
+
+
+def test_failed_batch_fails_its_own_leaves_only(small_ckpt):
+    """a queue created before any checkpoint is loaded: the leaves of that batch come back failed (outputs untouched),
+    and once weights are there the same queue evaluates — a failure belongs to a batch, not to the queue"""
+    import oracle
+    from unrealgo_b200 import DlTFNetworkEvaluator, LeafQueue
+    packed, _ = oracle.synthetic_positions(4, seed=8)
+    ev = DlTFNetworkEvaluator(small_ckpt[0], max_batch=64)        # graph only
+    q = LeafQueue(ev, max_batch=8, timeout_us=100)
+    t = q.submit(packed[0])
+    with pytest.raises(RuntimeError):
+        q.wait(t)
+    assert q.swap_checkpoint(small_ckpt[1])
+    pol, val = q.wait(q.submit(packed[1]))
+    want_p, want_v = ev.evaluate_packed(packed[1:2])
+    assert np.array_equal(pol, want_p[0]) and val == want_v[0]
+    st = q.stats_ex()
+    assert st["failed_batches"] == 1 and st["leaves"] == 2
+    q.close()
+    ev.close()
