@@ -1,3 +1,11 @@
+"""TEST INFRASTRUCTURE — where does the 16-bit tower's error come from?  
+
+A CPU emulation (torch fp32) of the tower's roundings on the flagship 20x256 synthetic net, 16 positions: operands are
+rounded to fp16 / bf16 exactly where the tensor-core path rounds them (weights once, activations at every layer input,
+the residual stream kept as a hi+lo pair), accumulation and epilogue in fp32, heads from the unrounded last layer.
+Rounding the weights only, or the activations only, shows that for bf16 each side alone already exceeds the 5e-3 value
+tolerance — which is why compensating one operand (2 MMAs per product) cannot rescue bf16, and 3 MMAs are too slow.
+    python tests/precision_sim.py [seed]      (about a minute on 8 cores)"""
 import sys, os, tempfile, time
 sys.path.insert(0,'/root/repo')
 import numpy as np, torch, torch.nn.functional as F
