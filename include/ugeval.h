@@ -237,7 +237,8 @@ int ug_queue_stats(ug_queue* q, uint64_t* batches, uint64_t* leaves, uint64_t* f
 int ug_queue_set_compact_priors(ug_queue* q, int on);
 /* out[0..count): batches, leaves, timeout flushes, full batches, batches cut back to whole kernel waves, failed batches,
  * deepest submission queue seen at a batch start, times the gather thread went to sleep, microseconds the evaluator
- * stream spent on batches (CUDA events around every batch: device busy time) */
+ * stream spent on batches (CUDA events around every batch: device busy time), batches launched onto an idle stream and
+ * the microseconds it had been idle for (host clock) */
 int ug_queue_stats_ex(ug_queue* q, uint64_t* out, int count);
 /* pause the consumer, swap the checkpoint, resume (hot swap between searches, search/UctSearch.cpp:178-182) */
 int ug_queue_swap_checkpoint(ug_queue* q, const char* prefix);
@@ -287,6 +288,8 @@ typedef struct ug_selfplay_stats {
   double search_busy_fraction, host_us_per_playout;
   uint64_t full_batches, wave_cut_batches, max_queue_depth, gather_sleeps;
   double gpu_busy_fraction;   /* share of the run the evaluator stream was working on a batch */
+  uint64_t idle_launches;     /* batches launched when nothing was running or queued */
+  double idle_gap_seconds;    /* total time the stream had been idle at those launches */
 } ug_selfplay_stats;
 /* moves_out (optional): [games][(max_moves or 722) + prelude_moves] policy indices (361 = pass), the prelude's moves
  * first; n_moves_out: [games] */

@@ -38,7 +38,8 @@ def main():
         st, _ = selfplay(ev, games=games, threads=threads, playouts_per_move=1600, max_moves=1, max_batch=mb,
                          timeout_us=300, reuse_tree=True, prelude_moves=prelude, seed=1000 + rank)
         row = [st["playouts_per_s"], st["gpu_busy_fraction"], st["mean_batch"], st["search_busy_fraction"],
-               st["host_us_per_playout"], float(st["flush_timeouts"]), st["seconds"], float(st["playouts"])]
+               st["host_us_per_playout"], float(st["flush_timeouts"]), st["seconds"], float(st["playouts"]),
+               float(st["idle_launches"]), st["idle_gap_seconds"], float(st["batches"])]
         t = torch.tensor(row, dtype=torch.float64, device="cuda")
         rows = [torch.zeros_like(t) for _ in range(world)]
         if world > 1:
@@ -53,7 +54,9 @@ def main():
                               "gpu_busy": [round(r[1], 3) for r in rows], "mean_batch": [round(r[2], 1) for r in rows],
                               "search_busy": [round(r[3], 2) for r in rows],
                               "host_us_per_playout": [round(r[4], 1) for r in rows],
-                              "flush_timeouts": [int(r[5]) for r in rows]}), flush=True)
+                              "flush_timeouts": [int(r[5]) for r in rows], "batches": [int(r[10]) for r in rows],
+                              "idle_launches": [int(r[8]) for r in rows],
+                              "idle_gap_s": [round(r[9], 2) for r in rows], "seconds": [round(r[6], 1) for r in rows]}), flush=True)
     ev.close()
     if world > 1:
         dist.destroy_process_group()

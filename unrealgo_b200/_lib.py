@@ -55,7 +55,8 @@ class SelfplayStats(C.Structure):
                 ("mean_batch", C.c_double), ("mean_tree_nodes", C.c_double),
                 ("search_busy_fraction", C.c_double), ("host_us_per_playout", C.c_double),
                 ("full_batches", C.c_uint64), ("wave_cut_batches", C.c_uint64), ("max_queue_depth", C.c_uint64),
-                ("gather_sleeps", C.c_uint64), ("gpu_busy_fraction", C.c_double)]
+                ("gather_sleeps", C.c_uint64), ("gpu_busy_fraction", C.c_double),
+                ("idle_launches", C.c_uint64), ("idle_gap_seconds", C.c_double)]
 
 
 class BenchResult(C.Structure):

@@ -123,6 +123,9 @@ struct ug_queue {
   // the stream behind it, and partial batches cost more per position (fixed per-launch work, unfilled waves).  The
   // gather thread therefore waits for a full batch until shortly before the evaluator stream is expected to run out of
   // work: gpu_free_at_ns is that estimate (steady clock), kept from the measured device time per kernel wave.
+  // how often a batch was launched while the evaluator stream was already idle, and for how long it had been (host clock)
+  std::atomic<uint64_t> n_launch_idle{0}, idle_gap_us{0};
+  std::atomic<int64_t> last_done_ns{0};
   std::atomic<int64_t> last_leaf_ns{0};   // when the gather thread last saw a leaf (latency mode spins only while hot)
   std::atomic<int64_t> gpu_free_at_ns{0};
   std::atomic<uint64_t> ema_wave_ns{0};
@@ -297,6 +300,11 @@ void ug_queue::gather_loop() {
     cudaEventRecord(S.ev_out, s_out);
     {
       std::lock_guard<std::mutex> lk(mu);
+      if (inflight.empty()) {  // nothing was running or queued: the GPU has been idle since the last completion
+        n_launch_idle.fetch_add(1, std::memory_order_relaxed);
+        const int64_t since = last_done_ns.load(std::memory_order_relaxed);
+        if (since > 0) idle_gap_us.fetch_add((uint64_t)std::max<int64_t>(0, (now_ns() - since) / 1000), std::memory_order_relaxed);
+      }
       inflight.push_back(which);
     }
     cv_inflight.notify_one();
@@ -352,6 +360,7 @@ void ug_queue::complete_loop() {
       S.busy = false;
       // re-anchor the estimate: the stream is idle now, or has just started on the other staging buffer's batch
       const int64_t now = now_ns();
+      last_done_ns.store(now, std::memory_order_relaxed);
       gpu_free_at_ns.store(inflight.empty() ? now : now + estimate_ns(st[inflight.front()].n_run), std::memory_order_relaxed);
     }
     cv_free.notify_all();
@@ -541,10 +550,10 @@ int ug_queue_set_compact_priors(ug_queue* q, int on) {
 
 int ug_queue_stats_ex(ug_queue* q, uint64_t* out, int count) {
   if (!q || !out) return -1;
-  const uint64_t v[9] = {q->n_batches.load(), q->n_leaves.load(), q->n_timeouts.load(), q->n_full.load(),
-                         q->n_wave_cut.load(), q->n_failed.load(), q->max_depth.load(), q->n_sleeps.load(),
-                         q->gpu_busy_us.load()};
-  for (int i = 0; i < count && i < 9; ++i) out[i] = v[i];
+  const uint64_t v[11] = {q->n_batches.load(), q->n_leaves.load(), q->n_timeouts.load(), q->n_full.load(),
+                          q->n_wave_cut.load(), q->n_failed.load(), q->max_depth.load(), q->n_sleeps.load(),
+                          q->gpu_busy_us.load(), q->n_launch_idle.load(), q->idle_gap_us.load()};
+  for (int i = 0; i < count && i < 11; ++i) out[i] = v[i];
   return 0;
 }
 

@@ -582,8 +582,8 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   uint64_t batches = 0, leaves = 0, timeouts = 0;
   ug_queue_stats(sh.q, &batches, &leaves, &timeouts);
-  uint64_t qx[9] = {0};
-  ug_queue_stats_ex(sh.q, qx, 9);
+  uint64_t qx[11] = {0};
+  ug_queue_stats_ex(sh.q, qx, 11);
   ug_queue_destroy(sh.q);
   stats->playouts = sh.playouts.load();
   stats->evaluations = leaves;
@@ -606,6 +606,8 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
     stats->max_queue_depth = qx[6];
     stats->gather_sleeps = qx[7];
     stats->gpu_busy_fraction = secs > 0 ? (double)qx[8] * 1e-6 / secs : 0;
+    stats->idle_launches = qx[9];
+    stats->idle_gap_seconds = (double)qx[10] * 1e-6;
   }
   if (moves_out && n_moves_out) {
     const int cap = (cfg.max_moves > 0 ? cfg.max_moves : 2 * 19 * 19) + cfg.prelude_moves;  // row length of moves_out
