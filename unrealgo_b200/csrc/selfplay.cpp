@@ -295,10 +295,11 @@ void reuse_subtree(Game& g, uint32_t child) {
       map_src.push_back(sbase + i);
     }
   }
-  // Copy the kept subtree back into the game's big arrays instead of swapping the vectors: the tree keeps the storage
-  // that was sized and prefaulted for a full move (a swap would leave it in the half-sized scratch arrays, which then
-  // regrow — a fresh 17 MB mapping and its page faults — in the middle of the next search, for every game and move).
-  src.assign_from(dst);
+  // Ping-pong: both trees of a game are sized and prefaulted for a full move, so the swap costs nothing and the next
+  // search never regrows an array (one copy of the kept subtree per move, not two: every game reaches its move
+  // boundary in the same evaluation wave — one leaf per game per wave — so this work arrives in bursts of all games
+  // at once, and on an 8-GPU box that burst is memory-bandwidth-bound).
+  src.swap(dst);
 }
 
 // RemoveVirtualLoss on every node of a finished descent (:847-850): from the leaf up to the root
@@ -402,12 +403,15 @@ void make_move(Game& g, Shared& sh) {
   g.moves.push_back((int16_t)move);
   sh.moves.fetch_add(1, std::memory_order_relaxed);
   sh.nodes.fetch_add(g.tree.size(), std::memory_order_relaxed);
-  if (sh.cfg.reuse_tree && rn && t.n_children[chosen]) reuse_subtree(g, chosen);
-  else new_root(g);
   g.playouts_this_move = 0;
   const int limit = sh.cfg.max_moves > 0 ? sh.cfg.max_moves : 2 * 19 * 19;
-  if (g.root_board.passes >= 2 || g.root_board.move_number - g.first_search_move >= limit ||
-      g.root_board.move_number >= 2 * 19 * 19) {
+  const bool over = g.root_board.passes >= 2 || g.root_board.move_number - g.first_search_move >= limit ||
+                    g.root_board.move_number >= 2 * 19 * 19;
+  if (!over) {  // a finished game needs no tree for a next search
+    if (sh.cfg.reuse_tree && rn && t.n_children[chosen]) reuse_subtree(g, chosen);
+    else new_root(g);
+  }
+  if (over) {
     g.finished = true;
     sh.games_done.fetch_add(1, std::memory_order_relaxed);
     if (sh.cfg.record_dir && !write_game_record(g, sh.cfg)) sh.record_errors.fetch_add(1, std::memory_order_relaxed);
@@ -505,7 +509,7 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
     const size_t cap = (size_t)cfg.playouts_per_move * UG_NUM_MOVES * (cfg.reuse_tree ? 5 : 4) / 4;
     const size_t bytes_per_node = 2 * sizeof(float) + 3 * sizeof(uint32_t) + 2 * sizeof(uint16_t);
     const char* pf = getenv("UGEVAL_SP_PREFAULT");
-    const bool prefault = !(pf && pf[0] == '0') && (double)cap * 1.5 * bytes_per_node * cfg.games < 48e9;
+    const bool prefault = !(pf && pf[0] == '0') && (double)cap * 2.0 * bytes_per_node * cfg.games < 64e9;
     const char* th = getenv("UGEVAL_SP_THP");
     const bool huge = !(th && th[0] == '0');
     std::vector<std::thread> init;
@@ -520,11 +524,11 @@ extern "C" int ug_selfplay_run(ug_eval* h, const ug_selfplay_config* cfg_in, ug_
           g.index = (int)i;
           g.tree.use_vloss = g.scratch.use_vloss = cfg.leaves_per_game > 1;
           g.tree.reserve(cap, huge);
-          if (cfg.reuse_tree) g.scratch.reserve(cap / 2, huge);
+          if (cfg.reuse_tree) g.scratch.reserve(cap, huge);
           if (prefault) {
             g.tree.resize(cap);
             g.tree.clear();
-            if (cfg.reuse_tree) { g.scratch.resize(cap / 2); g.scratch.clear(); }
+            if (cfg.reuse_tree) { g.scratch.resize(cap); g.scratch.clear(); }
           }
           new_root(g);
           // mid-game sample: random legal moves before the first search (see ug_selfplay_config.prelude_moves)
