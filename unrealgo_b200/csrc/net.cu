@@ -1014,7 +1014,7 @@ static int run_planes_common(ug_eval* h, const int8_t* planes, int hwc, int n, d
   cudaStream_t s = h->stream;
   // caller buffers registered with ug_eval_register_host are DMA sources/targets themselves (the reference's
   // EvalBuffer is one fixed allocation, search/UctSearch.h:126-130); anything else goes through pinned staging
-  if (h->is_registered(planes, in_bytes)) {
+  if (n > 32 && h->is_registered(planes, in_bytes)) {  // (small batches: the staged copy is faster, see below)
     cudaMemcpyAsync(h->d_planes.p, planes, in_bytes, cudaMemcpyHostToDevice, s);
   } else {
     memcpy(stage, planes, in_bytes);
