@@ -133,8 +133,10 @@ int ug_eval_set_fp16_range_policy(ug_eval* h, int policy);
 /* Batches of at most max_batch positions run the tower on the small-batch kernel (conv3x3_sb.cu: 128-row x nt-column
  * tiles on many SMs) — the batch sizes the reference's engine issues (1 .. MAX_BATCHES = 16,
  * funcapproximator/DlTFNetworkEvaluator.h:15; search/UctSearch.cpp:183-186).  max_batch 0 disables; nt = output
- * channels per CTA (16/32/64/128, 0 = chosen from the grid size).  Default 32 / 0 (UGEVAL_SB_MAX, UGEVAL_SB_NT); a batch
- * also has to fit one wave of the SMs at 128 channels per CTA (26 positions for 256 filters on 148 SMs). */
+ * channels per tile (16/32/64/128, 0 = chosen from the grid size), plus 256 to force single-CTA tiles or 512 to force
+ * CTA-pair tiles (cta_group::2, 256 rows x nt; nt >= 32) — otherwise chosen from the batch.  Default 32 / 0
+ * (UGEVAL_SB_MAX, UGEVAL_SB_NT, UGEVAL_SB_PAIR=0|1); a batch also has to fit one wave of the SMs at 128 channels per
+ * CTA (26 positions for 256 filters on 148 SMs). */
 int ug_eval_set_small_batch(ug_eval* h, int max_batch, int nt);
 /* carry the residual stream as a hi+lo pair of 16-bit tensors (1) or as one 16-bit tensor (0); numerics knob */
 int ug_eval_set_residual_split(ug_eval* h, int on);

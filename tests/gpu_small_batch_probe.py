@@ -1,7 +1,7 @@
 """Latency of one evaluation at the batch sizes the reference's engine issues (1 .. 16) and a little beyond, on the
 20x256 net: the small-batch tower kernel against the large-batch one, device time (CUDA events inside the library)
 and end to end through DlTFNetworkEvaluator::Evaluate with host buffers.  Run on the GPU box:
-    python tests/gpu_small_batch_probe.py [blocks filters]"""
+    python tests/gpu_small_batch_probe.py [blocks filters] [--pairs]   (--pairs: single-CTA against CTA-pair tiles)"""
 import json
 import sys
 import tempfile
@@ -14,8 +14,9 @@ from unrealgo_b200 import DlTFNetworkEvaluator, synth, tfformat  # noqa: E402
 
 
 def main():
-    blocks = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-    filters = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    blocks = int(args[0]) if len(args) > 0 else 20
+    filters = int(args[1]) if len(args) > 1 else 256
     d = tempfile.mkdtemp(prefix="ug_sb_")
     meta, prefix = tfformat.write_synthetic_checkpoint(d, blocks, filters, seed=20260119)
     ev = DlTFNetworkEvaluator(meta, max_batch=128)
@@ -23,9 +24,14 @@ def main():
     packed = synth.synthetic_packed_positions(128, seed=3)
     planes = synth.packed_to_planes(packed)
     out = {}
-    for n in (1, 2, 4, 8, 16, 24, 32, 48, 64, 96, 128):
+    sizes = (1, 2, 3, 4, 6, 8, 12, 16, 20, 24, 26) if "--pairs" in sys.argv else (1, 2, 4, 8, 16, 24, 32, 48, 64, 96, 128)
+    # nt + 256: single-CTA tiles, nt + 512: CTA-pair tiles (ug_eval_set_small_batch)
+    variants = (("v2", 0, 0), ("sb", 128, 0), ("single", 128, 256), ("pair", 128, 512), ("pair32", 128, 512 + 32),
+                ("pair64", 128, 512 + 64), ("pair128", 128, 512 + 128)) if "--pairs" in sys.argv else \
+               (("v2", 0, 0), ("sb", 128, 0), ("sb16", 128, 16), ("sb32", 128, 32), ("sb64", 128, 64), ("sb128", 128, 128))
+    for n in sizes:
         row = {}
-        for name, sb, nt in (("v2", 0, 0), ("sb", 128, 0), ("sb16", 128, 16), ("sb32", 128, 32), ("sb64", 128, 64), ("sb128", 128, 128)):
+        for name, sb, nt in variants:
             ev.set_small_batch(sb, nt)
             br = ev.bench(packed[:n], 50)
             pol, val = np.zeros((n, 362)), np.zeros(n)

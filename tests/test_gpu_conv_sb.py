@@ -1,5 +1,6 @@
-"""K3/K4 for small batches (conv3x3_sb.cu): 128-row x NT-column tiles, cta_group::1 — the tower kernel for the batch
-sizes the reference's own engine issues (1 .. MAX_BATCHES = 16, funcapproximator/DlTFNetworkEvaluator.h:15).
+"""K3/K4 for small batches (conv3x3_sb.cu): 128-row x NT-column tiles on single CTAs (cta_group::1) or 256-row x
+NT-column tiles on CTA pairs (cta_group::2, each SM stages half of the weights) — the tower kernel for the batch sizes
+the reference's own engine issues (1 .. MAX_BATCHES = 16, funcapproximator/DlTFNetworkEvaluator.h:15).
 
 Unit parity of the raw kernel against an fp32 torch convolution of the same 16-bit operands (same harness and
 tolerances as conv3x3_v2's), then the whole evaluator at n in {1, 7, 16, 24}: within the north-star tolerance of the
@@ -11,6 +12,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ALL = [(r, s) for r in range(3) for s in range(3)]
+SINGLE, PAIR = 256, 512   # added to the tile width: force single-CTA / CTA-pair tiles (otherwise chosen from the batch)
 
 
 def _run(*a, **k):
@@ -19,7 +21,7 @@ def _run(*a, **k):
     assert " bad 0/" in msg and "nonfinite 0" in msg, msg
 
 
-@pytest.mark.parametrize("nt", [16, 32])
+@pytest.mark.parametrize("nt", [16, SINGLE + 32, PAIR + 32])
 @pytest.mark.parametrize("tap", ALL)
 def test_single_tap_exact_padding(tap, nt):
     # n=3: 1083 rows = 8 full 128-row tiles + a partial one; tiles straddle image boundaries
@@ -37,17 +39,29 @@ def test_single_tap_exact_padding(tap, nt):
     (7, 32, 256, False, True, 0),       # stem: 32 stored input channels (SWIZZLE_64B), opens the hi/lo stream
     (9, 192, 192, False, False, 64),
     (24, 256, 256, False, False, 0),    # more CTAs than SMs at every tile width: two waves
+    # CTA pairs: an odd number of 128-row tiles (the last pair's second tile lies wholly past M), every width
+    (1, 256, 256, True, True, PAIR + 32),
+    (5, 256, 256, True, True, PAIR + 64),
+    (16, 256, 256, True, True, PAIR + 128),
+    (2, 128, 128, True, False, PAIR + 128),
+    (7, 32, 256, False, True, PAIR),
+    (9, 192, 192, False, False, PAIR + 64),
+    (24, 256, 256, False, False, PAIR),
+    (16, 256, 256, True, True, SINGLE + 128),
+    (3, 64, 64, False, False, SINGLE),
 ])
 def test_conv_sb_matches_fp32(n, cin, cout, residual, out_lo, nt, f16):
     _run(n, cin, cout, ALL, 0, residual, out_lo, f16=f16, seed=n + cin + cout, split_res=out_lo, nt=nt)
 
 
-def test_rows_past_the_batch_do_not_leak():
-    _run(2, 128, 128, ALL, 0, True, False, n_alloc=4, split_res=False)
+@pytest.mark.parametrize("mode", [SINGLE, PAIR])
+def test_rows_past_the_batch_do_not_leak(mode):
+    _run(2, 128, 128, ALL, 0, True, False, n_alloc=4, split_res=False, nt=mode)
 
 
-def test_no_relu_and_programmatic_launch():
-    _run(3, 64, 128, ALL, 0, False, False, relu=False, pdl=1, iters=3)
+@pytest.mark.parametrize("mode", [SINGLE, PAIR])
+def test_no_relu_and_programmatic_launch(mode):
+    _run(3, 64, 128, ALL, 0, False, False, relu=False, pdl=1, iters=3, nt=mode)
 
 
 def _ev(ckpt, precision, max_batch=64):
@@ -75,7 +89,8 @@ def test_small_batches_through_the_evaluator(small_ckpt, wide_ckpt, positions, w
         pol, val = np.zeros((n, 362)), np.zeros(n)
         assert ev.Evaluate(planes[:n], pol, val, n)     # the reference-facing entry takes the same path
         assert np.array_equal(pol.astype(np.float32), p) and np.array_equal(val.astype(np.float32), v)
-        for nt in (16, 32, 64, 128):                    # every tile width computes the same sums in the same order
+        # every tile width, on single CTAs or CTA pairs, computes the same sums in the same order
+        for nt in (16, 32, 64, 128, SINGLE + 32, SINGLE + 128, PAIR + 32, PAIR + 64, PAIR + 128):
             ev.set_small_batch(24, nt)
             pn, vn = ev.evaluate_packed(packed[:n])
             assert np.array_equal(pn, p) and np.array_equal(vn, v), (n, nt)

@@ -258,3 +258,44 @@ def test_large_batch_is_many_small_batches(small_ckpt):
         ps, vs = ev.evaluate_packed(big[lo:lo + 128])
         assert np.array_equal(ps, p[lo:lo + 128]) and np.array_equal(vs, v[lo:lo + 128]), lo
     ev.close()
+
+
+def test_public_tensor_members_and_data_formats(small_ckpt, positions, capsys):
+    """The members of DlTFNetworkEvaluator besides Evaluate (funcapproximator/DlTFNetworkEvaluator.h:40-52):
+    CreateTensor, both TransformFeature overloads under both DataFormats against the oracle's restatement of
+    .cc:366-412 (the DF_HWC / CHW-planes case is the GPU re-layout kernel), printFeature's text, and Evaluate with
+    DF_CHW — the CHW-ordered buffer read by the graph under {n,19,19,17} dims, as CreateTensor's dims make TensorFlow do."""
+    import oracle
+    from unrealgo_b200 import DF_CHW, DF_HWC, PREC_FP16, DlTFNetworkEvaluator
+    _, planes = positions
+    n = 7
+    chw = planes[:n]
+    hwc = np.ascontiguousarray(chw.transpose(0, 2, 3, 1))
+    ev = _evaluator(small_ckpt, PREC_FP16)
+    t = ev.CreateTensor(n)
+    assert t.shape == (n, 19, 19, 17) and t.dtype == np.bool_ and not t.any()     # .cc:273: dims whatever the format
+    for df in (DF_HWC, DF_CHW):
+        ev.m_dataFormat = df
+        for src, hwc_input in ((chw, False), (hwc, True)):
+            got = ev.TransformFeature(src, n)
+            want = oracle.transform_feature(src, data_format=df, as_bool=True, hwc_input=hwc_input)
+            assert got.shape == (n, 19, 19, 17)
+            assert np.array_equal(got.reshape(-1), want.reshape(-1) != 0), (df, hwc_input)
+    ev.m_dataFormat = DF_HWC
+    ev.printFeature(ev.TransformFeature(chw[:1]))
+    lines = capsys.readouterr().out.split("\n")
+    assert len(lines) == 361 + 2 and lines[0] == " ".join(str(int(v)) for v in hwc[0, 0, 0]) + " "
+    # Evaluate: DF_HWC both overloads agree; DF_CHW == DF_HWC fed the same bytes reinterpreted as [n][19][19][17]
+    p0, v0 = _run_reference_api(ev, chw)
+    p1, v1 = _run_reference_api(ev, hwc)
+    assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
+    reinterpreted = chw.reshape(n, 19, 19, 17)
+    pr, vr = _run_reference_api(ev, reinterpreted)
+    ev2 = DlTFNetworkEvaluator(small_ckpt[0], df=DF_CHW, precision=PREC_FP16, max_batch=128)
+    assert ev2.UpdateCheckPoint(small_ckpt[1])
+    for src in (chw, hwc):
+        pc, vc = _run_reference_api(ev2, src)
+        assert np.array_equal(pc, pr) and np.array_equal(vc, vr)
+    assert not np.array_equal(pr, p0)
+    ev.close()
+    ev2.close()

@@ -34,7 +34,10 @@ def test_reference_uct_board_evaluator_runs_on_ugeval(small_ckpt, positions, tmp
             pol[int(t[1])] = [float(x) for x in t[2:]]
         else:
             flags[t[0]] = int(t[1])
-    assert flags == {"loaded_before": 0, "bad_path_throws": 1, "loaded_after": 1}
+    assert flags == {"loaded_before": 0, "bad_path_throws": 1, "loaded_after": 1,
+                     # the class driven directly, as funcapproximator/test/DlTFTestVariableBatchSize.cc:80-90 does:
+                     "direct_loaded": 1, "direct_checkpoint": 1, "create_tensor": 1, "transform_chw_is_hwc": 1,
+                     "transform_hwc_is_copy": 1, "transform_df_chw": 1, "direct_identical": 1}
     want_p, want_v = GraphOracle(meta, prefix).evaluate_reference(planes[:n], value_transform=1)
     assert np.abs(pol - want_p).max() <= 1e-3 and np.abs(val - want_v).max() <= 5e-3
     ev = DlTFNetworkEvaluator("", feature_input="feature_input", outputs=outs.split(":"), max_batch=512)

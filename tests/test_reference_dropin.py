@@ -31,7 +31,8 @@ def test_reference_call_site_compiles_against_the_overlay_and_binds_only_the_c_a
     syms = [ln.split()[-1] for ln in und.splitlines() if ln.strip()]
     ug = sorted(s for s in syms if s.startswith("ug_"))
     assert ug == ["ug_eval_create", "ug_eval_destroy", "ug_eval_load_checkpoint", "ug_eval_load_graph", "ug_eval_ready",
-                  "ug_eval_run_planes", "ug_eval_set_io", "ug_eval_set_value_transform", "ug_last_error"]
+                  "ug_eval_run_planes", "ug_eval_run_planes_hwc",   # _hwc: Evaluate() under DF_CHW (see the header)
+                  "ug_eval_set_io", "ug_eval_set_value_transform", "ug_last_error"]
     header = open(os.path.join(ROOT, "include", "ugeval.h")).read()
     for s in ug:
         assert re.search(r"\b%s\s*\(" % s, header), s          # every one is a declared entry point

@@ -24,9 +24,18 @@
 // Warp roles (256 threads): 0 = A producer (waits for the previous layer: griddepcontrol.wait), 1 = MMA issuer,
 // 2 = TMEM allocator, 3 = weight producer (starts before the previous layer has finished); then every warp joins the
 // epilogue.
+//
+// PAIR variant (cta_group::2, clusters of two CTAs along M): what bounds the single-CTA kernel from a handful of
+// positions up is what each SM has to pull in from L2 — its A tile plus ALL the weights of its NT columns (n = 16,
+// NT = 128: 86 + 590 KB per CTA at ~50 B/clk).  A CTA pair computes a 256-row x NT tile with one MMA stream issued by
+// the leader: each CTA stages its own 128 rows of A and only HALF of the NT weight rows (the tensor cores of both SMs
+// read both halves), so the weight bytes per SM halve.  Barriers as in conv3x3_v2.cu: both CTAs' TMA loads complete
+// on the leader's full barriers, the leader's tcgen05.commit multicasts to both CTAs' empty / accumulator barriers.
+// Same MMA order per output element, so the results are the same bits as the single-CTA variant's.
 #include <cuda_bf16.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -47,6 +56,7 @@ constexpr int kThreads = 256;
 constexpr int kTapsPerStage = 3;            // filter taps per weight stage
 constexpr int kMaxStages = 12;              // 3 per 64-channel chunk of a 256-channel layer
 constexpr int kBRing = 96 * 1024;
+constexpr int kPairMinTiles = 2;             // auto mode: CTA pairs from this many 128-row tiles up
 constexpr int kMaxEpiSteps = 4;             // 16-column steps per warp: NT = 128 -> 8 steps over two warp groups
 
 template <int CK>
@@ -91,7 +101,7 @@ __device__ __forceinline__ long long globaltimer_ns() {
       args.prof[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (k)] = clock64();                   \
   } while (0)
 
-template <int CK, bool F16>
+template <int CK, bool F16, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const ConvSbArgs args) {
@@ -115,9 +125,15 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int nt = args.nt;
   const int stages = args.stages;
   const int chunks = args.cin / CK;
+  // PAIR: the cluster is two consecutive CTAs along x, i.e. two consecutive 128-row tiles; rank 0 leads
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
   const int m0 = (int)blockIdx.x * kTileM;
   const int n0 = (int)blockIdx.y * nt;
-  const uint32_t tap_bytes = (uint32_t)nt * kRowBytes;   // one filter tap's [NT x CK] weight tile
+  const int nb = PAIR ? nt >> 1 : nt;                    // weight rows this CTA stages per filter tap
+  const int nb0 = n0 + (int)cta_rank * nb;               // ... starting at this output channel
+  const uint32_t tap_bytes = (uint32_t)nb * kRowBytes;   // one filter tap's [nb x CK] weight tile
+  constexpr uint32_t kTxScale = PAIR ? 2u : 1u;          // the leader's full barriers count both CTAs' bytes
 
   if (warp == 0) {
     UG_SB_STAMP(0);
@@ -134,11 +150,24 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<1>(tmem_slot, nt < 32 ? 32u : (uint32_t)nt);
+  if (warp == 2) tmem_alloc<PAIR ? 2 : 1>(tmem_slot, nt < 32 ? 32u : (uint32_t)nt);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if constexpr (PAIR) {
+    // the pair's MMAs address the accumulator of both CTAs with ONE TMEM address: both allocations (same size, into
+    // an SM's empty TMEM — a CTA of this kernel has the SM to itself) must have landed on the same columns
+    if (threadIdx.x == 0) {
+      uint32_t peer_slot, peer_base;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_slot) : "r"(smem_u32(tmem_slot)), "r"(cta_rank ^ 1u));
+      asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(peer_base) : "r"(peer_slot) : "memory");
+      if (peer_base != tmem_base) {
+        printf("ugeval: conv3x3_sb pair: TMEM bases differ (%x vs %x)\n", tmem_base, peer_base);
+        __trap();
+      }
+    }
+  }
   // Programmatic dependent launch: the next layer's CTAs may be scheduled from here on (their prologue and weight
   // loads do not depend on this layer); they read this layer's output only behind their own griddepcontrol.wait.
   pdl_launch_dependents();
@@ -154,8 +183,9 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     UG_SB_STAMP(2);
     for (int j = 0; j < chunks; ++j) {
       if (elected) {
-        mbar_expect_tx(&a_full[j], C::kASlot);
-        tma_load_2d(smA + j * C::kASlot, &tmA, &a_full[j], j * CK, m0 - kHalo);
+        if (leader) mbar_expect_tx(&a_full[j], kTxScale * C::kASlot);
+        if constexpr (PAIR) tma_load_2d_2sm(smA + j * C::kASlot, &tmA, &a_full[j], j * CK, m0 - kHalo);
+        else tma_load_2d(smA + j * C::kASlot, &tmA, &a_full[j], j * CK, m0 - kHalo);
       }
       __syncwarp();
     }
@@ -168,38 +198,43 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int g = 0; g < 9 / kTapsPerStage; ++g) {
         mbar_wait(&b_empty[sb], phb ^ 1);
         if (elected) {
-          mbar_expect_tx(&b_full[sb], kTapsPerStage * tap_bytes);
+          if (leader) mbar_expect_tx(&b_full[sb], kTxScale * kTapsPerStage * tap_bytes);
           uint8_t* dst = smB + (size_t)sb * (kTapsPerStage * tap_bytes);
           for (int u = 0; u < kTapsPerStage; ++u) {
             const int t = g * kTapsPerStage + u;
             const int tap = (t == 0) ? 4 : (t <= 4 ? t - 1 : t);  // centre first, then 0,1,2,3,5,6,7,8
-            for (int i = 0; i < nt; i += 16)
-              tma_load_2d(dst + u * tap_bytes + i * kRowBytes, &tmW, &b_full[sb], tap * args.cin + j * CK, n0 + i);
+            for (int i = 0; i < nb; i += 16) {
+              if constexpr (PAIR)
+                tma_load_2d_2sm(dst + u * tap_bytes + i * kRowBytes, &tmW, &b_full[sb], tap * args.cin + j * CK, nb0 + i);
+              else
+                tma_load_2d(dst + u * tap_bytes + i * kRowBytes, &tmW, &b_full[sb], tap * args.cin + j * CK, nb0 + i);
+            }
           }
         }
         __syncwarp();
         if (++sb == stages) { sb = 0; phb ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (PAIR: the leader issues for both CTAs) =====================
     // One warp issues every MMA of the tile, and at these tile widths an MMA occupies the tensor pipe for only 8 .. 64
     // cycles: the issue loop itself is the critical path of the kernel.  (First version: one mbarrier wait, one mask
     // lookup and ~130 SASS instructions per filter tap — measured 0.2 us per tap, 7.2 of a layer's 10.4 us at n = 1.)
     // Hence: the nine taps fully unrolled with their row shifts as immediates, the lane masks of all taps fetched
     // once per CTA, and one barrier wait / one commit per stage of three taps (12 MMAs).
-    const uint32_t idesc = make_idesc_16(kTileM, nt, F16 ? 1 : 0);
+    constexpr int kMaskWords = PAIR ? 8 : 4;   // 32 rows each; PAIR: words 4-7 are the peer CTA's rows
+    const uint32_t idesc = make_idesc_16(PAIR ? 2 * kTileM : kTileM, nt, F16 ? 1 : 0);
     // pixel-in-image index of the tile's first row; the lane mask of 32 consecutive rows depends only on
     // (tap, that index mod 361)
     const int q0 = m0 % kPix;
-    uint32_t msk[9][4];
+    uint32_t msk[9][8];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
+      for (int w = 0; w < 8; ++w) {
         int q = q0 + 32 * w;
-        if (q >= kPix) q -= kPix;  // q0 < 361 and 32*w <= 96
-        msk[tap][w] = c_edge_mask_sb[tap][q];
+        if (q >= kPix) q -= kPix;  // q0 < 361 and 32*w <= 224
+        msk[tap][w] = w < kMaskWords ? c_edge_mask_sb[tap][q] : 0u;
       }
     const uint32_t tap_desc_step = tap_bytes >> 4;  // descriptor start-address units (16 B) between two taps of a stage
     int sb = 0;
@@ -223,22 +258,27 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int shift = kHalo + (tap / 3 - 1) * kBoard + (tap % 3 - 1);  // rows: a compile-time constant
             const uint64_t adesc = adesc0 + (uint64_t)(shift * (kRowBytes / 16));
             const uint64_t bdesc = bdesc0 + (uint64_t)(u * tap_desc_step);
-            const uint32_t m[8] = {msk[tap][0], msk[tap][1], msk[tap][2], msk[tap][3], 0u, 0u, 0u, 0u};
 #pragma unroll
             for (int k = 0; k < kMmaPerStep; ++k) {
               if (tap == 4)  // the centre tap never needs a mask; it goes first and initialises the accumulator
-                umma_f16<1>(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((j | k) != 0));
+                umma_f16<PAIR ? 2 : 1>(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((j | k) != 0));
+              else if constexpr (PAIR)
+                umma_f16_2sm_masked(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u, msk[tap]);
               else
-                umma_f16_1sm_masked(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u, m);
+                umma_f16_1sm_masked(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u, msk[tap]);
             }
           }
-          umma_commit(&b_empty[sb]);
+          if constexpr (PAIR) umma_commit_2sm(&b_empty[sb], 3);  // frees the stage in both CTAs
+          else umma_commit(&b_empty[sb]);
         }
         __syncwarp();
         if (++sb == stages) { sb = 0; phb ^= 1; }
       }
     }
-    if (elected) umma_commit(acc_full);
+    if (elected) {
+      if constexpr (PAIR) umma_commit_2sm(acc_full, 3);
+      else umma_commit(acc_full);
+    }
     __syncwarp();
     UG_SB_STAMP(5);
   }
@@ -341,8 +381,9 @@ conv3x3_sb_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (warp == 4) UG_SB_STAMP(7);
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<1>(tmem_base, nt < 32 ? 32u : (uint32_t)nt);
+  // PAIR: neither CTA may leave (free its shared memory, barriers, TMEM) while the other can still touch them
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<PAIR ? 2 : 1>(tmem_base, nt < 32 ? 32u : (uint32_t)nt);
   if (warp == 0) {
     UG_SB_STAMP(10);
     if (args.prof != nullptr && lane == 0)
@@ -378,10 +419,13 @@ bool upload_masks(int device) {
   return true;
 }
 
-template <int CK, bool F16>
+template <int CK, bool F16, bool PAIR>
 cudaError_t launch_sb(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvSbArgs& a, cudaStream_t stream) {
-  auto kfn = conv3x3_sb_kernel<CK, F16>;
-  constexpr int smem = SbCfg<CK>::kSmem;
+  auto kfn = conv3x3_sb_kernel<CK, F16, PAIR>;
+  // PAIR: more than half of an SM's shared memory even for the small stem configuration, so that two CTAs never share
+  // an SM — the pair's MMAs address both CTAs' accumulators with one TMEM address, which needs both allocations to
+  // start at the same column (checked in the kernel)
+  constexpr int smem = (PAIR && SbCfg<CK>::kSmem < 117 * 1024) ? 117 * 1024 : SbCfg<CK>::kSmem;
   static std::atomic<uint64_t> attr_done{0};  // function attributes are per device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -390,50 +434,87 @@ cudaError_t launch_sb(const CUtensorMap& tmA, const CUtensorMap& tmW, const Conv
     if (e != cudaSuccess) return e;
     attr_done.fetch_or(1ull << (dev & 63), std::memory_order_release);
   }
+  unsigned m_tiles = (unsigned)((a.M + kTileM - 1) / kTileM);
+  if (PAIR) m_tiles = (m_tiles + 1u) & ~1u;  // whole pairs: the odd tile's partner computes rows past M and stores nothing
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)((a.M + kTileM - 1) / kTileM), (unsigned)(a.cout / a.nt));
+  cfg.gridDim = dim3(m_tiles, (unsigned)(a.cout / a.nt));
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (PAIR) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (a.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = a.pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kfn, tmA, tmW, a);
+}
+
+template <int CK, bool F16>
+cudaError_t dispatch_sb(const CUtensorMap& tmA, const CUtensorMap& tmW, const ConvSbArgs& a, cudaStream_t stream) {
+  return a.pair ? launch_sb<CK, F16, true>(tmA, tmW, a, stream) : launch_sb<CK, F16, false>(tmA, tmW, a, stream);
+}
+
+// CTAs of the grid for tile width nt
+int grid_ctas(int m_tiles, int cout, int nt, bool pair) {
+  return (pair ? (m_tiles + 1) / 2 * 2 : m_tiles) * (cout / nt);
 }
 
 }  // namespace
 
 bool conv3x3_sb_prepare(int device) { return upload_masks(device); }
 
-int conv3x3_sb_pick_nt(int M, int cout, int sms) {
+int conv3x3_sb_pick_nt(int M, int cout, int sms, int pair) {
   const int m_tiles = (M + kTileM - 1) / kTileM;
   // the smallest tile width (largest grid) that still fits one wave; 16-column tiles only pay their 144 tiny MMAs
-  // back when nothing else fills the machine, so 32 is the floor unless asked for explicitly
+  // back when nothing else fills the machine, so 32 is the floor unless asked for explicitly (and a CTA pair stages
+  // nt / 2 weight rows per CTA in 16-row TMA boxes: 32 is its hard floor)
   for (int nt = 32; nt <= 128; nt <<= 1)
-    if (cout % nt == 0 && m_tiles * (cout / nt) <= sms) return nt;
-  for (int nt = 128; nt >= 16; nt >>= 1)
+    if (cout % nt == 0 && grid_ctas(m_tiles, cout, nt, pair != 0) <= sms) return nt;
+  for (int nt = 128; nt >= (pair ? 32 : 16); nt >>= 1)
     if (cout % nt == 0) return nt;
   return 0;
+}
+
+int conv3x3_sb_pick_pair(int M, int cout) {
+  // A CTA pair halves the weight bytes each SM pulls from L2 but spends two SMs per 256 rows even when the second
+  // tile is mostly (or wholly) past M; see DESIGN.md 5b for the measured crossover.
+  static const int min_tiles = [] {
+    const char* e = getenv("UGEVAL_SB_PAIR_MIN_TILES");
+    return e && atoi(e) > 0 ? atoi(e) : kPairMinTiles;
+  }();
+  return cout % 32 == 0 && (M + kTileM - 1) / kTileM >= min_tiles ? 1 : 0;
 }
 
 cudaError_t conv3x3_sb_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, ConvSbArgs a, int ck, int device, int sms,
                               cudaStream_t stream) {
   if (ck != 64 && ck != 32) return cudaErrorInvalidValue;
   if (a.cin % ck != 0 || a.cin / ck > (ck == 64 ? 4 : 1)) return cudaErrorInvalidValue;
+  if (a.pair < 0) a.pair = conv3x3_sb_pick_pair(a.M, a.cout);
   // a forced width that does not divide this layer's channel count (a narrow net) falls back to the automatic choice
-  if (a.nt == 0 || (a.nt > 0 && a.cout % a.nt != 0)) a.nt = conv3x3_sb_pick_nt(a.M, a.cout, sms);
+  if (a.nt == 0 || (a.nt > 0 && a.cout % a.nt != 0)) a.nt = conv3x3_sb_pick_nt(a.M, a.cout, sms, a.pair);
+  if (a.pair && a.nt == 16) a.pair = 0;  // 8 weight rows per CTA: below the TMA box
   if (a.nt != 16 && a.nt != 32 && a.nt != 64 && a.nt != 128) return cudaErrorInvalidValue;
   if (a.cout % a.nt != 0 || a.M <= 0 || !a.out_hi || !a.bias) return cudaErrorInvalidValue;
   if (a.res_lo && !a.res_hi) return cudaErrorInvalidValue;
   if (!upload_masks(device)) return cudaErrorUnknown;  // no-op after conv3x3_sb_prepare()
+  const int nb = a.pair ? a.nt / 2 : a.nt;                       // weight rows a CTA stages per tap
   const int need = (9 / kTapsPerStage) * (a.cin / ck);          // stages a tile consumes
-  const int fit = kBRing / (kTapsPerStage * a.nt * ck * 2);      // stages the ring holds (>= 2: NT = 128 -> 48 KB each)
+  const int fit = kBRing / (kTapsPerStage * nb * ck * 2);        // stages the ring holds (>= 2: 128 rows -> 48 KB each)
   a.stages = fit < need ? fit : need;
   if (a.stages > kMaxStages) a.stages = kMaxStages;
-  if (ck == 64) return a.f16 ? launch_sb<64, true>(tmA, tmW, a, stream) : launch_sb<64, false>(tmA, tmW, a, stream);
-  return a.f16 ? launch_sb<32, true>(tmA, tmW, a, stream) : launch_sb<32, false>(tmA, tmW, a, stream);
+  if (ck == 64) return a.f16 ? dispatch_sb<64, true>(tmA, tmW, a, stream) : dispatch_sb<64, false>(tmA, tmW, a, stream);
+  return a.f16 ? dispatch_sb<32, true>(tmA, tmW, a, stream) : dispatch_sb<32, false>(tmA, tmW, a, stream);
 }
 
 }  // namespace ug

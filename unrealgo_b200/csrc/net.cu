@@ -596,6 +596,7 @@ int ug_eval::enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, con
   a.pdl = use_pdl ? 1 : 0;
   a.sat_count = d_sat.as<unsigned long long>();
   a.nt = sb_nt;
+  a.pair = sb_pair;
   a.cin = kCinPad;
   a.bias = W.convs[0].bias_tc.as<float>();
   a.out_hi = d_s_hi[0].p;
@@ -687,7 +688,7 @@ int ug_eval::enqueue(Src kind, const void* d_src, int n, const uint32_t* d_leg, 
   if (!use_graphs) return enqueue_raw(kind, d_src, n, d_leg, vt, d_pol, d_val, s, compact);
   const GraphKey key((int)kind, n, d_src, (const void*)d_leg, (const void*)d_pol, (const void*)d_val, vt,
                      conv_ctas * 4 + precision + (resid_split ? 8192 : 0) + conv_impl * 16384 + (use_pdl ? 65536 : 0) + (fuse_heads ? 131072 : 0) + (tile_deps ? 262144 : 0) + (debug_stop + 1) * 16 +
-                         (use_small_batch(n) ? (1 << 19) + (sb_nt << 20) : 0) + (compact ? (1 << 28) : 0));
+                         (use_small_batch(n) ? (1 << 19) + (sb_nt << 20) + ((sb_pair + 1) << 29) : 0) + (compact ? (1 << 28) : 0));
   auto it = graphs.find(key);
   if (it == graphs.end()) {
     if (graphs.size() > 1024) drop_graphs();
@@ -761,6 +762,8 @@ ug_eval* ug_eval_create(int device, int precision, int max_batch) {
     const int v = atoi(sn);
     if (v == 16 || v == 32 || v == 64 || v == 128) h->sb_nt = v;
   }
+  const char* sp = getenv("UGEVAL_SB_PAIR");
+  if (sp && (sp[0] == '0' || sp[0] == '1')) h->sb_pair = sp[0] - '0';
   const char* rs = getenv("UGEVAL_RESID_SPLIT");
   if (rs && (rs[0] == '0' || rs[0] == '1')) h->resid_split = rs[0] == '1';
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -949,9 +952,13 @@ int ug_eval_set_fp16_range_policy(ug_eval* h, int policy) {
 }
 
 int ug_eval_set_small_batch(ug_eval* h, int max_batch, int nt) {
-  if (!h || max_batch < 0 || (nt != 0 && nt != 16 && nt != 32 && nt != 64 && nt != 128)) return -1;
+  const int width = nt & 0xff, mode = nt >> 8;  // mode: 0 = choose, 1 = single CTAs, 2 = CTA pairs
+  if (!h || max_batch < 0 || nt < 0 || mode > 2 || (width != 0 && width != 16 && width != 32 && width != 64 && width != 128))
+    return -1;
+  if (mode == 2 && width == 16) return -1;  // a pair stages nt / 2 weight rows per CTA in 16-row TMA boxes
   h->sb_max_batch = max_batch;
-  h->sb_nt = nt;
+  h->sb_nt = width;
+  h->sb_pair = mode - 1;
   return 0;
 }
 
@@ -1271,7 +1278,8 @@ int ug_k_conv3x3_sb(int device, const void* d_in, const void* d_w, const float* 
   a.cout = cout;
   a.relu = relu;
   a.f16 = f16;
-  a.nt = nt;
+  a.nt = nt & 0xff;
+  a.pair = (nt >> 8) - 1;  // as ug_eval_set_small_batch: +256 = single CTAs, +512 = CTA pairs, else the launcher chooses
   a.pdl = pdl;
   cudaStream_t s = nullptr;
   cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);

@@ -91,8 +91,11 @@ struct ug_eval {
   // Batches of up to sb_max_batch positions run the tower on conv3x3_sb.cu (128 x NT tiles over many SMs) instead of
   // conv3x3_v2.cu (256 x 256 CTA-pair tiles): the batch sizes the reference's own engine issues (1 .. 16).
   // UGEVAL_SB_MAX / ug_eval_set_small_batch_max; 0 disables.  sb_nt: tile width override (0 = from the grid size).
+  // sb_pair: 1 = CTA pairs (cta_group::2: each SM stages half of the weights), 0 = single CTAs, -1 = chosen from the
+  // batch (UGEVAL_SB_PAIR=0|1 forces).
   int sb_max_batch = 32;
   int sb_nt = 0;
+  int sb_pair = 0;   // TODO(after the GPU measurement): -1
   bool resid_split = true;  // carry the residual stream as hi + lo 16-bit pair (numerics)
   int value_transform = UG_TR_IDENTITY;
   bool use_graphs = true;

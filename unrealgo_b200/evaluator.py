@@ -154,9 +154,10 @@ class DlTFNetworkEvaluator:
             raise ValueError("policy: 0/'auto', 1/'refuse', 2/'ignore', 3/'bf16'")
 
     def set_small_batch(self, max_batch, nt=0):
-        """batches <= max_batch run the small-batch tower kernel (0 disables); nt = output channels per CTA (0 = auto)"""
+        """batches <= max_batch run the small-batch tower kernel (0 disables); nt = output channels per tile (0 = auto),
+        + 256 to force single-CTA tiles, + 512 to force CTA-pair tiles (nt >= 32)"""
         if self._lib.ug_eval_set_small_batch(self._h, max_batch, nt) != 0:
-            raise ValueError("max_batch >= 0, nt in (0, 16, 32, 64, 128)")
+            raise ValueError("max_batch >= 0, nt in (0, 16, 32, 64, 128) [+ 256 | + 512]")
 
     def set_residual_split(self, on):
         self._lib.ug_eval_set_residual_split(self._h, 1 if on else 0)
@@ -167,14 +168,59 @@ class DlTFNetworkEvaluator:
             raise RuntimeError("no network loaded")
         return {f: getattr(ni, f) for f, _ in _lib.NetInfo._fields_}
 
-    def Evaluate(self, feature, policies_, value_, numBatches=None):
-        """feature: int8 [n][17][19][19] (or [n][19][19][17]); policies_: float64 [n][362]; value_: float64 [n].
-        As in the reference a failed run logs and leaves the outputs untouched (.cc:315-317); returns bool."""
+    @staticmethod
+    def _is_hwc(feature):
+        return feature.ndim == 4 and feature.shape[-1] == NUM_PLANES and feature.shape[1] == 19
+
+    def CreateTensor(self, batches):
+        """.cc:271-284: a tensor shaped {batches, 19, 19, 17} whatever m_dataFormat says (the device workspace itself
+        is sized once per architecture); kept per batch size like m_input_tensors[batches - 1]"""
+        if not hasattr(self, "m_input_tensors"):
+            self.m_input_tensors = {}
+        if batches not in self.m_input_tensors:
+            self.m_input_tensors[batches] = np.zeros((batches, 19, 19, NUM_PLANES), np.bool_)
+        return self.m_input_tensors[batches]
+
+    def TransformFeature(self, feature, numBatches=None):
+        """.cc:366-412, both overloads: fills and returns the bool tensor Session::Run would be fed.  DF_HWC: the NHWC
+        re-layout of the planes (CHW planes go through the GPU kernel Evaluate() runs, ug_transform_planes); DF_CHW: the
+        planes' CHW order written under the same {n, 19, 19, 17} dims, as the reference does."""
         feature = np.ascontiguousarray(feature, np.int8)
         n = feature.shape[0] if numBatches is None else numBatches
-        hwc = feature.ndim == 4 and feature.shape[-1] == NUM_PLANES and feature.shape[1] == 19
+        t = self.CreateTensor(n)
+        flat = t.reshape(-1)
+        if self._is_hwc(feature):
+            src = feature[:n] if self.m_dataFormat == DF_HWC else feature[:n].transpose(0, 3, 1, 2)
+            flat[:] = np.ascontiguousarray(src).reshape(-1) != 0
+        elif self.m_dataFormat == DF_HWC:
+            out = np.empty((n, 19, 19, NUM_PLANES), np.int8)
+            if self._lib.ug_transform_planes(self._h, feature.ctypes.data, n, out.ctypes.data) != 0:
+                raise RuntimeError(self._err())
+            flat[:] = out.reshape(-1) != 0
+        else:
+            flat[:] = feature[:n].reshape(-1) != 0
+        return t
+
+    @staticmethod
+    def printFeature(data):
+        """.cc:353-363"""
+        d = np.asarray(data).reshape(-1)[:19 * 19 * NUM_PLANES].reshape(19 * 19, NUM_PLANES)
+        print("\n".join(" ".join(str(int(v)) for v in row) + " " for row in d) + "\n")
+
+    def Evaluate(self, feature, policies_, value_, numBatches=None):
+        """feature: int8 [n][17][19][19] (or [n][19][19][17]); policies_: float64 [n][362]; value_: float64 [n].
+        As in the reference a failed run logs and leaves the outputs untouched (.cc:315-317); returns bool.
+        With m_dataFormat == DF_CHW the graph is handed the CHW-ordered buffer under NHWC dims, as the reference's
+        TransformFeature + CreateTensor do (no reference caller passes DF_CHW, search/UctBoardEvaluator.cpp:6)."""
+        feature = np.ascontiguousarray(feature, np.int8)
+        n = feature.shape[0] if numBatches is None else numBatches
+        hwc = self._is_hwc(feature)
         assert policies_.dtype == np.float64 and value_.dtype == np.float64
         assert policies_.flags.c_contiguous and value_.flags.c_contiguous
+        if self.m_dataFormat != DF_HWC:
+            if hwc:
+                feature = np.ascontiguousarray(feature[:n].transpose(0, 3, 1, 2))
+            hwc = True   # the buffer is read as [n][19][19][17] whatever order it was written in
         fn = self._lib.ug_eval_run_planes_hwc if hwc else self._lib.ug_eval_run_planes
         rc = fn(self._h, feature.ctypes.data, n, policies_.ctypes.data, value_.ctypes.data)
         if rc != 0:

@@ -9,14 +9,21 @@
 //   LoadGraph                                 :77-83    ug_eval_load_graph   (<0 -> throw std::runtime_error)
 //   UpdateCheckPoint                          :230-236  ug_eval_load_checkpoint
 //   MetaGraphLoaded                           :239-241  ug_eval_ready
+//   CreateTensor                              :271-284  (device workspace sized once per architecture; host tensor here)
+//   TransformFeature (CHW / HWC overloads)    :366-412  ug_transform_planes (the GPU kernel Evaluate runs) / host cast
+//   printFeature                              :353-363  same text
 //   Evaluate (CHW / HWC overloads)            :287-352  ug_eval_run_planes / ug_eval_run_planes_hwc
 //   ~DlTFNetworkEvaluator                     :67-69    ug_eval_destroy
+// Not provided: WritePbText / GetMetaGraph (:244-252) hand out TensorFlow's own protobuf objects; their only callers
+// are the graph-printing programs under funcapproximator/test/, which are not on the evaluation path.
 #ifndef UGEVAL_HOST_DLTFNETWORKEVALUATOR_H
 #define UGEVAL_HOST_DLTFNETWORKEVALUATOR_H
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -89,17 +96,87 @@ class DlTFNetworkEvaluator {
   }
   bool MetaGraphLoaded() { return ug_eval_ready(m_h) != 0; }
 
-  // value_transform comes from the DlConfig singleton, as at DlTFNetworkEvaluator.cc:300
+  // .cc:271-284.  The reference allocates one TensorFlow tensor per batch size, always shaped {batches, 19, 19, 17}
+  // whatever m_dataFormat says, and keeps it for good.  The device workspace here is sized once per architecture
+  // (ug_eval_load_checkpoint); what CreateTensor keeps is the host-side tensor TransformFeature() fills.
+  void CreateTensor(int batches) {
+    if (batches < 1 || batches > UGEVAL_MAX_BATCH) return;
+    std::unique_ptr<T[]>& t = m_input_tensors[batches];
+    if (!t) t.reset(new T[(size_t)batches * FEATURE_SIZE]());  // value-initialised, like a fresh tensor
+  }
+  // .cc:366-389: data[GetOffset(...)] = (T)feature[b][depth][i][j].  DF_HWC is the NHWC re-layout — done by the same
+  // GPU kernel Evaluate() runs (planes_to_nhwc_kernel through ug_transform_planes); DF_CHW keeps the planes' own order.
+  void TransformFeature(char feature[][NUM_MAPS][BD_SIZE][BD_SIZE], int numBatches = MAX_BATCHES) {
+    CreateTensor(numBatches);
+    if (numBatches < 1 || numBatches > UGEVAL_MAX_BATCH) return;
+    T* data = m_input_tensors[numBatches].get();
+    const size_t total = (size_t)numBatches * FEATURE_SIZE;
+    const char* flat = &feature[0][0][0][0];
+    if (m_dataFormat == DF_HWC) {
+      std::vector<int8_t> hwc(total);
+      if (ug_transform_planes(m_h, reinterpret_cast<const int8_t*>(flat), numBatches, hwc.data()) != 0) {
+        fprintf(stderr, "TransformFeature failed: %s\n", ug_last_error(m_h));
+        return;
+      }
+      for (size_t i = 0; i < total; ++i) data[i] = (T)hwc[i];
+    } else {
+      for (size_t i = 0; i < total; ++i) data[i] = (T)flat[i];
+    }
+  }
+  // .cc:391-412: the same for planes that already are [b][i][j][depth]
+  void TransformFeature(char feature[][BD_SIZE][BD_SIZE][NUM_MAPS], int numBatches = MAX_BATCHES) {
+    CreateTensor(numBatches);
+    if (numBatches < 1 || numBatches > UGEVAL_MAX_BATCH) return;
+    T* data = m_input_tensors[numBatches].get();
+    const char* flat = &feature[0][0][0][0];
+    if (m_dataFormat == DF_HWC) {
+      for (size_t i = 0; i < (size_t)numBatches * FEATURE_SIZE; ++i) data[i] = (T)flat[i];
+    } else {
+      for (int b = 0; b < numBatches; ++b)
+        for (int p = 0; p < BD_SIZE * BD_SIZE; ++p)
+          for (int d = 0; d < NUM_MAPS; ++d)
+            data[((size_t)b * NUM_MAPS + d) * BD_SIZE * BD_SIZE + p] = (T)flat[((size_t)b * BD_SIZE * BD_SIZE + p) * NUM_MAPS + d];
+    }
+  }
+  // extension: the tensor the last CreateTensor/TransformFeature(.., batches) left (m_input_tensors[batches - 1] there)
+  const T* InputTensor(int batches) const {
+    auto it = m_input_tensors.find(batches);
+    return it == m_input_tensors.end() ? nullptr : it->second.get();
+  }
+  void printFeature(T data[]) {  // .cc:353-363
+    for (int i = 0; i < BD_SIZE * BD_SIZE; ++i) {
+      for (int j = 0; j < NUM_MAPS; ++j) printf("%d ", (int)data[i * NUM_MAPS + j]);
+      printf("\n");
+    }
+    printf("\n");
+  }
+
+  // value_transform comes from the DlConfig singleton, as at DlTFNetworkEvaluator.cc:300.  The graph always reads its
+  // placeholder as [n][19][19][17] (CreateTensor's dims): with DF_HWC that is the NHWC re-layout of the planes; with
+  // DF_CHW the reference hands TensorFlow the CHW-ordered buffer under those same dims, and so does this — no caller in
+  // the reference passes DF_CHW (search/UctBoardEvaluator.cpp:6), it is kept for the interface's sake.
   void Evaluate(char feature[][NUM_MAPS][BD_SIZE][BD_SIZE], double actions_[][GO_MAX_MOVES], double value_[],
                 int numBatches = MAX_BATCHES) {
     ug_eval_set_value_transform(m_h, (int)DlConfig::GetInstance().get_value_transform());
-    const int rc = ug_eval_run_planes(m_h, reinterpret_cast<const int8_t*>(feature), numBatches, &actions_[0][0], value_);
+    const int8_t* flat = reinterpret_cast<const int8_t*>(feature);
+    const int rc = m_dataFormat == DF_HWC ? ug_eval_run_planes(m_h, flat, numBatches, &actions_[0][0], value_)
+                                          : ug_eval_run_planes_hwc(m_h, flat, numBatches, &actions_[0][0], value_);
     if (rc != 0) fprintf(stderr, "Running model failed: %s\n", ug_last_error(m_h));  // outputs untouched (.cc:315-317)
   }
   void Evaluate(char feature[][BD_SIZE][BD_SIZE][NUM_MAPS], double actions_[][GO_MAX_MOVES], double value_[],
                 int batch_size = MAX_BATCHES) {
     ug_eval_set_value_transform(m_h, (int)DlConfig::GetInstance().get_value_transform());
-    const int rc = ug_eval_run_planes_hwc(m_h, reinterpret_cast<const int8_t*>(feature), batch_size, &actions_[0][0], value_);
+    const int8_t* flat = reinterpret_cast<const int8_t*>(feature);
+    std::vector<int8_t> chw;
+    if (m_dataFormat != DF_HWC && batch_size >= 1 && batch_size <= UGEVAL_MAX_BATCH) {  // see TransformFeature
+      chw.resize((size_t)batch_size * FEATURE_SIZE);
+      for (int b = 0; b < batch_size; ++b)
+        for (int p = 0; p < BD_SIZE * BD_SIZE; ++p)
+          for (int d = 0; d < NUM_MAPS; ++d)
+            chw[((size_t)b * NUM_MAPS + d) * BD_SIZE * BD_SIZE + p] = flat[((size_t)b * BD_SIZE * BD_SIZE + p) * NUM_MAPS + d];
+      flat = chw.data();
+    }
+    const int rc = ug_eval_run_planes_hwc(m_h, flat, batch_size, &actions_[0][0], value_);
     if (rc != 0) fprintf(stderr, "Running model failed: %s\n", ug_last_error(m_h));
   }
 
@@ -122,6 +199,7 @@ class DlTFNetworkEvaluator {
   }
   DataFormat m_dataFormat;
   ug_eval* m_h;
+  std::map<int, std::unique_ptr<T[]>> m_input_tensors;  // by batch size (the reference: Tensor m_input_tensors[MAX_BATCHES])
 };
 
 }  // namespace tensorflow
