@@ -124,13 +124,18 @@ if __name__ == "__main__":
     if which == "sbprof":
         # per-CTA time stamps of a chain of identical launches: where do the ~10 us per layer go at n = 1?
         import numpy as np
-        for n, nt in ((1, 32), (1, 16), (16, 128)):
+        # nt + 256: single-CTA tiles, nt + 512: CTA-pair tiles
+        for n, nt in ((1, 256 + 32), (1, 512 + 32), (1, 16), (16, 256 + 128), (16, 512 + 128)):
             iters = 12
             prof = torch.zeros(iters, 148, 16, dtype=torch.int64, device="cuda")
             msg = run(n, 256, 256, ALL, 0, True, True, impl="sb", nt=nt, pdl=1, iters=iters, sb_prof=prof)
             p = prof.cpu().numpy().astype(np.float64)
-            ctas = ((n * 361 + 127) // 128) * (256 // nt)
-            p = p[2:, :ctas]   # skip the first launches
+            m_tiles = (n * 361 + 127) // 128
+            ctas = ((m_tiles + 1) // 2 * 2 if nt & 512 else m_tiles) * (256 // (nt & 255))
+            gx = (m_tiles + 1) // 2 * 2 if nt & 512 else m_tiles
+            # CTA pairs: the MMA-issue stamps exist in the leader (even blockIdx.x) only
+            sel = [i for i in range(ctas) if not (nt & 512) or (i % gx) % 2 == 0]
+            p = p[2:, sel]   # skip the first launches
             clk = lambda a, b: (p[:, :, b] - p[:, :, a])
             ghz = 1.9
             names = [("prologue (start -> roles)", 0, 1), ("pdl_wait", 1, 2), ("wait -> first A chunk", 2, 3),

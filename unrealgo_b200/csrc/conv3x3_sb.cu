@@ -56,7 +56,7 @@ constexpr int kThreads = 256;
 constexpr int kTapsPerStage = 3;            // filter taps per weight stage
 constexpr int kMaxStages = 12;              // 3 per 64-channel chunk of a 256-channel layer
 constexpr int kBRing = 96 * 1024;
-constexpr int kPairMinTiles = 2;             // auto mode: CTA pairs from this many 128-row tiles up
+constexpr int kPairMaxFewTiles = 6;          // auto mode: CTA pairs up to this many 128-row tiles (two positions) ...
 constexpr int kMaxEpiSteps = 4;             // 16-column steps per warp: NT = 128 -> 8 steps over two warp groups
 
 template <int CK>
@@ -486,21 +486,27 @@ int conv3x3_sb_pick_nt(int M, int cout, int sms, int pair) {
   return 0;
 }
 
-int conv3x3_sb_pick_pair(int M, int cout) {
+int conv3x3_sb_pick_pair(int M, int cout, int sms) {
   // A CTA pair halves the weight bytes each SM pulls from L2 but spends two SMs per 256 rows even when the second
-  // tile is mostly (or wholly) past M; see DESIGN.md 5b for the measured crossover.
-  static const int min_tiles = [] {
-    const char* e = getenv("UGEVAL_SB_PAIR_MIN_TILES");
-    return e && atoi(e) > 0 ? atoi(e) : kPairMinTiles;
+  // tile is mostly (or wholly) past M.  Measured on the 20x256 net (tests/gpu_small_batch_probe.py
+  // --pairs): pairs win 5 % at one or two positions (few tiles: nothing else wants the SMs) and 5-9 % from the batch
+  // size at which single-CTA tiles have to be 128 columns wide (n >= 14 for 256 filters); in between single CTAs at
+  // 32 / 64 columns are 1-6 % faster.
+  static const int force = [] {
+    const char* e = getenv("UGEVAL_SB_PAIR_MIN_TILES");   // experiments: pairs from this many tiles up, whatever else
+    return e ? atoi(e) : 0;
   }();
-  return cout % 32 == 0 && (M + kTileM - 1) / kTileM >= min_tiles ? 1 : 0;
+  if (cout % 32 != 0) return 0;
+  const int m_tiles = (M + kTileM - 1) / kTileM;
+  if (force > 0) return m_tiles >= force ? 1 : 0;
+  return m_tiles <= kPairMaxFewTiles || conv3x3_sb_pick_nt(M, cout, sms, 0) >= 128 ? 1 : 0;
 }
 
 cudaError_t conv3x3_sb_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, ConvSbArgs a, int ck, int device, int sms,
                               cudaStream_t stream) {
   if (ck != 64 && ck != 32) return cudaErrorInvalidValue;
   if (a.cin % ck != 0 || a.cin / ck > (ck == 64 ? 4 : 1)) return cudaErrorInvalidValue;
-  if (a.pair < 0) a.pair = conv3x3_sb_pick_pair(a.M, a.cout);
+  if (a.pair < 0) a.pair = conv3x3_sb_pick_pair(a.M, a.cout, sms);
   // a forced width that does not divide this layer's channel count (a narrow net) falls back to the automatic choice
   if (a.nt == 0 || (a.nt > 0 && a.cout % a.nt != 0)) a.nt = conv3x3_sb_pick_nt(a.M, a.cout, sms, a.pair);
   if (a.pair && a.nt == 16) a.pair = 0;  // 8 weight rows per CTA: below the TMA box

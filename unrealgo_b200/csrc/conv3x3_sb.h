@@ -34,7 +34,7 @@ cudaError_t conv3x3_sb_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, Co
 // output channels per tile the launcher would pick for M rows (largest grid that still fits one wave of `sms` CTAs)
 int conv3x3_sb_pick_nt(int M, int cout, int sms, int pair);
 // 1 when the launcher's automatic choice for M rows is the CTA-pair variant
-int conv3x3_sb_pick_pair(int M, int cout);
+int conv3x3_sb_pick_pair(int M, int cout, int sms);
 // uploads the lane-mask table for `device`: call once outside any stream capture
 bool conv3x3_sb_prepare(int device);
 

@@ -95,7 +95,7 @@ struct ug_eval {
   // batch (UGEVAL_SB_PAIR=0|1 forces).
   int sb_max_batch = 32;
   int sb_nt = 0;
-  int sb_pair = 0;   // TODO(after the GPU measurement): -1
+  int sb_pair = -1;
   bool resid_split = true;  // carry the residual stream as hi + lo 16-bit pair (numerics)
   int value_transform = UG_TR_IDENTITY;
   bool use_graphs = true;

@@ -267,13 +267,6 @@ class DlTFNetworkEvaluator:
             raise RuntimeError(self._err())
         return out
 
-    def TransformFeature(self, feature):
-        feature = np.ascontiguousarray(feature, np.int8)
-        out = np.empty((feature.shape[0], 19, 19, NUM_PLANES), np.int8)
-        if self._lib.ug_transform_planes(self._h, feature.ctypes.data, feature.shape[0], out.ctypes.data) != 0:
-            raise RuntimeError(self._err())
-        return out
-
     def set_debug_stop(self, layer):
         self._lib.ug_eval_set_debug_stop(self._h, layer)
 
