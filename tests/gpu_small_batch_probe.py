@@ -29,6 +29,8 @@ def main():
     variants = (("v2", 0, 0), ("sb", 128, 0), ("single", 128, 256), ("pair", 128, 512), ("pair32", 128, 512 + 32),
                 ("pair64", 128, 512 + 64), ("pair128", 128, 512 + 128)) if "--pairs" in sys.argv else \
                (("v2", 0, 0), ("sb", 128, 0), ("sb16", 128, 16), ("sb32", 128, 32), ("sb64", 128, 64), ("sb128", 128, 128))
+    if "--auto" in sys.argv:
+        sizes, variants = (1, 2, 4, 6, 8, 12, 14, 16, 20, 24, 26), (("v2", 0, 0), ("sb", 128, 0))
     for n in sizes:
         row = {}
         for name, sb, nt in variants:

@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 
 ALL = [(r, s) for r in range(3) for s in range(3)]
 SINGLE, PAIR = 256, 512   # added to the tile width: force single-CTA / CTA-pair tiles (otherwise chosen from the batch)
+DIRECT = 1024             # raw entry only: per-thread global stores even for tiles of 64+ columns (else TMA stores)
 
 
 def _run(*a, **k):
@@ -49,6 +50,11 @@ def test_single_tap_exact_padding(tap, nt):
     (24, 256, 256, False, False, PAIR),
     (16, 256, 256, True, True, SINGLE + 128),
     (3, 64, 64, False, False, SINGLE),
+    # wide tiles with per-thread stores (the default for them is staged TMA stores)
+    (16, 256, 256, True, True, SINGLE + 128 + DIRECT),
+    (5, 256, 256, True, True, PAIR + 64 + DIRECT),
+    (9, 192, 192, False, False, 64 + DIRECT),
+    (3, 128, 128, True, False, PAIR + 128),   # 9 tiles: the last pair's second tile is past M, TMA stores skip it
 ])
 def test_conv_sb_matches_fp32(n, cin, cout, residual, out_lo, nt, f16):
     _run(n, cin, cout, ALL, 0, residual, out_lo, f16=f16, seed=n + cin + cout, split_res=out_lo, nt=nt)

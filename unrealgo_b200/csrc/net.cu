@@ -601,7 +601,8 @@ int ug_eval::enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, con
   a.bias = W.convs[0].bias_tc.as<float>();
   a.out_hi = d_s_hi[0].p;
   a.out_lo = split ? d_s_lo[0].p : nullptr;
-  cudaError_t e = conv3x3_sb_launch(v2_a_in, W.convs[0].tm_w_sb, a, 32, device, sms, s);
+  cudaError_t e = conv3x3_sb_launch(v2_a_in, W.convs[0].tm_w_sb, &v2_out_hi[0], split ? &v2_out_lo[0] : nullptr, a, 32,
+                                    device, sms, s);
   if (e != cudaSuccess) return fail(-1, std::string("stem conv launch (small batch): ") + cudaGetErrorString(e));
   a.cin = C;
   *final_act = d_s_hi[0].p;
@@ -614,7 +615,7 @@ int ug_eval::enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, con
     a.res_hi = a.res_lo = nullptr;
     a.out_hi = d_t.p;
     a.out_lo = nullptr;
-    e = conv3x3_sb_launch(v2_a_s[x], c1.tm_w_sb, a, 64, device, sms, s);
+    e = conv3x3_sb_launch(v2_a_s[x], c1.tm_w_sb, &v2_out_t, nullptr, a, 64, device, sms, s);
     if (e != cudaSuccess) return fail(-1, std::string("tower conv launch (small batch): ") + cudaGetErrorString(e));
     *final_act = d_t.p;
     *final_lo = nullptr;
@@ -651,7 +652,7 @@ int ug_eval::enqueue_tower_sb(int n, cudaStream_t s, const void** final_act, con
     a.res_lo = split ? d_s_lo[x].p : nullptr;
     a.out_hi = d_s_hi[y].p;
     a.out_lo = split ? d_s_lo[y].p : nullptr;
-    e = conv3x3_sb_launch(v2_a_t, c2.tm_w_sb, a, 64, device, sms, s);
+    e = conv3x3_sb_launch(v2_a_t, c2.tm_w_sb, &v2_out_hi[y], split ? &v2_out_lo[y] : nullptr, a, 64, device, sms, s);
     if (e != cudaSuccess) return fail(-1, std::string("tower conv launch (small batch): ") + cudaGetErrorString(e));
     *final_act = d_s_hi[y].p;
     *final_lo = split ? d_s_lo[y].p : nullptr;
@@ -1262,8 +1263,11 @@ int ug_k_conv3x3_sb(int device, const void* d_in, const void* d_w, const float* 
   std::string err;
   const int ck = (cin % 64 == 0) ? 64 : 32;
   CUtensorMap ta, tw;
+  CUtensorMap toh, tol;
   if (!make_tmap_rows(&ta, d_in, (long)n_alloc * UG_NUM_POINTS, cin, ck, 168, &err) ||
-      !make_tmap_weights(&tw, d_w, cout, 9 * cin, ck, 16, &err)) {
+      !make_tmap_weights(&tw, d_w, cout, 9 * cin, ck, 16, &err) ||
+      !make_tmap_rows(&toh, d_out_hi, (long)n_alloc * UG_NUM_POINTS, cout, 32, 32, &err) ||
+      (d_out_lo && !make_tmap_rows(&tol, d_out_lo, (long)n_alloc * UG_NUM_POINTS, cout, 32, 32, &err))) {
     g_create_error = err;
     return -2;
   }
@@ -1279,21 +1283,22 @@ int ug_k_conv3x3_sb(int device, const void* d_in, const void* d_w, const float* 
   a.relu = relu;
   a.f16 = f16;
   a.nt = nt & 0xff;
-  a.pair = (nt >> 8) - 1;  // as ug_eval_set_small_batch: +256 = single CTAs, +512 = CTA pairs, else the launcher chooses
+  a.pair = ((nt >> 8) & 3) - 1;  // as ug_eval_set_small_batch: +256 = single CTAs, +512 = CTA pairs, else the launcher chooses
+  a.tma_out = (nt & 1024) ? -1 : 1;   // +1024: per-thread stores even for wide tiles; else TMA stores from 64 columns
   a.pdl = pdl;
   cudaStream_t s = nullptr;
   cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  cudaError_t e = conv3x3_sb_launch(ta, tw, a, ck, device, prop.multiProcessorCount, s);
+  cudaError_t e = conv3x3_sb_launch(ta, tw, &toh, d_out_lo ? &tol : nullptr, a, ck, device, prop.multiProcessorCount, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e == cudaSuccess && iters > 0) {
     cudaEventRecord(e0, s);
     for (int i = 0; i < iters && e == cudaSuccess; ++i) {
       // time stamps: launch i writes its own [ctas][16] block (the caller sizes d_prof for iters x 148 CTAs)
       if (d_prof) a.prof = d_prof + (size_t)i * 148 * 16;
-      e = conv3x3_sb_launch(ta, tw, a, ck, device, prop.multiProcessorCount, s);
+      e = conv3x3_sb_launch(ta, tw, &toh, d_out_lo ? &tol : nullptr, a, ck, device, prop.multiProcessorCount, s);
     }
     cudaEventRecord(e1, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
