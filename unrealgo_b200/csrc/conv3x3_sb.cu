@@ -56,7 +56,7 @@ constexpr int kThreads = 256;
 constexpr int kTapsPerStage = 3;            // filter taps per weight stage
 constexpr int kMaxStages = 12;              // 3 per 64-channel chunk of a 256-channel layer
 constexpr int kBRing = 96 * 1024;
-constexpr int kPairMaxFewTiles = 6;          // auto mode: CTA pairs up to this many 128-row tiles (two positions) ...
+constexpr int kPairNarrowTiles = 6;           // CTA pairs: 32-column tiles up to this many 128-row tiles (two positions)
 constexpr int kStageHalf = 32 * 64;           // TMA-store staging: 32 rows x 64 B (one warp, 32 output channels)
 constexpr int kStageSlot = 2 * kStageHalf;    // hi + lo
 constexpr int kMaxEpiSteps = 4;             // 16-column steps per warp: NT = 128 -> 8 steps over two warp groups
@@ -532,10 +532,13 @@ bool conv3x3_sb_prepare(int device) { return upload_masks(device); }
 
 int conv3x3_sb_pick_nt(int M, int cout, int sms, int pair) {
   const int m_tiles = (M + kTileM - 1) / kTileM;
-  // the smallest tile width (largest grid) that still fits one wave; 16-column tiles only pay their 144 tiny MMAs
+  // The smallest tile width (largest grid) that still fits one wave.  16-column tiles only pay their 144 tiny MMAs
   // back when nothing else fills the machine, so 32 is the floor unless asked for explicitly (and a CTA pair stages
-  // nt / 2 weight rows per CTA in 16-row TMA boxes: 32 is its hard floor)
-  for (int nt = 32; nt <= 128; nt <<= 1)
+  // nt / 2 weight rows per CTA in 16-row TMA boxes: 32 is its hard floor).  CTA pairs: 32 columns only for one or two
+  // positions; from there 64-column tiles on half as many CTAs are as fast or faster (measured at n = 3, 4, 6: -1, -1,
+  // -4 %), every MMA re-reads its 128 x 16 A operand from shared memory, which narrow tiles amortise badly.
+  const int floor_nt = pair && m_tiles > kPairNarrowTiles ? 64 : 32;
+  for (int nt = floor_nt; nt <= 128; nt <<= 1)
     if (cout % nt == 0 && grid_ctas(m_tiles, cout, nt, pair != 0) <= sms) return nt;
   for (int nt = 128; nt >= (pair ? 32 : 16); nt >>= 1)
     if (cout % nt == 0) return nt;
@@ -543,19 +546,19 @@ int conv3x3_sb_pick_nt(int M, int cout, int sms, int pair) {
 }
 
 int conv3x3_sb_pick_pair(int M, int cout, int sms) {
-  // A CTA pair halves the weight bytes each SM pulls from L2 but spends two SMs per 256 rows even when the second
-  // tile is mostly (or wholly) past M.  Measured on the 20x256 net (tests/gpu_small_batch_probe.py
-  // --pairs): pairs win 5 % at one or two positions (few tiles: nothing else wants the SMs) and 5-9 % from the batch
-  // size at which single-CTA tiles have to be 128 columns wide (n >= 14 for 256 filters); in between single CTAs at
-  // 32 / 64 columns are 1-6 % faster.
+  // A CTA pair halves the weight bytes each SM pulls from L2 and the shared-memory operand reads per MMA row.  Measured
+  // on the 20x256 net (tests/gpu_small_batch_probe.py --pairs) against single CTAs at their best width:
+  // -11 % at one or two positions, -13 % from the batch size at which single-CTA tiles have to be 128 columns wide
+  // (n >= 14 for 256 filters), within +-1 % in between (-4 % at n = 6): pairs whenever the channel count allows.
+  (void)M;
+  (void)sms;
   static const int force = [] {
-    const char* e = getenv("UGEVAL_SB_PAIR_MIN_TILES");   // experiments: pairs from this many tiles up, whatever else
+    const char* e = getenv("UGEVAL_SB_PAIR_MIN_TILES");   // experiments: pairs from this many tiles up only
     return e ? atoi(e) : 0;
   }();
   if (cout % 32 != 0) return 0;
-  const int m_tiles = (M + kTileM - 1) / kTileM;
-  if (force > 0) return m_tiles >= force ? 1 : 0;
-  return m_tiles <= kPairMaxFewTiles || conv3x3_sb_pick_nt(M, cout, sms, 0) >= 128 ? 1 : 0;
+  if (force > 0) return (M + kTileM - 1) / kTileM >= force ? 1 : 0;
+  return 1;
 }
 
 cudaError_t conv3x3_sb_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap* tmOhi,
