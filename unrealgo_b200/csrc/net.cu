@@ -406,6 +406,12 @@ bool ug_eval::ensure_workspace(int C) {
       last_error = "cannot allocate pinned staging memory";
       return false;
     }
+    void* alias = nullptr;
+    const char* zc = getenv("UGEVAL_ZERO_COPY_OUT");
+    if (!(zc && zc[0] == '0') && cudaHostGetDevicePointer(&alias, h_pinned, 0) == cudaSuccess)
+      d_pinned_alias = static_cast<uint8_t*>(alias);
+    else
+      cudaGetLastError();
   }
   ws_C = C;
   return true;
@@ -1028,9 +1034,15 @@ static int run_planes_common(ug_eval* h, const int8_t* planes, int hwc, int n, d
     memcpy(stage, planes, in_bytes);
     cudaMemcpyAsync(h->d_planes.p, stage, in_bytes, cudaMemcpyHostToDevice, s);
   }
+  // At the reference engine's own batch sizes the head kernel writes its 363 floats per position straight into the
+  // pinned staging area (posted writes over PCIe) instead of two device-to-host copies being queued behind it: two
+  // API calls and two copy-engine start-ups less per Evaluate() (measured at n = 1: see DESIGN.md 5b).
+  const bool zero_copy_out = n <= 32 && h->d_pinned_alias != nullptr;
+  float* d_pol = zero_copy_out ? reinterpret_cast<float*>(h->d_pinned_alias + (reinterpret_cast<uint8_t*>(out_stage) - stage))
+                               : h->d_policy.as<float>();
+  float* d_val = zero_copy_out ? d_pol + pol_count : h->d_value.as<float>();
   // value_transform is applied in double after widening, exactly as the reference does (.cc:298-310)
-  int rc = h->enqueue(hwc ? ug_eval::SRC_HWC : ug_eval::SRC_CHW, h->d_planes.p, n, nullptr, UG_TR_IDENTITY,
-                      h->d_policy.as<float>(), h->d_value.as<float>(), s);
+  int rc = h->enqueue(hwc ? ug_eval::SRC_HWC : ug_eval::SRC_CHW, h->d_planes.p, n, nullptr, UG_TR_IDENTITY, d_pol, d_val, s);
   if (rc) return rc;
   // Registered outputs are worth it for large batches only (the widening kernel and two DMA writes of doubles replace
   // a host loop over n * 362 floats); at the reference engine's own batch sizes the extra launch costs more than the
@@ -1047,8 +1059,10 @@ static int run_planes_common(ug_eval* h, const int8_t* planes, int hwc, int n, d
     if (e != cudaSuccess) return h->fail(-1, std::string("Running model failed: ") + cudaGetErrorString(e));
     return 0;
   }
-  cudaMemcpyAsync(out_stage, h->d_policy.p, pol_count * 4, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(out_stage + pol_count, h->d_value.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s);
+  if (!zero_copy_out) {
+    cudaMemcpyAsync(out_stage, h->d_policy.p, pol_count * 4, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(out_stage + pol_count, h->d_value.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s);
+  }
   const cudaError_t e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return h->fail(-1, std::string("Running model failed: ") + cudaGetErrorString(e));
   for (size_t i = 0; i < pol_count; ++i) policy[i] = (double)out_stage[i];  // DlTensorUtil::GetValue
@@ -1115,12 +1129,16 @@ int ug_eval_run_packed(ug_eval* h, const ug_packed_pos* pos, int n, const uint32
     cudaMemcpyAsync(h->d_legal.p, stage + legal_off, (size_t)n * UG_MASK_WORDS * 4, cudaMemcpyHostToDevice, s);
     d_legal = h->d_legal.as<uint32_t>();
   }
-  int rc = h->enqueue(ug_eval::SRC_PACKED, h->d_pos.p, n, d_legal, h->value_transform, h->d_policy.as<float>(),
-                      h->d_value.as<float>(), s);
-  if (rc) return rc;
   float* out_stage = reinterpret_cast<float*>(stage + out_off);
-  cudaMemcpyAsync(out_stage, h->d_policy.p, (size_t)n * UG_NUM_MOVES * 4, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(out_stage + (size_t)n * UG_NUM_MOVES, h->d_value.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s);
+  const bool zero_copy_out = n <= 32 && h->d_pinned_alias != nullptr;   // as in run_planes_common
+  float* d_pol = zero_copy_out ? reinterpret_cast<float*>(h->d_pinned_alias + out_off) : h->d_policy.as<float>();
+  float* d_val = zero_copy_out ? d_pol + (size_t)n * UG_NUM_MOVES : h->d_value.as<float>();
+  int rc = h->enqueue(ug_eval::SRC_PACKED, h->d_pos.p, n, d_legal, h->value_transform, d_pol, d_val, s);
+  if (rc) return rc;
+  if (!zero_copy_out) {
+    cudaMemcpyAsync(out_stage, h->d_policy.p, (size_t)n * UG_NUM_MOVES * 4, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(out_stage + (size_t)n * UG_NUM_MOVES, h->d_value.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s);
+  }
   const cudaError_t e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return h->fail(-1, std::string("CUDA error: ") + cudaGetErrorString(e));
   memcpy(policy, out_stage, (size_t)n * UG_NUM_MOVES * 4);

@@ -127,6 +127,9 @@ struct ug_eval {
   // conv v2 maps over the same buffers: halo-tile loads, residual loads (hi/lo), staged stores (hi/lo)
   CUtensorMap v2_a_in, v2_a_s[2], v2_a_t, v2_res_hi[2], v2_res_lo[2], v2_out_hi[2], v2_out_lo[2], v2_out_t;
   void* h_pinned = nullptr;  // staging for host-buffer entry points
+  // Device-side alias of h_pinned (equal to it under unified addressing), or null: small batches let the head kernel
+  // write policy and value straight into the staging area instead of queueing two device-to-host copies behind it.
+  uint8_t* d_pinned_alias = nullptr;
   size_t h_pinned_bytes = 0;
 
   // cuda graphs keyed by (kind, n, legal?, ctas, pointers)
