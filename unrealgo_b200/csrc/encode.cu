@@ -25,12 +25,11 @@ __global__ void __launch_bounds__(256) encode_packed_nhwc_kernel(const ug_packed
                                                                  __nv_bfloat16* __restrict__ out, int n,
                                                                  uint32_t kOneBf16) {
   __shared__ uint32_t masks[2][UG_HISTORY][UG_MASK_WORDS];  // [0] = side to move, [1] = opponent
-  __shared__ uint32_t s_to_play;
   for (int p = blockIdx.x; p < n; p += gridDim.x) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(pos + p);
-    if (threadIdx.x == 0) s_to_play = src[2 * UG_HISTORY * UG_MASK_WORDS] & 1u;
-    __syncthreads();
-    const uint32_t tp = s_to_play;
+    // every thread fetches the to-play word itself (one broadcast load) together with its mask word: one global-memory
+    // round trip before the stores instead of two (the kernel is latency-bound: 784 bytes in per position)
+    const uint32_t tp = __ldg(src + 2 * UG_HISTORY * UG_MASK_WORDS) & 1u;
     if (threadIdx.x < 2 * UG_HISTORY * UG_MASK_WORDS) {
       // source order: black[8][12] then white[8][12]; colour c goes to slot (c ^ to_play)
       const int colour = threadIdx.x / (UG_HISTORY * UG_MASK_WORDS);
@@ -64,12 +63,9 @@ __global__ void __launch_bounds__(256) encode_packed_nhwc_kernel(const ug_packed
 __global__ void __launch_bounds__(256) encode_packed_chw_kernel(const ug_packed_pos* __restrict__ pos,
                                                                 int8_t* __restrict__ out, int n) {
   __shared__ uint32_t masks[2][UG_HISTORY][UG_MASK_WORDS];
-  __shared__ uint32_t s_to_play;
   for (int p = blockIdx.x; p < n; p += gridDim.x) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(pos + p);
-    if (threadIdx.x == 0) s_to_play = src[2 * UG_HISTORY * UG_MASK_WORDS] & 1u;
-    __syncthreads();
-    const uint32_t tp = s_to_play;
+    const uint32_t tp = __ldg(src + 2 * UG_HISTORY * UG_MASK_WORDS) & 1u;
     if (threadIdx.x < 2 * UG_HISTORY * UG_MASK_WORDS) {
       const int colour = threadIdx.x / (UG_HISTORY * UG_MASK_WORDS);
       const int rest = threadIdx.x - colour * (UG_HISTORY * UG_MASK_WORDS);
