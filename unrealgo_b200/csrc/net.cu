@@ -1036,7 +1036,7 @@ static int run_planes_common(ug_eval* h, const int8_t* planes, int hwc, int n, d
   }
   // At the reference engine's own batch sizes the head kernel writes its 363 floats per position straight into the
   // pinned staging area (posted writes over PCIe) instead of two device-to-host copies being queued behind it: two
-  // API calls and two copy-engine start-ups less per Evaluate() (measured at n = 1: see DESIGN.md 5b).
+  // API calls and two copy-engine start-ups less per Evaluate() (measured at n = 1: see DESIGN.md 5a).
   const bool zero_copy_out = n <= 32 && h->d_pinned_alias != nullptr;
   float* d_pol = zero_copy_out ? reinterpret_cast<float*>(h->d_pinned_alias + (reinterpret_cast<uint8_t*>(out_stage) - stage))
                                : h->d_policy.as<float>();
