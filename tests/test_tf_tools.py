@@ -42,6 +42,15 @@ def test_subgraph_description_answers_the_surveys_unknowns():
     assert "save/restore_all" not in info["ops"] and info["nodes_on_path"] < len(meta.graph_def.node)
 
 
+def test_dump_script_side_feeds():
+    mod = _load("tf_dump_reference")
+    assert mod.parse_feeds(["training=false", "keep_prob:0=1.0", "k=3"]) == {"training:0": False, "keep_prob:0": 1.0, "k:0": 3}
+    assert mod.parse_feeds([]) == {} and mod.parse_feeds(None) == {}
+    import pytest
+    with pytest.raises(SystemExit):
+        mod.parse_feeds(["training"])
+
+
 def test_dump_script_needs_tensorflow_and_says_so(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tf_dump_reference.py"), "--meta", "x.meta", "--ckpt", "x",
                         "--positions", "p.npz", "--out", str(tmp_path / "o.npz")], capture_output=True, text=True)

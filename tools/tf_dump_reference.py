@@ -16,6 +16,8 @@ libugeval against.
 
     python tools/tf_dump_reference.py --meta bootstrap-ckpt.meta --ckpt bootstrap-ckpt \\
         --positions tests/golden/positions_64.npz --out tf_reference.npz [--dlcfg config/dlcfg-19] [--fetch NODE ...]
+        [--feed training=false ...]     (a plain `Placeholder` training switch has to be fed; the engine itself feeds
+                                         nothing but nn_input, so a graph that needs this cannot run in the reference)
 """
 import argparse
 import collections
@@ -38,6 +40,25 @@ def read_dlcfg(path):
             k, v = line.split("=", 1)
             cfg[k.strip()] = v.strip()
     return cfg
+
+
+def parse_feeds(items):
+    """--feed NAME=VALUE ... -> {tensor name: python scalar}; true/false -> bool, otherwise int, then float"""
+    feeds = {}
+    for item in items or []:
+        if "=" not in item:
+            raise SystemExit(f"--feed expects NAME=VALUE, got {item!r}")
+        name, value = item.split("=", 1)
+        low = value.strip().lower()
+        if low in ("true", "false"):
+            v = low == "true"
+        else:
+            try:
+                v = int(low)
+            except ValueError:
+                v = float(low)
+        feeds[name if ":" in name else name + ":0"] = v
+    return feeds
 
 
 def describe_inference_subgraph(graph_def, input_name, outputs):
@@ -69,7 +90,9 @@ def main():
     ap.add_argument("--dlcfg", help="take nn_input / nn_outputs / value_transform from this dlcfg file")
     ap.add_argument("--batch", type=int, default=16, help="positions per Session::Run (MAX_BATCHES in the reference)")
     ap.add_argument("--fetch", nargs="*", default=[], help="extra tensors to dump (localises a mismatch)")
+    ap.add_argument("--feed", nargs="*", default=[], help="NAME=VALUE scalars fed beside nn_input (e.g. training=false)")
     args = ap.parse_args()
+    extra_feeds = parse_feeds(args.feed)
 
     import tensorflow as tf
     tf1 = tf.compat.v1
@@ -104,8 +127,14 @@ def main():
     fetches = [graph.get_tensor_by_name(o + ":0") for o in outputs] + \
               [graph.get_tensor_by_name(f if ":" in f else f + ":0") for f in args.fetch]
     pol, val, extra = [], [], [[] for _ in args.fetch]
+    info = describe_inference_subgraph(meta_graph.graph_def, input_name, outputs)
+    unfed = [p for p, op in info["placeholders"].items() if op == "Placeholder" and p != input_name and p + ":0" not in extra_feeds]
+    if unfed:
+        print(f"note: the inference sub-graph has plain placeholders besides {input_name}: {unfed} — feed them with --feed "
+              "(the reference engine cannot: it feeds nn_input only, DlTFNetworkEvaluator.cc:295)", file=sys.stderr)
+    side = {graph.get_tensor_by_name(k): v for k, v in extra_feeds.items()}
     for lo in range(0, n, args.batch):
-        out = sess.run(fetches, feed_dict={x: feed_arr[lo:lo + args.batch]})
+        out = sess.run(fetches, feed_dict={x: feed_arr[lo:lo + args.batch], **side})
         pol.append(np.asarray(out[0], np.float32).reshape(-1, 362))
         val.append(np.asarray(out[1], np.float32).reshape(-1))
         for k in range(len(args.fetch)):
@@ -113,8 +142,7 @@ def main():
     pol, val = np.concatenate(pol), np.concatenate(val)
     v64 = val.astype(np.float64)                              # DlTensorUtil::GetValue widening, then .cc:300-310
     v64 = -v64 if vt == 1 else (1 - v64 if vt == 2 else v64)
-    info = describe_inference_subgraph(meta_graph.graph_def, input_name, outputs)
-    info.update({"producer": "tensorflow", "tensorflow_version": tf.__version__, "input": input_name, "outputs": outputs,
+    info.update({"producer": "tensorflow", "extra_feeds": {k: v for k, v in extra_feeds.items()}, "tensorflow_version": tf.__version__, "input": input_name, "outputs": outputs,
                  "input_dtype": x.dtype.name, "value_transform": vt, "positions": n, "batch": args.batch,
                  "policy_row_sums_minmax": [float(pol.sum(1).min()), float(pol.sum(1).max())],
                  "value_minmax": [float(val.min()), float(val.max())]})
