@@ -352,6 +352,12 @@ int ug_dlcfg_network_outputs(const ug_dlcfg* c, char* out, int cap, int max);
 int ug_inspect_model(const char* graph_path, const char* ckpt_prefix, const char* input, const char* policy_out,
                      const char* value_out, char* out, int cap);
 
+/* Host-only: one DT_FLOAT variable of a TF V2 checkpoint bundle through the same reader UpdateCheckPoint uses
+ * (.index SSTable walk, <prefix>.data-0000k-of-0000N shard files, masked crc32c per tensor).  Returns the element count
+ * and fills dims[0..*ndim) (up to 8); -1 = unreadable (reason in err), -2 = cap too small. */
+long long ug_bundle_read_float(const char* ckpt_prefix, const char* key, float* out, long long cap, long long* dims,
+                               int* ndim, char* err, int err_cap);
+
 /* library build info */
 const char* ug_version(void);
 /* CRC-32C (Castagnoli), the checksum of TF bundle entries; exported for the checkpoint tooling */

@@ -281,8 +281,10 @@ class _Block:
         return bytes(self.buf) + b"".join(struct.pack("<I", r) for r in self.restarts) + struct.pack("<I", len(self.restarts))
 
 
-def write_bundle(prefix, tensors, extra_entries=True, block_size=262144):
-    """TensorFlow's BundleWriter: data file = tensors in key order, back to back; index = SSTable of BundleEntryProto"""
+def write_bundle(prefix, tensors, extra_entries=True, block_size=262144, num_shards=1, endianness=0):
+    """TensorFlow's BundleWriter: data file = tensors in key order, back to back; index = SSTable of BundleEntryProto.
+    num_shards > 1: what Saver(sharded=True) leaves after MergeBundles — one merged index, the tensors spread over
+    <prefix>.data-0000k-of-0000N, every entry naming its shard"""
     items = {k: np.ascontiguousarray(v, "<f4") for k, v in tensors.items()}
     other = {}
     if extra_entries:
@@ -290,18 +292,24 @@ def write_bundle(prefix, tensors, extra_entries=True, block_size=262144):
         other["beta1_power"] = (P.DT_FLOAT, (), struct.pack("<f", 0.9))   # optimizer slot: a float the net does not use
     keys = sorted(list(items) + list(other))
     entries = []
-    with open(prefix + ".data-00000-of-00001", "wb") as df:
-        for k in keys:
-            if k in items:
-                dtype, shape, raw = P.DT_FLOAT, items[k].shape, items[k].tobytes()
-            else:
-                dtype, shape, raw = other[k]
-            e = P.BundleEntryProto(dtype=dtype, offset=df.tell(), size=len(raw), crc32c=_crc(raw))
-            for d in shape:
-                e.shape.dim.add().size = int(d)
-            df.write(raw)
-            entries.append((k.encode(), e.SerializeToString()))
-    header = P.BundleHeaderProto(num_shards=1)
+    files = [open(prefix + ".data-%05d-of-%05d" % (k, num_shards), "wb") for k in range(num_shards)]
+    for i, k in enumerate(keys):
+        if k in items:
+            dtype, shape, raw = P.DT_FLOAT, items[k].shape, items[k].tobytes()
+        else:
+            dtype, shape, raw = other[k]
+        shard = (i * 7) % num_shards
+        df = files[shard]
+        e = P.BundleEntryProto(dtype=dtype, offset=df.tell(), size=len(raw), crc32c=_crc(raw))
+        if shard:
+            e.shard_id = shard
+        for d in shape:
+            e.shape.dim.add().size = int(d)
+        df.write(raw)
+        entries.append((k.encode(), e.SerializeToString()))
+    for df in files:
+        df.close()
+    header = P.BundleHeaderProto(num_shards=num_shards, endianness=endianness)   # 0 = little, 1 = big
     header.version.producer = 1
     rows = [(b"", header.SerializeToString())] + entries
     with open(prefix + ".index", "wb") as f:
@@ -350,7 +358,7 @@ def random_weights(variables, seed):
     return out
 
 
-def write(directory, name="model.ckpt-123456", seed=7, small_blocks=False, **kw):
+def write(directory, name="model.ckpt-123456", seed=7, small_blocks=False, num_shards=1, **kw):
     """-> (meta path, checkpoint prefix)"""
     os.makedirs(directory, exist_ok=True)
     g, meta = build(**kw)
@@ -358,5 +366,6 @@ def write(directory, name="model.ckpt-123456", seed=7, small_blocks=False, **kw)
     with open(mpath, "wb") as f:
         f.write(meta.SerializeToString())
     prefix = os.path.join(directory, name)
-    write_bundle(prefix, random_weights(g.variables, seed), block_size=700 if small_blocks else 262144)
+    write_bundle(prefix, random_weights(g.variables, seed), block_size=700 if small_blocks else 262144,
+                 num_shards=num_shards)
     return mpath, prefix

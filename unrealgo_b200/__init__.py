@@ -6,4 +6,4 @@ the tests and bench.py.  No CPU fallback exists anywhere in this package.
 """
 from ._lib import PREC_BF16, PREC_FP16, PREC_FP32, TR_FLIP_PROB, TR_FLIP_SIGN, TR_IDENTITY  # noqa: F401
 from .evaluator import (DF_CHW, DF_HWC, DlConfig, DlTFNetworkEvaluator, DlTFRecordWriter, LeafQueue, ProductBoard,  # noqa: F401
-                        UctBoardEvaluator, inspect_model, pack_planes, selfplay)
+                        UctBoardEvaluator, bundle_read_float, inspect_model, pack_planes, selfplay)

@@ -142,6 +142,8 @@ SIGNATURES = {
     "ug_dlcfg_reuse_search_tree": (C.c_int, [C.c_void_p]),
     "ug_dlcfg_network_outputs": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "ug_inspect_model": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+    "ug_bundle_read_float": (C.c_longlong, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                                            C.c_char_p, C.c_int]),
     "ug_version": (C.c_char_p, []),
     "ug_crc32c": (C.c_uint32, [C.c_void_p, C.c_size_t]),
 }

@@ -97,3 +97,23 @@ extern "C" int ug_inspect_model(const char* graph_path, const char* ckpt_prefix,
   emit(o.str(), out, cap);
   return 0;
 }
+
+// One DT_FLOAT tensor of a checkpoint bundle through the product's reader (SSTable index walk, shard files, masked
+// crc32c): the CPU test-suite compares it value for value with what the writers stored.  Returns the element count
+// (and up to 8 dims), -1 with the reason in err when the bundle or the variable cannot be read, -2 when cap is too small.
+extern "C" long long ug_bundle_read_float(const char* ckpt_prefix, const char* key, float* out, long long cap,
+                                          long long* dims, int* ndim, char* err_out, int err_cap) {
+  std::string err;
+  TfBundle ck;
+  std::vector<float> v;
+  std::vector<int64_t> shape;
+  if (!ckpt_prefix || !key || !ck.open(ckpt_prefix, &err) || !ck.read_float(key, &v, &shape, &err)) {
+    emit(err.empty() ? "bad arguments" : err, err_out, err_cap);
+    return -1;
+  }
+  if (ndim) *ndim = (int)shape.size();
+  if (dims) for (size_t i = 0; i < shape.size() && i < 8; ++i) dims[i] = (long long)shape[i];
+  if ((long long)v.size() > cap || (!out && !v.empty())) return -2;
+  if (!v.empty()) memcpy(out, v.data(), v.size() * sizeof(float));
+  return (long long)v.size();
+}

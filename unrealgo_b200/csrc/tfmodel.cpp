@@ -586,7 +586,8 @@ bool parse_entry(const uint8_t* p, size_t n, BundleEntry* e) {
 
 bool TfBundle::open(const std::string& prefix, std::string* err) {
   entries_.clear();
-  data_.clear();
+  shards_.clear();
+  int num_shards = 1;
   std::vector<uint8_t> idx;
   if (!read_file(prefix + ".index", &idx)) { *err = "cannot read " + prefix + ".index"; return false; }
   if (idx.size() < 48) { *err = "index file too small"; return false; }
@@ -602,7 +603,15 @@ bool TfBundle::open(const std::string& prefix, std::string* err) {
     BlockHandle dh;
     if (!parse_handle(q, v + vn, &dh)) { *err = "bad data block handle"; return false; }
     return block_entries(idx, dh, [&](const std::string& key, const uint8_t* ev, size_t en) {
-      if (key.empty()) return true;  // BundleHeaderProto
+      if (key.empty()) {  // BundleHeaderProto: num_shards = 1, endianness = 2 (0 = little), version = 3
+        PbReader r(ev, en);
+        PbField f;
+        while (r.next(&f)) {
+          if (f.number == 1 && f.wire == 0) num_shards = (int)f.value;
+          if (f.number == 2 && f.wire == 0 && f.value != 0) { *err = "big-endian checkpoint bundles are not supported"; return false; }
+        }
+        return true;
+      }
       BundleEntry e;
       if (!parse_entry(ev, en, &e)) { *err = "malformed BundleEntryProto for " + key; return false; }
       entries_[key] = e;
@@ -610,9 +619,17 @@ bool TfBundle::open(const std::string& prefix, std::string* err) {
     }, err);
   }, err);
   if (!ok) return false;
-  if (!read_file(prefix + ".data-00000-of-00001", &data_)) {
-    *err = "cannot read " + prefix + ".data-00000-of-00001";
-    return false;
+  if (num_shards < 1 || num_shards > 4096) { *err = "implausible shard count in " + prefix + ".index"; return false; }
+  // a Saver(sharded=True) spreads the tensors over <prefix>.data-0000k-of-0000N; the usual case is N = 1
+  shards_.resize((size_t)num_shards);
+  for (int k = 0; k < num_shards; ++k) {
+    char suffix[40];
+    snprintf(suffix, sizeof suffix, ".data-%05d-of-%05d", k, num_shards);
+    if (!read_file(prefix + suffix, &shards_[(size_t)k])) {
+      *err = "cannot read " + prefix + suffix;
+      shards_.clear();
+      return false;
+    }
   }
   return true;
 }
@@ -627,14 +644,18 @@ bool TfBundle::read_float(const std::string& key, std::vector<float>* out, std::
   const BundleEntry* e = find(key);
   if (!e) { *err = "variable '" + key + "' not in checkpoint"; return false; }
   if (e->dtype != 1) { *err = "variable '" + key + "' is not DT_FLOAT"; return false; }
-  if (e->shard != 0) { *err = "variable '" + key + "' lives in shard " + std::to_string(e->shard) + " (single-shard bundles only)"; return false; }
-  int64_t count = 1;
-  for (int64_t d : e->shape) count *= d;
-  if (e->size != count * 4 || e->offset < 0 || (uint64_t)(e->offset + e->size) > data_.size()) {
-    *err = "variable '" + key + "' has inconsistent size/offset";
+  if (e->shard < 0 || e->shard >= (int)shards_.size()) {
+    *err = "variable '" + key + "' lives in shard " + std::to_string(e->shard) + " of " + std::to_string(shards_.size());
     return false;
   }
-  const uint8_t* src = data_.data() + e->offset;
+  const std::vector<uint8_t>& data = shards_[(size_t)e->shard];
+  int64_t count = 1;
+  for (int64_t d : e->shape) count *= d;
+  if (e->size != count * 4 || e->offset < 0 || (uint64_t)(e->offset + e->size) > data.size()) {
+    *err = "variable '" + key + "' has inconsistent size/offset (a partitioned variable is stored as slices: not supported)";
+    return false;
+  }
+  const uint8_t* src = data.data() + e->offset;
   if (e->has_crc && crc32c_mask(crc32c(src, (size_t)e->size)) != e->crc32c) {
     *err = "variable '" + key + "' fails its crc32c check";
     return false;

@@ -102,9 +102,10 @@ class TfBundle {
   bool read_float(const std::string& key, std::vector<float>* out, std::vector<int64_t>* shape,
                   std::string* err) const;
   const std::map<std::string, BundleEntry>& entries() const { return entries_; }
+  int num_shards() const { return (int)shards_.size(); }
  private:
   std::map<std::string, BundleEntry> entries_;
-  std::vector<uint8_t> data_;
+  std::vector<std::vector<uint8_t>> shards_;   // <prefix>.data-0000k-of-0000N, N = BundleHeaderProto.num_shards
 };
 
 uint32_t crc32c(const uint8_t* p, size_t n);

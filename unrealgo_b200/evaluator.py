@@ -72,6 +72,24 @@ def inspect_model(graph_path, ckpt_prefix=None, input_name=None, outputs=None):
     return json.loads(buf.value.decode())
 
 
+def bundle_read_float(ckpt_prefix, key):
+    """host-only: one DT_FLOAT variable of a TF V2 checkpoint bundle through the product's reader -> float32 array
+    (shaped as stored); raises RuntimeError with the reader's message"""
+    lib = _lib.load()
+    dims = (C.c_longlong * 8)()
+    ndim = C.c_int(0)
+    err = C.create_string_buffer(1024)
+    n = lib.ug_bundle_read_float(ckpt_prefix.encode(), key.encode(), None, 0, dims, C.byref(ndim), err, len(err))
+    if n == -1:
+        raise RuntimeError(err.value.decode())
+    shape = tuple(int(dims[i]) for i in range(ndim.value))
+    out = np.empty(int(np.prod(shape, dtype=np.int64)) if shape else 1, np.float32)
+    n = lib.ug_bundle_read_float(ckpt_prefix.encode(), key.encode(), out.ctypes.data, out.size, dims, C.byref(ndim), err, len(err))
+    if n < 0:
+        raise RuntimeError(err.value.decode() or f"ug_bundle_read_float returned {n}")
+    return out[:n].reshape(shape)
+
+
 class DlTFNetworkEvaluator:
     """DlTFNetworkEvaluator<bool>: LoadGraph / UpdateCheckPoint / Evaluate, plus the native packed entry points."""
 
