@@ -219,36 +219,46 @@ def read_bundle(prefix, verify=True):
     _, pos = read_varint(footer, pos)
     ioff, pos = read_varint(footer, pos)
     isize, pos = read_varint(footer, pos)
-    data = np.memmap(prefix + ".data-00000-of-00001", dtype=np.uint8, mode="r")
-    out = {}
+    rows = []
+    num_shards = 1
     for _, handle in _block(idx, ioff, isize, verify):
         boff, p = read_varint(handle, 0)
         bsize, p = read_varint(handle, p)
         for key, val in _block(idx, boff, bsize, verify):
-            if not key:
+            if not key:   # BundleHeaderProto: num_shards = 1
+                for num, _, v in fields(val):
+                    if num == 1:
+                        num_shards = v
                 continue
-            dtype, shape, offset, size, crc = 0, [], 0, 0, None
-            for num, _, v in fields(val):
-                if num == 1:
-                    dtype = v
-                elif num == 2:
-                    for n2, _, v2 in fields(v):
-                        if n2 == 2:
-                            d = 0
-                            for n3, _, v3 in fields(v2):
-                                if n3 == 1:
-                                    d = v3
-                            shape.append(d)
-                elif num == 4:
-                    offset = v
-                elif num == 5:
-                    size = v
-                elif num == 6:
-                    crc = v
-            if dtype != 1:
-                continue
-            raw = bytes(data[offset:offset + size])
-            if verify and crc is not None and _mask(_crc32c(raw)) != crc:
-                raise ValueError(f"crc mismatch for {key!r}")
-            out[key.decode()] = np.frombuffer(raw, "<f4").reshape(shape).copy()
+            rows.append((key, val))
+    # <prefix>.data-0000k-of-0000N (N > 1: a merged Saver(sharded=True) bundle)
+    shards = [np.memmap(prefix + ".data-%05d-of-%05d" % (k, num_shards), dtype=np.uint8, mode="r") for k in range(num_shards)]
+    out = {}
+    for key, val in rows:
+        dtype, shape, offset, size, crc, shard = 0, [], 0, 0, None, 0
+        for num, _, v in fields(val):
+            if num == 1:
+                dtype = v
+            elif num == 3:
+                shard = v
+            elif num == 2:
+                for n2, _, v2 in fields(v):
+                    if n2 == 2:
+                        d = 0
+                        for n3, _, v3 in fields(v2):
+                            if n3 == 1:
+                                d = v3
+                        shape.append(d)
+            elif num == 4:
+                offset = v
+            elif num == 5:
+                size = v
+            elif num == 6:
+                crc = v
+        if dtype != 1:
+            continue
+        raw = bytes(shards[shard][offset:offset + size])
+        if verify and crc is not None and _mask(_crc32c(raw)) != crc:
+            raise ValueError(f"crc mismatch for {key!r}")
+        out[key.decode()] = np.frombuffer(raw, "<f4").reshape(shape).copy()
     return out

@@ -36,7 +36,7 @@ def test_reader_returns_what_the_foreign_writer_stored(tmp_path, shards, block):
         bundle_read_float(prefix, "resnet/no_such/kernel")
 
 
-def test_sharded_bundle_loads_like_the_single_file_one(tmp_path):
+def test_sharded_bundle_loads_like_the_single_file_one(tmp_path, positions):
     """the whole loader (graph walk + every variable the plan needs) on a three-shard bundle"""
     one = FG.write(str(tmp_path / "one"), seed=3, bn="cond", filters=64)
     three = FG.write(str(tmp_path / "three"), seed=3, bn="cond", filters=64, num_shards=3)
@@ -44,6 +44,18 @@ def test_sharded_bundle_loads_like_the_single_file_one(tmp_path):
     assert a["checkpoint"] == b["checkpoint"] and a["tower"] == b["tower"]
     for key in (a["stem"]["kernel"], a["tower"][-1]["mean"], a["value_fc2"]["bias"]):
         assert np.array_equal(bundle_read_float(one[1], key), bundle_read_float(three[1], key))
+    # ... and so do the oracle's reader and both float oracles: same policy, same value
+    from oracle import tf_reader
+    from oracle.net_oracle import GraphOracle
+    from oracle.net_oracle_np import NumpyGraphOracle
+    r1, r3 = tf_reader.read_bundle(one[1]), tf_reader.read_bundle(three[1])
+    assert sorted(r1) == sorted(r3) and all(np.array_equal(r1[k], r3[k]) for k in r1)
+    _, planes = positions
+    p1 = GraphOracle(*one).evaluate_reference(planes[:3])
+    p3 = GraphOracle(*three).evaluate_reference(planes[:3])
+    q3 = NumpyGraphOracle(*three).evaluate_reference(planes[:3])
+    assert np.array_equal(p1[0], p3[0]) and np.array_equal(p1[1], p3[1])
+    assert np.abs(p3[0] - q3[0]).max() <= 2e-6 and np.abs(p3[1] - q3[1]).max() <= 5e-6
     os.remove(three[1] + ".data-00002-of-00003")
     with pytest.raises(RuntimeError, match="data-00002-of-00003"):
         inspect_model(*three)
