@@ -37,7 +37,8 @@ class GraphOracle:
     def __init__(self, graph_path, ckpt_prefix, input_name="feature_input",
                  outputs=("resnet/tower_0/policy_head/policy_predict", "resnet/tower_0/value_head/reward_predict")):
         self.nodes, self.saver = tf_reader.read_graph(graph_path)
-        self.vars = {k: torch.from_numpy(v) for k, v in tf_reader.read_bundle(ckpt_prefix).items()}
+        # ckpt_prefix None: a frozen graph (every variable folded into a Const node), nothing to restore
+        self.vars = {k: torch.from_numpy(v) for k, v in tf_reader.read_bundle(ckpt_prefix).items()} if ckpt_prefix else {}
         self.input_name = input_name
         self.outputs = list(outputs)
 

@@ -369,3 +369,29 @@ def write(directory, name="model.ckpt-123456", seed=7, small_blocks=False, num_s
     write_bundle(prefix, random_weights(g.variables, seed), block_size=700 if small_blocks else 262144,
                  num_shards=num_shards)
     return mpath, prefix
+
+
+def freeze(meta, weights):
+    """what tensorflow.python.tools.freeze_graph does to the inference graph: every variable becomes a float Const of
+    the same name holding its checkpoint value (the `read` Identity / ReadVariableOp consumers stay).  -> GraphDef"""
+    gd = P.GraphDef()
+    gd.CopyFrom(meta.graph_def)
+    for n in gd.node:
+        if n.op in ("VariableV2", "Variable", "VarHandleOp") and n.name in weights:
+            w = np.ascontiguousarray(weights[n.name], "<f4")
+            n.op = "Const"
+            n.ClearField("attr")
+            n.attr["dtype"].type = P.DT_FLOAT
+            t = n.attr["value"].tensor
+            t.dtype = P.DT_FLOAT
+            for d in w.shape:
+                t.tensor_shape.dim.add().size = int(d)
+            if w.size == 1:
+                t.float_val.append(float(w.reshape(-1)[0]))   # TensorFlow stores single values this way
+            else:
+                t.tensor_content = w.tobytes()
+        elif n.op == "ReadVariableOp":
+            n.op = "Identity"
+            n.ClearField("attr")
+            n.attr["T"].type = P.DT_FLOAT
+    return gd

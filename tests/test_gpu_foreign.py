@@ -38,3 +38,37 @@ def test_foreign_checkpoint_parity(tmp_path, positions, case):
             dp, dv = np.abs(p - want_p[:n]).max(), np.abs(v - want_v[:n]).max()
             assert dp <= ptol and dv <= vtol, (case, prec, n, dp, dv)
         ev.close()
+
+
+def test_frozen_graph_evaluates_straight_after_load_graph(tmp_path, positions):
+    """a graph run through freeze_graph (weights as Const nodes): the reference's session evaluates it after LoadPbGraph
+    alone and its UpdateCheckPointForPbGraph merely fails (funcapproximator/DlTFNetworkEvaluator.cc:85-111, :203-226).
+    Same here, and the answers are the bits the graph + checkpoint pair gives."""
+    from oracle.net_oracle_np import NumpyGraphOracle
+    from unrealgo_b200 import PREC_FP16, DlTFNetworkEvaluator
+    g, meta = FG.build(bn="v3", conv_bias=True, filters=128)
+    w = FG.random_weights(g.variables, 21)
+    prefix = str(tmp_path / "model.ckpt-9")
+    FG.write_bundle(prefix, w)
+    mpath = tmp_path / "model.ckpt-9.meta"
+    mpath.write_bytes(meta.SerializeToString())
+    frozen = tmp_path / "frozen.pb"
+    frozen.write_bytes(FG.freeze(meta, w).SerializeToString())
+    packed, planes = positions
+    want_p, want_v = NumpyGraphOracle(str(frozen), None).evaluate_reference(planes[:40])
+    ev = DlTFNetworkEvaluator(str(frozen), precision=PREC_FP16, max_batch=64)
+    assert ev.MetaGraphLoaded() and ev.info()["filters"] == 128          # weights are in: no UpdateCheckPoint needed
+    ref = DlTFNetworkEvaluator(str(mpath), precision=PREC_FP16, max_batch=64)
+    assert ref.UpdateCheckPoint(prefix), ref._err()
+    for n in (40, 3):
+        p, v = ev.evaluate_packed(packed[:n])
+        assert np.abs(p - want_p[:n]).max() <= 1e-3 and np.abs(v - want_v[:n]).max() <= 5e-3
+        p2, v2 = ref.evaluate_packed(packed[:n])
+        assert np.array_equal(p, p2) and np.array_equal(v, v2)
+    assert not ev.UpdateCheckPoint(prefix) and "frozen" in ev._err()     # nothing to restore; the evaluator stays usable
+    p3, v3 = ev.evaluate_packed(packed[:3])
+    assert np.array_equal(p3, p) and np.array_equal(v3, v)
+    pol, val = np.zeros((3, 362)), np.zeros(3)
+    assert ev.Evaluate(planes[:3], pol, val, 3) and np.array_equal(pol.astype(np.float32), p)
+    ev.close()
+    ref.close()

@@ -59,38 +59,28 @@ extern "C" int ug_inspect_model(const char* graph_path, const char* ckpt_prefix,
   o << ",\"policy_fc\":{\"kernel\":\"" << plan.policy_fc.kernel << "\",\"bias\":\"" << plan.policy_fc.bias << "\"}"
     << ",\"value_fc1\":{\"kernel\":\"" << plan.value_fc1.kernel << "\",\"bias\":\"" << plan.value_fc1.bias << "\"}"
     << ",\"value_fc2\":{\"kernel\":\"" << plan.value_fc2.kernel << "\",\"bias\":\"" << plan.value_fc2.bias << "\"}";
-  if (ckpt_prefix && ckpt_prefix[0]) {
+  o << ",\"const_weights\":" << plan.const_weights << ",\"frozen\":" << (plan.frozen ? "true" : "false");
+  const bool have_prefix = ckpt_prefix && ckpt_prefix[0];
+  if (have_prefix || plan.frozen) {
+    // a frozen graph carries every weight as a Const node: it is checked like a checkpoint, without one
     TfBundle ck;
-    if (!ck.open(ckpt_prefix, &err)) { emit(err, out, cap); return 2; }
-    std::vector<std::string> need;
-    auto add_conv = [&](const ConvPlan& c) {
-      need.push_back(c.kernel);
-      if (!c.bias.empty()) need.push_back(c.bias);
-      if (c.has_bn) {
-        if (!c.gamma.empty()) need.push_back(c.gamma);  // empty: a Const in the graph (scale=False)
-        if (!c.beta.empty()) need.push_back(c.beta);    // empty: a Const in the graph (center=False)
-        need.push_back(c.mean);
-        need.push_back(c.var);
-      }
-    };
-    add_conv(plan.stem);
-    for (const ConvPlan& c : plan.tower) add_conv(c);
-    add_conv(plan.policy_conv);
-    add_conv(plan.value_conv);
-    for (const DensePlan* d : {&plan.policy_fc, &plan.value_fc1, &plan.value_fc2}) {
-      need.push_back(d->kernel);
-      if (!d->bias.empty()) need.push_back(d->bias);
+    if (have_prefix && !ck.open(ckpt_prefix, &err)) {
+      if (!plan.frozen) { emit(err, out, cap); return 2; }
+      err.clear();   // nothing of a frozen graph lives in the checkpoint files
     }
+    if (!add_graph_constants(g, plan, &ck, &err)) { emit(err, out, cap); return 2; }
+    std::vector<std::string> need;
+    plan_variable_keys(plan, &need);
     size_t params = 0;
     std::vector<float> tmp;
-    std::vector<int64_t> shape;
+    std::vector<int64_t> shape, stem_shape;
     for (const std::string& k : need) {
       if (!ck.read_float(k, &tmp, &shape, &err)) { emit(err, out, cap); return 2; }
       params += tmp.size();
+      if (k == plan.stem.kernel) stem_shape = shape;
     }
-    const BundleEntry* stem = ck.find(plan.stem.kernel);
-    o << ",\"checkpoint\":{\"entries\":" << ck.entries().size() << ",\"variables_used\":" << need.size()
-      << ",\"parameters\":" << params << ",\"filters\":" << (stem && stem->shape.size() == 4 ? stem->shape[3] : 0)
+    o << ",\"checkpoint\":{\"entries\":" << ck.entries().size() + ck.memory_entries() << ",\"variables_used\":" << need.size()
+      << ",\"parameters\":" << params << ",\"filters\":" << (stem_shape.size() == 4 ? stem_shape[3] : 0)
       << "}";
   }
   o << "}";

@@ -807,6 +807,8 @@ static int rebuild_plan(ug_eval* h) {
   return 0;
 }
 
+static int install_weights(ug_eval* h, const TfBundle& ck, const std::string& label);
+
 int ug_eval_load_graph(ug_eval* h, const char* path) {
   if (!h) return -1;
   const std::string p = path ? path : "";
@@ -823,30 +825,32 @@ int ug_eval_load_graph(ug_eval* h, const char* path) {
   h->plan_ready = false;
   const int rc = rebuild_plan(h);
   if (rc) { h->graph_loaded = false; return rc; }
+  if (h->plan.frozen) {
+    // every weight is a Const node (a graph run through freeze_graph): evaluate straight after LoadGraph, as the
+    // reference's session does after LoadPbGraph (DlTFNetworkEvaluator.cc:85-111)
+    cudaSetDevice(h->device);
+    TfBundle consts;
+    if (!add_graph_constants(h->graph, h->plan, &consts, &err)) { h->graph_loaded = false; return h->fail(-1, "frozen graph " + p + ": " + err); }
+    if (install_weights(h, consts, "frozen graph " + p) != 0) { h->graph_loaded = false; return -1; }
+  }
   return 0;
 }
 
-int ug_eval_load_checkpoint(ug_eval* h, const char* prefix) {
-  if (!h) return 1;
-  if (prefix && prefix[0]) h->ckpt_prefix = prefix;
-  if (h->ckpt_prefix.empty()) return h->fail(1, "empty checkpoint path");
-  if (!h->graph_loaded) return h->fail(1, "UpdateCheckPoint before LoadGraph");
-  if (!h->plan_ready && rebuild_plan(h) != 0) return 1;
-  cudaSetDevice(h->device);
+// Weights from `ck` (a checkpoint bundle, or the Const nodes of a frozen graph) -> folded, packed, device-resident;
+// range calibration and the fp16 policy; swapped in between batches.  `label` names the source in messages.
+static int install_weights(ug_eval* h, const TfBundle& ck, const std::string& label) {
   std::string err;
-  TfBundle ck;
-  if (!ck.open(h->ckpt_prefix, &err)) return h->fail(1, err);
   int precision = h->precision_requested;
   Weights* W = build_weights(h->plan, ck, precision == UG_PREC_FP16, nullptr, &err);
-  if (!W) return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err);
-  if (!calibrate_range(h, W, &err)) { delete W; return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err); }
+  if (!W) return h->fail(1, label + ": " + err);
+  if (!calibrate_range(h, W, &err)) { delete W; return h->fail(1, label + ": " + err); }
   {
     const float worst = W->max_activation > W->max_weight ? W->max_activation : W->max_weight;
-    if (worst != worst) { delete W; return h->fail(1, "checkpoint " + h->ckpt_prefix + ": weights or calibration activations are NaN"); }
+    if (worst != worst) { delete W; return h->fail(1, label + ": weights or calibration activations are NaN"); }
     if (precision == UG_PREC_FP16 && worst > 65504.f / 8 && h->fp16_policy != 2) {
       char msg[512];
-      snprintf(msg, sizeof(msg), "checkpoint %s leaves fp16 less than 8x headroom (largest |activation| %.4g after layer %d, "
-               "largest |folded weight| %.4g in layer %d, fp16 saturates at 65504)", h->ckpt_prefix.c_str(),
+      snprintf(msg, sizeof(msg), "%s leaves fp16 less than 8x headroom (largest |activation| %.4g after layer %d, "
+               "largest |folded weight| %.4g in layer %d, fp16 saturates at 65504)", label.c_str(),
                (double)W->max_activation, W->max_activation_layer, (double)W->max_weight, W->max_weight_layer);
       if (h->fp16_policy == 1) { delete W; return h->fail(1, std::string(msg) + ": refused (UGEVAL_FP16_RANGE=refuse)"); }
       // auto-ranging: store every hot tensor times 2^-shift so that its calibrated maximum sits near 2^11 (32x headroom)
@@ -864,7 +868,7 @@ int ug_eval_load_checkpoint(ug_eval* h, const char* prefix) {
       W = nullptr;
       if (h->fp16_policy == 0) {
         W = build_weights(h->plan, ck, true, &shifts, &err);
-        if (!W) return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err);
+        if (!W) return h->fail(1, label + ": " + err);
         if (W->max_weight > 65504.f / 2 || !(W->max_weight == W->max_weight)) {  // rescaling cannot help the weights
           delete W;
           W = nullptr;
@@ -879,7 +883,7 @@ int ug_eval_load_checkpoint(ug_eval* h, const char* prefix) {
         fprintf(stderr, "ugeval: %s: evaluating with bf16 operands instead\n", msg);
         precision = UG_PREC_BF16;
         W = build_weights(h->plan, ck, false, nullptr, &err);
-        if (!W) return h->fail(1, "checkpoint " + h->ckpt_prefix + ": " + err);
+        if (!W) return h->fail(1, label + ": " + err);
       }
       if (W->stream_shift == 0) W->max_weight = mw;  // (rescaled weights keep the maximum of what was packed)
       W->layer_max = lm; W->max_activation = ma; W->max_activation_layer = la; W->max_weight_layer = lw;
@@ -904,6 +908,23 @@ int ug_eval_load_checkpoint(ug_eval* h, const char* prefix) {
   delete h->weights;
   h->weights = W;
   return 0;
+}
+
+int ug_eval_load_checkpoint(ug_eval* h, const char* prefix) {
+  if (!h) return 1;
+  if (prefix && prefix[0]) h->ckpt_prefix = prefix;
+  if (h->ckpt_prefix.empty()) return h->fail(1, "empty checkpoint path");
+  if (!h->graph_loaded) return h->fail(1, "UpdateCheckPoint before LoadGraph");
+  if (!h->plan_ready && rebuild_plan(h) != 0) return 1;
+  // A frozen graph has no restore op to run: the reference's UpdateCheckPointForPbGraph fails on it and the session
+  // goes on evaluating the constants (DlTFNetworkEvaluator.cc:203-226); so does this (the weights came with LoadGraph).
+  if (h->plan.frozen) return h->fail(1, "the graph is frozen (every weight is a constant): there is nothing to restore");
+  cudaSetDevice(h->device);
+  std::string err;
+  TfBundle ck;
+  if (!ck.open(h->ckpt_prefix, &err)) return h->fail(1, err);
+  if (h->plan.const_weights > 0 && !add_graph_constants(h->graph, h->plan, &ck, &err)) return h->fail(1, err);
+  return install_weights(h, ck, "checkpoint " + h->ckpt_prefix);
 }
 
 int ug_eval_ready(const ug_eval* h) { return h && h->graph_loaded ? 1 : 0; }

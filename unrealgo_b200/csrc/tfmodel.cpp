@@ -125,6 +125,7 @@ static void parse_tensor_proto(const uint8_t* p, size_t n, TfAttr* a) {
         int64_t size = 0;
         while (d.next(&df)) if (df.number == 1) size = (int64_t)df.value;
         elems *= size;
+        a->tensor_shape.push_back(size);
       }
     } else if (f.number == 4 && f.wire == 2) {
       vals.resize(f.size / 4);
@@ -322,6 +323,13 @@ struct Walker {
     for (int guard = 0; v && guard < 16; ++guard) {
       if (v->op == "VariableV2" || v->op == "Variable" || v->op == "VarHandleOp") { *key = v->name; return true; }
       if (v->op == "Identity" || v->op == "ReadVariableOp" || v->op == "Switch" || v->op == "Enter") { v = in(v, 0); continue; }
+      if (v->op == "Const") {  // a frozen graph: the variable has been folded into a float constant
+        auto it = v->attrs.find("value");
+        if (it == v->attrs.end() || !it->second.has_tensor || it->second.tensor_dtype != 1 || it->second.tensor_f.empty())
+          return fail("constant '" + v->name + "' is not a float tensor the loader can read");
+        *key = std::string(kConstKeyPrefix) + v->name;
+        return true;
+      }
       break;
     }
     return fail("expected a variable, found '" + (v ? v->name + "' (" + v->op + ")" : std::string("?'")));
@@ -507,6 +515,53 @@ bool build_net_plan(const TfGraph& g, const std::string& input, const std::strin
   }
   if (plan->input.empty()) { *err = "tower: did not reach the input placeholder"; return false; }
   plan->tower.assign(rev.rbegin(), rev.rend());
+  std::vector<std::string> keys;
+  plan_variable_keys(*plan, &keys);
+  const size_t plen = strlen(kConstKeyPrefix);
+  plan->const_weights = 0;
+  for (const std::string& k : keys) plan->const_weights += k.compare(0, plen, kConstKeyPrefix) == 0 ? 1 : 0;
+  plan->frozen = !keys.empty() && plan->const_weights == (int)keys.size();
+  return true;
+}
+
+const char* const kConstKeyPrefix = "@const:";
+
+void plan_variable_keys(const NetPlan& plan, std::vector<std::string>* keys) {
+  keys->clear();
+  auto add_conv = [&](const ConvPlan& c) {
+    keys->push_back(c.kernel);
+    if (!c.bias.empty()) keys->push_back(c.bias);
+    if (c.has_bn) {
+      if (!c.gamma.empty()) keys->push_back(c.gamma);  // empty: values carried in the plan (scale=False / frozen)
+      if (!c.beta.empty()) keys->push_back(c.beta);
+      keys->push_back(c.mean);
+      keys->push_back(c.var);
+    }
+  };
+  add_conv(plan.stem);
+  for (const ConvPlan& c : plan.tower) add_conv(c);
+  add_conv(plan.policy_conv);
+  add_conv(plan.value_conv);
+  for (const DensePlan* d : {&plan.policy_fc, &plan.value_fc1, &plan.value_fc2}) {
+    keys->push_back(d->kernel);
+    if (!d->bias.empty()) keys->push_back(d->bias);
+  }
+}
+
+bool add_graph_constants(const TfGraph& g, const NetPlan& plan, TfBundle* ck, std::string* err) {
+  std::vector<std::string> keys;
+  plan_variable_keys(plan, &keys);
+  const size_t plen = strlen(kConstKeyPrefix);
+  for (const std::string& k : keys) {
+    if (k.compare(0, plen, kConstKeyPrefix) != 0) continue;
+    const TfNode* n = g.find(k.substr(plen));
+    auto it = n ? n->attrs.find("value") : std::map<std::string, TfAttr>::const_iterator();
+    if (!n || it == n->attrs.end() || !it->second.has_tensor || it->second.tensor_dtype != 1) {
+      *err = "constant '" + k.substr(plen) + "' has no float tensor";
+      return false;
+    }
+    ck->add_memory(k, it->second.tensor_shape, it->second.tensor_f);
+  }
   return true;
 }
 
@@ -634,6 +689,12 @@ bool TfBundle::open(const std::string& prefix, std::string* err) {
   return true;
 }
 
+void TfBundle::add_memory(const std::string& key, const std::vector<int64_t>& shape, const std::vector<float>& values) {
+  MemTensor& t = mem_[key];
+  t.shape = shape;
+  t.values = values;
+}
+
 const BundleEntry* TfBundle::find(const std::string& key) const {
   auto it = entries_.find(key);
   return it == entries_.end() ? nullptr : &it->second;
@@ -641,6 +702,15 @@ const BundleEntry* TfBundle::find(const std::string& key) const {
 
 bool TfBundle::read_float(const std::string& key, std::vector<float>* out, std::vector<int64_t>* shape,
                           std::string* err) const {
+  auto mt = mem_.find(key);
+  if (mt != mem_.end()) {  // a Const node of the graph standing in for a variable
+    int64_t count = 1;
+    for (int64_t d : mt->second.shape) count *= d;
+    if (count != (int64_t)mt->second.values.size()) { *err = "constant '" + key + "' has an inconsistent shape"; return false; }
+    *out = mt->second.values;
+    if (shape) *shape = mt->second.shape;
+    return true;
+  }
   const BundleEntry* e = find(key);
   if (!e) { *err = "variable '" + key + "' not in checkpoint"; return false; }
   if (e->dtype != 1) { *err = "variable '" + key + "' is not DT_FLOAT"; return false; }

@@ -45,6 +45,7 @@ struct TfAttr {
   bool has_tensor = false;
   int tensor_dtype = 0;
   std::vector<float> tensor_f;
+  std::vector<int64_t> tensor_shape;   // dims as stored (empty: a scalar, or no shape given)
 };
 struct TfNode {
   std::string name, op;
@@ -81,7 +82,15 @@ struct NetPlan {
   ConvPlan policy_conv, value_conv;
   DensePlan policy_fc, value_fc1, value_fc2;
   bool policy_softmax = false, value_tanh = false;
+  // Weights that are Const nodes of the graph instead of variables (a graph run through freeze_graph): their "checkpoint
+  // key" is kConstKeyPrefix + node name.  frozen: every weight is one, so there is nothing to restore from a checkpoint
+  // (the reference's Session evaluates such a .pb straight after LoadPbGraph, DlTFNetworkEvaluator.cc:85-111).
+  int const_weights = 0;
+  bool frozen = false;
 };
+extern const char* const kConstKeyPrefix;   // "@const:"
+// every checkpoint key the plan needs, in a fixed order (stem, tower, head convs, FCs)
+void plan_variable_keys(const NetPlan& plan, std::vector<std::string>* keys);
 bool build_net_plan(const TfGraph& g, const std::string& input, const std::string& policy_out,
                     const std::string& value_out, NetPlan* plan, std::string* err);
 
@@ -103,10 +112,18 @@ class TfBundle {
                   std::string* err) const;
   const std::map<std::string, BundleEntry>& entries() const { return entries_; }
   int num_shards() const { return (int)shards_.size(); }
+  // a tensor held in memory under `key` (weights that are Const nodes of the graph); read_float serves it like a variable
+  void add_memory(const std::string& key, const std::vector<int64_t>& shape, const std::vector<float>& values);
+  size_t memory_entries() const { return mem_.size(); }
  private:
+  struct MemTensor { std::vector<int64_t> shape; std::vector<float> values; };
+  std::map<std::string, MemTensor> mem_;
   std::map<std::string, BundleEntry> entries_;
   std::vector<std::vector<uint8_t>> shards_;   // <prefix>.data-0000k-of-0000N, N = BundleHeaderProto.num_shards
 };
+
+// registers every kConstKeyPrefix key of the plan with the bundle, from the graph's Const nodes
+bool add_graph_constants(const TfGraph& g, const NetPlan& plan, TfBundle* ck, std::string* err);
 
 uint32_t crc32c(const uint8_t* p, size_t n);
 inline uint32_t crc32c_mask(uint32_t crc) { return ((crc >> 15) | (crc << 17)) + 0xa282ead8u; }
